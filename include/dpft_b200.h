@@ -1,0 +1,84 @@
+/*
+ * dpft_b200.h — C ABI of libdpft_b200.so, the sm_100a implementation of the DPFT (dprt) model hot path.
+ *
+ * Conventions (all entry points):
+ *   - plain pointers and sizes only; every tensor pointer is a DEVICE pointer unless the name says host;
+ *   - tensors are contiguous, row-major, in the layout the cited reference call site uses;
+ *   - the caller owns every buffer; nothing here allocates, frees or synchronises;
+ *   - work is enqueued on `stream` (a cudaStream_t passed as void*; NULL = legacy default stream);
+ *   - return 0 on success, a negative DPFT_ERR_* for argument errors, a positive cudaError_t value for
+ *     CUDA failures; dpft_last_error() gives the message for the calling thread;
+ *   - stateless and re-entrant (the only process state is the per-thread error string).
+ *
+ * Citations are into /root/reference (TUMFTM/DPFT); see INTEGRATION.md for the reference-side bindings.
+ */
+#ifndef DPFT_B200_H
+#define DPFT_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DPFT_ABI_VERSION 1
+
+#if defined(__GNUC__)
+#define DPFT_API __attribute__((visibility("default")))
+#else
+#define DPFT_API
+#endif
+
+/* element types (the `dtype` argument) */
+#define DPFT_F32 0
+#define DPFT_F64 1
+#define DPFT_F16 2
+#define DPFT_BF16 3
+
+/* error codes */
+#define DPFT_OK 0
+#define DPFT_ERR_INVALID_ARGUMENT (-1)
+#define DPFT_ERR_UNSUPPORTED (-2)
+
+DPFT_API int dpft_abi_version(void);
+DPFT_API const char* dpft_last_error(void);
+/* Fills sm_count / cc_major / cc_minor of `device`; returns a cudaError_t value if no usable GPU. */
+DPFT_API int dpft_device_info(int device, int* sm_count, int* cc_major, int* cc_minor);
+
+/*
+ * Multi-scale deformable attention, forward.
+ * Replaces MSDA.ms_deform_attn_forward(value, spatial_shapes, level_start_index, sampling_loc, attn_weight,
+ * im2col_step) — called at src/dprt/models/layers/ms_deform_attn.py:32-39 (im2col_step is a batching knob of
+ * the upstream kernel and has no effect on results; it is accepted by the Python binding and ignored).
+ *   value  (B, S, M, D)          dtype
+ *   shapes (L, 2) int64 device   [H_l, W_l]                     (ms_deform_attn.py:153-154)
+ *   lsi    (L,)   int64 device   level start index into S       (ms_deform_attn.py:155-156)
+ *   loc    (B, N, M, L, P, 2)    dtype, (x, y) normalised       (ms_deform_attn.py:185-191)
+ *   attn   (B, N, M, L, P)       dtype
+ *   out    (B, N, M*D)           dtype, fully overwritten
+ * Arithmetic: accumulate in f32 (f64 for DPFT_F64).  L <= 16.
+ */
+DPFT_API int dpft_msda_forward(const void* value, const int64_t* shapes, const int64_t* lsi, const void* loc,
+                      const void* attn, void* out, int B, int S, int M, int D, int N, int L, int P,
+                      int dtype, void* stream);
+
+/*
+ * Multi-scale deformable attention, backward.
+ * Replaces MSDA.ms_deform_attn_backward(value, spatial_shapes, level_start_index, sampling_loc, attn_weight,
+ * grad_output, im2col_step) -> (grad_value, grad_sampling_loc, grad_attn_weight) — called at
+ * src/dprt/models/layers/ms_deform_attn.py:58-66; the three results are returned at :68.
+ *   grad_out    (B, N, M*D)        dtype
+ *   grad_value  (B, S, M, D)       ACCUMULATION type: f32 for DPFT_F32/F16/BF16, f64 for DPFT_F64.
+ *                                  The caller zero-fills it; this call adds into it with red.global.add.
+ *   grad_loc    (B, N, M, L, P, 2) dtype, fully overwritten
+ *   grad_attn   (B, N, M, L, P)    dtype, fully overwritten
+ */
+DPFT_API int dpft_msda_backward(const void* value, const int64_t* shapes, const int64_t* lsi, const void* loc,
+                       const void* attn, const void* grad_out, void* grad_value, void* grad_loc,
+                       void* grad_attn, int B, int S, int M, int D, int N, int L, int P, int dtype,
+                       void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DPFT_B200_H */
