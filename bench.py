@@ -1,0 +1,311 @@
+#!/usr/bin/env python
+"""bench.py — frames/s of the DPRT hot path on B200 (BASELINE.json metric), one JSON line on rank 0.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--batch B]
+
+A "step" is one eval-mode forward of the full camera+radar fusion model (reference config kradar.json with the
+BASELINE cfg-3 query grid: 300 queries) over one synthetic batch of B=8 frames per GPU: 1280x720 camera plus
+256x256 range-azimuth and 256x256 elevation-azimuth radar projections.  N > 1 runs one replica per GPU
+(launched by torch.distributed.run) on its own batch shard — weak scaling, no data-path collective.
+
+  value   frames/s with the batch already resident in HBM (CUDA events, max over ranks, L2 flushed between steps)
+  e2e     frames/s through the public call model(batch) with HOST (pinned) input buffers: H2D of the batch and
+          D2H of the four outputs inside the timed region
+  roofline     the deformable-attention forward kernel on the step's own tensors (HBM bound)
+  cpu_baseline the CPU oracle port of the reference forward on the host cores (rank 0, N=1, bounded sample)
+
+--impl reference times the reference's CPU forward (the oracle port in oracle/dprt_oracle.py — the reference is
+pure Python and cannot travel to the GPU box) on the same workload, one bounded sample per step.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+WORKLOAD = "kradar.json full C+R fusion, eval forward, 300 queries, bs=8/GPU, 1280x720 camera + 256x256 RA + 256x256 EA"
+N_QUERIES = (20, 15, 1)
+METRIC, UNIT = "frames_per_sec", "frames/s"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch", type=int, default=8, help="frames per GPU per step")
+    ap.add_argument("--cpu-sample", type=int, default=1, help="frames per CPU-baseline forward")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--small", action="store_true", help="debug: tiny inputs (NOT a valid bench number)")
+    return ap.parse_args()
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            p = json.load(f)
+        return p["hbm_gbs"], p.get("bf16_tflops_sustained", p.get("bf16_tflops")), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, 1400.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled during the timed region (B200_PROFILING.md recipe)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.rows, self.proc, self.index = [], None, index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except OSError:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        sm, mx, reasons = [], None, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0]))
+                mx = float(r[1])
+                for n, v in zip(names, r[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(n)
+            except (ValueError, IndexError):
+                continue
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": mx, "samples": len(sm),
+                "reasons": sorted(reasons)}
+
+
+def build_case(args):
+    from dpft_b200 import configs, synthetic
+    cfg = synthetic.offline_config(configs.make_config("kradar"), n_queries=N_QUERIES)
+    sizes = dict(synthetic.BASELINE_SIZES)
+    if args.small:
+        sizes = {"camera_mono": (96, 160, 3), "radar_bev": (64, 64, 6), "radar_front": (64, 64, 6)}
+    return cfg, sizes
+
+
+def cpu_forward_fps(cfg, sizes, sd, frames, reps, seed=1234):
+    """Frames/s of the CPU oracle port of the reference forward (all host threads torch will use)."""
+    from dpft_b200 import synthetic
+    from oracle import dprt_oracle
+    batch = synthetic.synthetic_batch(cfg, frames, seed=seed, sizes=sizes)
+    with torch.no_grad():
+        dprt_oracle.forward(sd, cfg, batch)                   # warm-up
+        best = float("inf")
+        for _ in range(reps):
+            t = time.perf_counter()
+            dprt_oracle.forward(sd, cfg, batch)
+            best = min(best, time.perf_counter() - t)
+    return frames / best, best
+
+
+def run_reference(args):
+    """--impl reference: the reference's CPU forward (oracle port) on the same workload, rank 0 only."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from dpft_b200 import models, synthetic
+    cfg, sizes = build_case(args)
+    torch.set_num_threads(os.cpu_count())
+    sd = synthetic.seeded_state_dict(models.build("dprt", cfg).state_dict(), seed=1)
+    from oracle import dprt_oracle
+    frames = args.cpu_sample
+    batch = synthetic.synthetic_batch(cfg, frames, seed=1234, sizes=sizes)
+    times = []
+    with torch.no_grad():
+        for i in range(args.warmup + args.steps):
+            t = time.perf_counter()
+            dprt_oracle.forward(sd, cfg, batch)
+            if i >= args.warmup:
+                times.append(time.perf_counter() - t)
+    total = sum(times)
+    fps = frames * len(times) / total
+    sample = f"{frames} frame(s) per step of the same workload (full sizes), {len(times)} timed steps"
+    line = {"impl": "reference", "metric": METRIC, "value": fps, "unit": UNIT, "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / len(times),
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "frames_per_step": frames},
+            "cpu_baseline": {"value": fps, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
+                             "sample": sample, "host_cpus": os.cpu_count()},
+            "e2e": {"value": fps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+def msda_roofline(model, feats_flat, dev, hbm_peak, peak_src, reps=20):
+    """Times the deformable-attention forward kernel on tensors of the step's own shape (camera view: the largest
+    pyramid), L2 flushed between launches; algorithmic bytes per SURVEY.md §8d."""
+    from dpft_b200 import msda
+    flat, shapes_t, lsi_t = feats_flat
+    B, S, C = flat.shape
+    layer = model.fuser.mpfusion["fusion0"].ml_fusion_layers["ms_deform_attn0"].ms_deform_attn
+    M, L, P = layer.n_heads, layer.n_levels, layer.n_points
+    D = C // M
+    N = model.fuser.n_queries
+    g = torch.Generator(device=dev).manual_seed(0)
+    value = flat.view(B, S, M, D).contiguous()
+    loc = torch.rand(B, N, M, L, P, 2, generator=g, device=dev)
+    attn = torch.softmax(torch.randn(B, N, M, L * P, generator=g, device=dev), -1).view(B, N, M, L, P)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    for _ in range(3):
+        msda.ms_deform_attn_forward(value, shapes_t, lsi_t, loc, attn, 64)
+    ts = []
+    for _ in range(reps):
+        flush.zero_()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        msda.ms_deform_attn_forward(value, shapes_t, lsi_t, loc, attn, 64)
+        e1.record()
+        e1.synchronize()
+        ts.append(e0.elapsed_time(e1) * 1e-3)
+    t = statistics.mean(ts)
+    s = value.element_size()
+    alg = B * N * M * L * P * (4 * D + 3) * s + B * N * M * D * s
+    achieved = alg / t / 1e9
+    return {"kernel": "msda_fwd_kernel", "bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
+            "frac": achieved / hbm_peak, "traffic": None, "peak_source": peak_src,
+            "algorithmic_bytes_per_launch": alg, "us_per_launch": t * 1e6,
+            "shape": {"B": B, "N": N, "M": M, "D": D, "L": L, "P": P, "S": S, "dtype": str(value.dtype)}}
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        run_reference(args)
+        return
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    assert torch.cuda.is_available(), "bench.py needs a GPU (there is no CPU fallback)"
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+
+    from dpft_b200 import models, native, synthetic
+    cfg, sizes = build_case(args)
+    model = models.build("dprt", cfg).eval()
+    sd = synthetic.seeded_state_dict(model.state_dict(), seed=1)
+    model.load_state_dict(sd)
+    model = model.to(dev)
+
+    B = args.batch
+    host = synthetic.synthetic_batch(cfg, B, seed=1000 + rank, sizes=sizes)
+    host = {k: v.pin_memory() for k, v in host.items()}
+    resident = {k: v.to(dev) for k, v in host.items()}
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)       # > 126 MB L2
+    h2d_bytes = sum(v.numel() * v.element_size() for v in host.values())
+
+    def barrier():
+        if world > 1:
+            torch.distributed.barrier()
+        torch.cuda.synchronize()
+
+    def step_resident():
+        with torch.no_grad():
+            return model(resident)
+
+    out_host = None
+
+    def step_e2e():
+        nonlocal out_host
+        with torch.no_grad():
+            dev_batch = {k: v.to(dev, non_blocking=True) for k, v in host.items()}
+            out = model(dev_batch)
+            if out_host is None:
+                out_host = {k: torch.empty(v.shape, dtype=v.dtype).pin_memory() for k, v in out.items()}
+            for k, v in out.items():
+                out_host[k].copy_(v, non_blocking=True)
+        return out
+
+    def timed(step_fn, steps, warmup):
+        for _ in range(warmup):
+            step_fn()
+        barrier()
+        evs = []
+        for _ in range(steps):
+            flush.zero_()                                    # L2 flush between timed iterations (untimed)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            step_fn()
+            e1.record()
+            evs.append((e0, e1))
+        barrier()
+        total = sum(a.elapsed_time(b) for a, b in evs) * 1e-3
+        t = torch.tensor([total], device=dev, dtype=torch.float64)
+        if world > 1:
+            torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
+        return float(t.item())
+
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    l0 = native.launches()
+    t_res = timed(step_resident, args.steps, max(args.warmup, 3))
+    launches = native.launches() - l0
+    clocks = sampler.stop() if rank == 0 else None
+    t_e2e = timed(step_e2e, args.steps, 2)
+    d2h_bytes = sum(v.numel() * v.element_size() for v in out_host.values())
+
+    frames = B * world * args.steps
+    line = None
+    if rank == 0:
+        hbm_peak, _, peak_src = peaks()
+        # the deformable-attention kernel on the camera pyramid of this very workload
+        with torch.no_grad():
+            feats = model.extract_features(resident)
+            from dpft_b200.models.fuser import FeaturePyramid
+            pyr = FeaturePyramid.from_levels(feats[model.inputs[0]])
+            roof = msda_roofline(model, (pyr.flat, pyr.shapes_t, pyr.lsi_t), dev, hbm_peak, peak_src)
+            del feats, pyr
+        line = {"metric": METRIC, "value": frames / t_res, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+                "warmup": max(args.warmup, 3), "ms_per_step": 1e3 * t_res / args.steps, "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "config": {"workload": WORKLOAD, "frames_per_gpu": B, "l2": "flushed between timed steps (256 MiB write)",
+                           "sizes": {k: list(v) for k, v in sizes.items()}, "parallelism": f"replicas x{world}",
+                           "valid": not args.small},
+                "roofline": roof, "clocks": clocks,
+                "e2e": {"value": frames / t_e2e, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes,
+                        "d2h_bytes_per_step": d2h_bytes, "ms_per_step": 1e3 * t_e2e / args.steps},
+                "gpu_launches": launches}
+        if world == 1 and not args.no_cpu_baseline:
+            torch.set_num_threads(os.cpu_count())
+            fps, secs = cpu_forward_fps(cfg, sizes, sd, args.cpu_sample, reps=3)
+            line["cpu_baseline"] = {"value": fps, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
+                                    "host_cpus": os.cpu_count(),
+                                    "sample": f"{args.cpu_sample} frame(s) of the same workload, best of 3 after 1 warm-up "
+                                              f"({secs:.2f} s per forward)"}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        torch.distributed.barrier()
+        torch.distributed.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,108 @@
+"""DPRT model assembly (mirror of reference src/dprt/models/dprt.py): per-input backbone -> skip link (raw
+input as level '0') -> FPN neck -> sinusoidal embedding, then querent -> fuser(+heads).
+
+``DPRT.from_config(config)`` reads the same JSON keys as the reference (``config['computing']`` merged into
+every sub-module config, dprt.py:35) and ``forward(batch)`` takes / returns the same dictionaries
+(dprt.py:200-244).  In ``eval()`` on a CUDA device the forward runs through the fused sm_100a pipeline
+(dpft_b200/engine.py) when the configuration is eligible; otherwise module by module on the GPU with the
+deformable-attention op from libdpft_b200.so.
+"""
+from __future__ import annotations
+
+from collections import OrderedDict
+from typing import Any, Callable, Dict, List, Optional, Tuple
+
+import torch
+from torch import nn
+
+from .backbone import build_backbone
+from .embedding import build_embedding
+from .fuser import build_fuser
+from .head import build_head
+from .neck import build_neck
+from .querent import build_querent
+
+
+def _build(build_fn: Callable, section: Optional[Dict[str, Any]], computing: Dict[str, Any], **kwargs):
+    if section is None:
+        return None
+    return build_fn(section["name"], dict(computing | section), **kwargs)
+
+
+def _build_each(build_fn: Callable, sections: Optional[Dict[str, Any]], computing: Dict[str, Any]):
+    if sections is None:
+        return None
+    return {k: _build(build_fn, v, computing) for k, v in sections.items()}
+
+
+class DPRT(nn.Module):
+    def __init__(self, inputs: List[str], skiplinks: Dict[str, bool] = None, backbones: Dict[str, nn.Module] = None,
+                 necks: Dict[str, nn.Module] = None, embeddings: Dict[str, nn.Module] = None,
+                 querent: nn.Module = None, fuser: nn.Module = None, head: nn.Module = None, **kwargs):
+        super().__init__()
+        self.inputs = list(inputs)
+        skiplinks = skiplinks or {}
+        self.skiplinks = {i: bool(skiplinks.get(i, False)) for i in self.inputs}
+
+        def per_input(mods):
+            mods = mods or {}
+            return nn.ModuleDict({i: (mods.get(i) if mods.get(i) is not None else nn.Identity()) for i in self.inputs})
+
+        self.backbones = per_input(backbones)
+        self.necks = per_input(necks)
+        self.embeddings = per_input(embeddings)
+        self.querent = querent if querent is not None else nn.Identity()
+        self.fuser = fuser if fuser is not None else nn.Identity()
+        self.head = head if head is not None else nn.Identity()   # registered but unused, like the reference (dprt.py:112)
+        self.use_fused = True          # eval-mode fused pipeline switch (tests flip it to compare the two paths)
+        self._engine = None
+
+    @classmethod
+    def from_config(cls, config: Dict[str, Any]) -> "DPRT":
+        computing, model = config["computing"], config["model"]
+        head = _build(build_head, model.get("head"), computing)
+        fuser = _build(build_fuser, model.get("fuser"), computing, head=head)
+        return cls(inputs=model.get("inputs"), skiplinks=model.get("skiplinks"),
+                   backbones=_build_each(build_backbone, model.get("backbones"), computing),
+                   necks=_build_each(build_neck, model.get("necks"), computing),
+                   embeddings=_build_each(build_embedding, model.get("embeddings"), computing),
+                   querent=_build(build_querent, model.get("querent"), computing),
+                   fuser=fuser, head=head)
+
+    def __getstate__(self):            # torch.save(model) (reference trainer.py:258) must not pickle device caches
+        state = self.__dict__.copy()
+        state["_engine"] = None
+        return state
+
+    # -- composed (module by module) path -------------------------------------------------------------------
+    def extract_features(self, batch: Dict[str, torch.Tensor]) -> Dict[str, "OrderedDict[str, torch.Tensor]"]:
+        feats = {}
+        for name in self.inputs:
+            f = self.backbones[name](batch[name])
+            if self.skiplinks[name]:
+                f = OrderedDict([("0", batch[name])] + list(f.items()))
+            f = self.necks[name](f)
+            feats[name] = self.embeddings[name](f)
+        return feats
+
+    def forward_composed(self, batch: Dict[str, torch.Tensor]) -> "OrderedDict[str, torch.Tensor]":
+        feats = self.extract_features(batch)
+        out = self.querent(batch)
+        return self.fuser(batch=[feats[i] for i in self.inputs],
+                          shape=[batch[f"{i}_shape"][:, :2] for i in self.inputs],
+                          projection=[(batch[f"label_to_{i}_t"], batch[f"label_to_{i}_p"]) for i in self.inputs],
+                          out=out)
+
+    # -- dispatch -------------------------------------------------------------------------------------------
+    def forward(self, batch: Dict[str, torch.Tensor]) -> "OrderedDict[str, torch.Tensor]":
+        if self.use_fused and not self.training and not torch.is_grad_enabled():
+            from ..engine import FusedEngine
+            if self._engine is None:
+                self._engine = FusedEngine.try_create(self)
+            if self._engine is not None and self._engine.accepts(batch):
+                return self._engine.forward(batch)
+        return self.forward_composed(batch)
+
+
+def build_dprt(config: Dict[str, Any], *args, **kwargs) -> DPRT:
+    return DPRT.from_config(config)

@@ -76,11 +76,12 @@ def msda_forward_torch(value: torch.Tensor, shapes, loc: torch.Tensor, attn: tor
 
 def msda_backward_torch(value, shapes, loc, attn, grad_out):
     """Returns (grad_value, grad_loc, grad_attn) of ``msda_forward_torch`` through autograd."""
-    v = value.detach().clone().requires_grad_(True)
-    lo = loc.detach().clone().requires_grad_(True)
-    a = attn.detach().clone().requires_grad_(True)
-    out = msda_forward_torch(v, shapes, lo, a)
-    gv, gl, ga = torch.autograd.grad(out, (v, lo, a), grad_out)
+    with torch.enable_grad():  # callers may sit inside a once_differentiable backward
+        v = value.detach().clone().requires_grad_(True)
+        lo = loc.detach().clone().requires_grad_(True)
+        a = attn.detach().clone().requires_grad_(True)
+        out = msda_forward_torch(v, shapes, lo, a)
+        gv, gl, ga = torch.autograd.grad(out, (v, lo, a), grad_out)
     return gv, gl, ga
 
 
