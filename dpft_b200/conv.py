@@ -1,0 +1,74 @@
+"""Host side of the sm_100a convolution kernels: BatchNorm folding, weight re-layout, launch wrappers.
+
+Inference form of the torchvision ResNet blocks the reference runs (src/dprt/models/backbones/resnet.py:101):
+``conv -> BatchNorm2d(eval) [-> + identity] [-> ReLU]`` becomes one call of ``dpft_conv2d_nhwc_bf16`` with
+``w' = w * gamma / sqrt(var + eps)`` and ``bias' = beta - mean * gamma / sqrt(var + eps)``.
+"""
+from __future__ import annotations
+
+from typing import Optional, Tuple
+
+import torch
+from torch import nn
+
+from . import native
+
+
+def fold_conv_bn(conv: nn.Conv2d, bn: Optional[nn.Module]) -> Tuple[torch.Tensor, torch.Tensor]:
+    """Returns (weight (Cout, R, S, Cin) fp32, bias (Cout,) fp32) of conv followed by eval-mode BatchNorm."""
+    w = conv.weight.detach().float()
+    cout = w.shape[0]
+    b = conv.bias.detach().float() if conv.bias is not None else torch.zeros(cout, device=w.device)
+    if bn is not None:
+        scale = bn.weight.detach().float() / torch.sqrt(bn.running_var.detach().float() + bn.eps)
+        w = w * scale.view(-1, 1, 1, 1)
+        b = (b - bn.running_mean.detach().float()) * scale + bn.bias.detach().float()
+    return w.permute(0, 2, 3, 1).contiguous(), b.contiguous()
+
+
+class FoldedConv:
+    """One ``conv+bn`` of the backbone prepared for the tcgen05 kernel (weights bf16 [Cout,R,S,Cin], bias fp32)."""
+
+    def __init__(self, conv: nn.Conv2d, bn: Optional[nn.Module], device):
+        w, b = fold_conv_bn(conv, bn)
+        self.weight = w.to(device=device, dtype=torch.bfloat16).contiguous()
+        self.bias = b.to(device=device, dtype=torch.float32).contiguous()
+        self.cout, self.r, self.s, self.cin = self.weight.shape
+        self.stride = conv.stride[0]
+        self.pad = conv.padding[0]
+
+    def out_hw(self, h: int, w: int) -> Tuple[int, int]:
+        return ((h + 2 * self.pad - self.r) // self.stride + 1, (w + 2 * self.pad - self.s) // self.stride + 1)
+
+    def __call__(self, x: torch.Tensor, relu: bool, residual: Optional[torch.Tensor] = None,
+                 out: Optional[torch.Tensor] = None, block_n: int = 0) -> torch.Tensor:
+        return conv2d_nhwc_bf16(x, self.weight, self.bias, self.stride, self.pad, relu, residual, out, block_n)
+
+
+def conv2d_nhwc_bf16(x: torch.Tensor, weight: torch.Tensor, bias: torch.Tensor, stride: int, pad: int, relu: bool,
+                     residual: Optional[torch.Tensor] = None, out: Optional[torch.Tensor] = None,
+                     block_n: int = 0) -> torch.Tensor:
+    """x (B,H,W,Cin) bf16 contiguous, weight (Cout,R,S,Cin) bf16, bias (Cout,) fp32 -> (B,P,Q,Cout) bf16."""
+    native.require_cuda(x, weight, bias)
+    if x.dtype != torch.bfloat16 or weight.dtype != torch.bfloat16 or bias.dtype != torch.float32:
+        raise RuntimeError("conv2d_nhwc_bf16: x and weight must be bfloat16 and bias float32")
+    if not (x.is_contiguous() and weight.is_contiguous() and bias.is_contiguous()):
+        raise RuntimeError("conv2d_nhwc_bf16: tensors have to be contiguous")
+    B, H, W, Cin = x.shape
+    Cout, R, S, Cin_w = weight.shape
+    if Cin_w != Cin:
+        raise RuntimeError(f"conv2d_nhwc_bf16: weight expects {Cin_w} input channels, got {Cin}")
+    P, Q = (H + 2 * pad - R) // stride + 1, (W + 2 * pad - S) // stride + 1
+    if out is None:
+        out = torch.empty((B, P, Q, Cout), dtype=torch.bfloat16, device=x.device)
+    if residual is not None and (residual.shape != out.shape or not residual.is_contiguous()
+                                 or residual.dtype != torch.bfloat16):
+        raise RuntimeError("conv2d_nhwc_bf16: residual must be a contiguous bf16 tensor of the output shape")
+    lib = native.load_library()
+    with torch.cuda.device(x.device):
+        st = lib.dpft_conv2d_nhwc_bf16(native.ptr(x), native.ptr(weight), native.ptr(bias), native.ptr(residual),
+                                       native.ptr(out), B, H, W, Cin, Cout, R, S, stride, pad, int(relu), block_n,
+                                       native.stream_ptr(x.device))
+    native.check(st, "dpft_conv2d_nhwc_bf16")
+    native.count_launch()
+    return out

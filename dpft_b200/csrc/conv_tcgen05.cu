@@ -1,0 +1,488 @@
+// Backbone convolutions as tcgen05 implicit GEMMs for sm_100a.
+//
+// Replaces the cuDNN convolution + BatchNorm + ReLU (+ residual add) launches behind the ResNet bodies the
+// reference builds at src/dprt/models/backbones/resnet.py:54-55,101 (torchvision Bottleneck blocks), in
+// inference form: BatchNorm folded into the weights/bias on the host, activations NHWC bf16, fp32
+// accumulation in TMEM.
+//
+//   D[m, n] = act( sum_k A[m, k] * Wt[n, k] + bias[n] (+ residual[m, n]) )
+//   m = output pixel (b, p, q) linearised,  n = output channel,  k = (r, s, c) with c fastest.
+//
+// One persistent CTA per SM, 192 threads:
+//   warp 0   TMA producer   A tile (128 pixels x 64 channels of one filter tap) by an im2col-mode tensor map
+//                           (cp.async.bulk.tensor.4d...im2col; the tap (s, r) goes in the offset operands) or,
+//                           for 1x1/stride-1 layers, a plain 2-d tiled map over the [M, Cin] activation matrix;
+//                           B tile (BLOCK_N filters x 64) from the [Cout, R*S*Cin] weight matrix.  128B swizzle.
+//   warp 1   MMA issuer     one elected lane issues tcgen05.mma.cta_group::1.kind::f16 (M=128, N=BLOCK_N, K=16)
+//                           x4 per stage; tcgen05.commit releases the stage / publishes the accumulator.
+//   warps 2-5 epilogue      tcgen05.ld the fp32 accumulator (lane quadrant = warp_id % 4), + bias, + residual,
+//                           ReLU, pack to bf16, 16-byte global stores.
+// The accumulator is double-buffered in TMEM (2 x BLOCK_N columns) so the epilogue of tile i overlaps the
+// main loop of tile i+1.  Stages: a ring of STAGES {A 16 KB, B BLOCK_N*128 B} buffers with full/empty mbarriers.
+#include <cuda.h>
+
+#include "common.cuh"
+
+namespace dpft {
+namespace {
+
+constexpr int BLOCK_M = 128;
+constexpr int BLOCK_K = 64;          // bf16 elements = 128 bytes = one swizzle row
+constexpr int UMMA_K = 16;
+constexpr int kNumThreads = 192;
+constexpr int kEpilogueWarp0 = 2;
+
+enum ConvMode : int { kTiled2D = 0, kIm2col = 1, kRowTiled = 2 };
+
+struct ConvParams {
+    int M, N;               // output pixels, output channels
+    int P, Q;               // output height, width
+    int taps_s;             // filter width S (k-block -> (r, s))
+    int cblocks;            // Cin / 64
+    int kblocks;            // R * S * cblocks
+    int stride, pad;
+    int relu;
+    int mode;
+    int m_tiles, n_tiles;
+    int q_tiles;            // kRowTiled: tiles per output row
+    const float* bias;      // [N]
+    const __nv_bfloat16* residual;  // [M, N] or null
+    __nv_bfloat16* out;     // [M, N]
+};
+
+// ---- PTX wrappers -------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_LOOP:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra WAIT_DONE;\n"
+        "bra WAIT_LOOP;\n"
+        "WAIT_DONE:\n"
+        "}\n" ::"r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tcgen05_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tcgen05_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void tma_load_2d(const CUtensorMap* map, uint64_t* bar, void* dst, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
+            smem_u32(dst)),
+        "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+        : "memory");
+}
+__device__ __forceinline__ void tma_load_4d(const CUtensorMap* map, uint64_t* bar, void* dst, int c0, int c1, int c2,
+                                            int c3) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];" ::
+            "r"(smem_u32(dst)),
+        "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+        : "memory");
+}
+__device__ __forceinline__ void tma_load_im2col_4d(const CUtensorMap* map, uint64_t* bar, void* dst, int c, int w, int h,
+                                                   int n, uint16_t off_w, uint16_t off_h) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.shared::cluster.global.im2col.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], "
+        "[%2], {%7, %8};" ::"r"(smem_u32(dst)),
+        "l"(map), "r"(smem_u32(bar)), "r"(c), "r"(w), "r"(h), "r"(n), "h"(off_w), "h"(off_h)
+        : "memory");
+}
+__device__ __forceinline__ void prefetch_tmap(const CUtensorMap* map) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
+}
+
+// K-major, 128-byte-swizzled operand tile: rows of 128 B, 8-row groups 1024 B apart (SBO), descriptor version 1.
+__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);
+    d |= (uint64_t)1 << 16;                  // leading byte offset (unused for swizzled K-major) = 1
+    d |= (uint64_t)(1024 >> 4) << 32;        // stride byte offset
+    d |= (uint64_t)1 << 46;                  // version = 1 (Blackwell)
+    d |= (uint64_t)2 << 61;                  // SWIZZLE_128B
+    return d;
+}
+// kind::f16 instruction descriptor: D = f32, A = B = bf16, both K-major, M = 128, N = n.
+__host__ __device__ constexpr uint32_t umma_idesc_bf16(int n) {
+    return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(BLOCK_M >> 4) << 24);
+}
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+        "}\n" ::"r"(tmem_d),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tmem_ld_32x32b_x32(uint32_t taddr, uint32_t* r) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+          "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+          "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile(
+        "{\n"
+        ".reg .pred P;\n"
+        "elect.sync _|P, 0xffffffff;\n"
+        "selp.b32 %0, 1, 0, P;\n"
+        "}\n"
+        : "=r"(pred));
+    return pred != 0;
+}
+
+template <int BLOCK_N, int STAGES> struct SmemLayout {
+    static constexpr int kABytes = BLOCK_M * BLOCK_K * 2;
+    static constexpr int kBBytes = BLOCK_N * BLOCK_K * 2;
+    static constexpr int kStageBytes = kABytes + kBBytes;
+    static constexpr int kBarrierBytes = (2 * STAGES + 4) * 8 + 16;
+    static constexpr int kTotal = STAGES * kStageBytes + kBarrierBytes + 1024;   // +1024: manual alignment slack
+};
+
+// ---- the kernel -------------------------------------------------------------------------------------------------
+template <int BLOCK_N, int STAGES>
+__global__ void __launch_bounds__(kNumThreads, 1)
+conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+                 const ConvParams prm) {
+    using L = SmemLayout<BLOCK_N, STAGES>;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint8_t* smem_a = smem;
+    uint8_t* smem_b = smem + STAGES * L::kABytes;
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * L::kStageBytes);
+    uint64_t* empty_bar = full_bar + STAGES;
+    uint64_t* tmem_full = empty_bar + STAGES;
+    uint64_t* tmem_empty = tmem_full + 2;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    constexpr uint32_t kTmemCols = 2 * BLOCK_N;       // 128, 256 or 512: a power of two >= 32
+
+    if (warp == 0 && elect_one()) {
+        prefetch_tmap(&tmap_a);
+        prefetch_tmap(&tmap_b);
+        for (int i = 0; i < STAGES; ++i) {
+            mbar_init(&full_bar[i], 1);
+            mbar_init(&empty_bar[i], 1);
+        }
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(&tmem_full[i], 1);
+            mbar_init(&tmem_empty[i], 4);             // one arrive per epilogue warp
+        }
+        fence_barrier_init();
+    } else if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                     "r"(kTmemCols)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tcgen05_fence_before();
+    __syncthreads();
+    tcgen05_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    const int num_tiles = prm.m_tiles * prm.n_tiles;
+
+    if (warp == 0) {
+        // ===================================== TMA producer =====================================
+        if (elect_one()) {
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+                const int m_tile = tile / prm.n_tiles, n_tile = tile % prm.n_tiles;
+                int cw = 0, ch = 0, cn = 0;           // first pixel of the tile in tensor-map coordinates
+                if (prm.mode == kIm2col) {
+                    const int m0 = m_tile * BLOCK_M;
+                    const int pq = prm.P * prm.Q;
+                    cn = m0 / pq;
+                    const int rem = m0 - cn * pq;
+                    const int p = rem / prm.Q, q = rem - p * prm.Q;
+                    cw = q * prm.stride - prm.pad;
+                    ch = p * prm.stride - prm.pad;
+                } else if (prm.mode == kRowTiled) {
+                    const int row = m_tile / prm.q_tiles;          // (b, p)
+                    cw = (m_tile - row * prm.q_tiles) * BLOCK_M;   // q0
+                    cn = row / prm.P;
+                    ch = (row - cn * prm.P) * prm.stride;          // first input row of the window (pre-padded input)
+                }
+                for (int kb = 0; kb < prm.kblocks; ++kb) {
+                    mbar_wait(&empty_bar[stage], phase ^ 1);
+                    mbar_expect_tx(&full_bar[stage], L::kStageBytes);
+                    void* a_dst = smem_a + stage * L::kABytes;
+                    void* b_dst = smem_b + stage * L::kBBytes;
+                    const int tap = kb / prm.cblocks;
+                    const int c0 = (kb - tap * prm.cblocks) * BLOCK_K;
+                    if (prm.mode == kTiled2D) {
+                        tma_load_2d(&tmap_a, &full_bar[stage], a_dst, c0, m_tile * BLOCK_M);
+                    } else if (prm.mode == kIm2col) {
+                        const int r = tap / prm.taps_s, s = tap - r * prm.taps_s;
+                        tma_load_im2col_4d(&tmap_a, &full_bar[stage], a_dst, c0, cw, ch, cn, (uint16_t)s, (uint16_t)r);
+                    } else {
+                        // kRowTiled (stem): k-block = one filter row r; 64 contiguous elements = 8 taps x 8 channels
+                        tma_load_4d(&tmap_a, &full_bar[stage], a_dst, 0, cw, ch + tap, cn);
+                    }
+                    tma_load_2d(&tmap_b, &full_bar[stage], b_dst, kb * BLOCK_K, n_tile * BLOCK_N);
+                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ====================================== MMA issuer ======================================
+        constexpr uint32_t idesc = umma_idesc_bf16(BLOCK_N);
+        int stage = 0;
+        uint32_t phase = 0;
+        int acc = 0;
+        uint32_t acc_phase = 0;
+        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+            mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+            tcgen05_fence_after();
+            const uint32_t tmem_d = tmem_base + acc * BLOCK_N;
+            for (int kb = 0; kb < prm.kblocks; ++kb) {
+                mbar_wait(&full_bar[stage], phase);
+                tcgen05_fence_after();
+                if (elect_one()) {
+                    const uint64_t adesc = umma_desc_sw128(smem_u32(smem_a + stage * L::kABytes));
+                    const uint64_t bdesc = umma_desc_sw128(smem_u32(smem_b + stage * L::kBBytes));
+#pragma unroll
+                    for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
+                        // +32 bytes per K=16 step inside the 128-byte swizzle row: start-address field += 2
+                        umma_bf16(tmem_d, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) ? 1u : 0u);
+                    }
+                    umma_commit(&empty_bar[stage]);                  // frees the smem stage when the MMAs retire
+                    if (kb == prm.kblocks - 1) umma_commit(&tmem_full[acc]);
+                }
+                __syncwarp();
+                if (++stage == STAGES) { stage = 0; phase ^= 1; }
+            }
+            if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+        }
+    } else {
+        // ======================================= epilogue =======================================
+        const int quad = warp & 3;                    // TMEM lane quadrant this warp may read
+        int acc = 0;
+        uint32_t acc_phase = 0;
+        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+            const int m_tile = tile / prm.n_tiles, n_tile = tile % prm.n_tiles;
+            mbar_wait(&tmem_full[acc], acc_phase);
+            tcgen05_fence_after();
+            const int r_in_tile = quad * 32 + lane;
+            long long m;
+            bool row_ok;
+            if (prm.mode == kRowTiled) {
+                const int row = m_tile / prm.q_tiles;
+                const int q = (m_tile - row * prm.q_tiles) * BLOCK_M + r_in_tile;
+                m = (long long)row * prm.Q + q;
+                row_ok = q < prm.Q;
+            } else {
+                m = (long long)m_tile * BLOCK_M + r_in_tile;
+                row_ok = m < prm.M;
+            }
+            const int n0 = n_tile * BLOCK_N;
+            __nv_bfloat16* orow = prm.out + m * prm.N + n0;
+            const __nv_bfloat16* rrow = prm.residual ? prm.residual + m * prm.N + n0 : nullptr;
+#pragma unroll 1
+            for (int c = 0; c < BLOCK_N; c += 32) {
+                uint32_t v[32];
+                tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * BLOCK_N + c), v);
+                tmem_ld_wait();
+                if (row_ok) {
+#pragma unroll
+                    for (int j = 0; j < 32; j += 8) {
+                        float f[8];
+#pragma unroll
+                        for (int t = 0; t < 8; ++t) f[t] = __uint_as_float(v[j + t]) + __ldg(prm.bias + n0 + c + j + t);
+                        if (rrow) {
+                            const uint4 rv = *reinterpret_cast<const uint4*>(rrow + c + j);
+                            const __nv_bfloat162* rb = reinterpret_cast<const __nv_bfloat162*>(&rv);
+#pragma unroll
+                            for (int t = 0; t < 4; ++t) {
+                                const float2 rf = __bfloat1622float2(rb[t]);
+                                f[2 * t] += rf.x;
+                                f[2 * t + 1] += rf.y;
+                            }
+                        }
+                        if (prm.relu) {
+#pragma unroll
+                            for (int t = 0; t < 8; ++t) f[t] = fmaxf(f[t], 0.0f);
+                        }
+                        uint4 ov;
+                        __nv_bfloat162* ob = reinterpret_cast<__nv_bfloat162*>(&ov);
+#pragma unroll
+                        for (int t = 0; t < 4; ++t) ob[t] = __floats2bfloat162_rn(f[2 * t], f[2 * t + 1]);
+                        *reinterpret_cast<uint4*>(orow + c + j) = ov;
+                    }
+                }
+            }
+            tcgen05_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+            if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+        }
+    }
+
+    tcgen05_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tcgen05_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemCols) : "memory");
+    }
+}
+
+// ---- host side: tensor maps through the driver entry points (no link-time libcuda dependency) -----------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+typedef CUresult (*EncodeIm2colFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                   const int*, const int*, cuuint32_t, cuuint32_t, const cuuint32_t*, CUtensorMapInterleave,
+                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn g_encode_tiled = nullptr;
+EncodeIm2colFn g_encode_im2col = nullptr;
+int g_driver_version = 0;
+int g_sm_count = 0;
+
+int resolve_driver() {
+    if (g_encode_tiled && g_encode_im2col) return 0;
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    int st = cuda_status(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q), "cuTensorMapEncodeTiled");
+    if (st) return st;
+    if (!fn) { set_error("cuTensorMapEncodeTiled not available in this driver"); return DPFT_ERR_UNSUPPORTED; }
+    g_encode_tiled = (EncodeTiledFn)fn;
+    fn = nullptr;
+    st = cuda_status(cudaGetDriverEntryPoint("cuTensorMapEncodeIm2col", &fn, cudaEnableDefault, &q), "cuTensorMapEncodeIm2col");
+    if (st) return st;
+    if (!fn) { set_error("cuTensorMapEncodeIm2col not available in this driver"); return DPFT_ERR_UNSUPPORTED; }
+    g_encode_im2col = (EncodeIm2colFn)fn;
+    cudaDriverGetVersion(&g_driver_version);
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&g_sm_count, cudaDevAttrMultiProcessorCount, dev);
+    return 0;
+}
+
+int encode_2d(CUtensorMap* map, const void* base, uint64_t inner, uint64_t outer, uint64_t row_bytes, uint32_t box_inner,
+              uint32_t box_outer) {
+    cuuint64_t dims[2] = {inner, outer};
+    cuuint64_t strides[1] = {row_bytes};
+    cuuint32_t box[2] = {box_inner, box_outer};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = g_encode_tiled(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+                                CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled(2d) failed with CUresult %d", (int)r); return DPFT_ERR_INVALID_ARGUMENT; }
+    return 0;
+}
+
+template <int BLOCK_N, int STAGES>
+int launch(const CUtensorMap& ta, const CUtensorMap& tb, const ConvParams& prm, cudaStream_t stream) {
+    using L = SmemLayout<BLOCK_N, STAGES>;
+    static bool configured = false;
+    if (!configured) {
+        int st = cuda_status(cudaFuncSetAttribute(conv_gemm_kernel<BLOCK_N, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                  L::kTotal), "cudaFuncSetAttribute(conv_gemm_kernel)");
+        if (st) return st;
+        configured = true;
+    }
+    const int tiles = prm.m_tiles * prm.n_tiles;
+    const int grid = tiles < g_sm_count ? tiles : g_sm_count;
+    conv_gemm_kernel<BLOCK_N, STAGES><<<grid, kNumThreads, L::kTotal, stream>>>(ta, tb, prm);
+    DPFT_LAUNCH_CHECK("conv_gemm_kernel");
+    return DPFT_OK;
+}
+
+int pick_block_n(int Cout, int m_tiles, int want) {
+    if (want == 64 || want == 128 || want == 256) return (Cout % want == 0) ? want : 64;
+    // largest tile that still leaves every SM a tile or so; small problems prefer more, smaller tiles
+    const int cands[3] = {256, 128, 64};
+    for (int i = 0; i < 3; ++i) {
+        const int bn = cands[i];
+        if (Cout % bn) continue;
+        if ((long long)m_tiles * (Cout / bn) >= (long long)g_sm_count || bn == 64) return bn;
+    }
+    return 64;
+}
+
+}  // namespace
+}  // namespace dpft
+
+using namespace dpft;
+
+extern "C" int dpft_conv2d_nhwc_bf16(const void* x, const void* w, const float* bias, const void* residual, void* y,
+                                     int B, int H, int W, int Cin, int Cout, int R, int S, int stride, int pad, int relu,
+                                     int block_n, void* stream) {
+    DPFT_REQUIRE(x && w && bias && y, "conv2d: null pointer");
+    DPFT_REQUIRE(B > 0 && H > 0 && W > 0, "conv2d: bad input size %dx%dx%d", B, H, W);
+    DPFT_REQUIRE(Cin % 64 == 0 && Cout % 64 == 0, "conv2d: Cin=%d and Cout=%d must be multiples of 64", Cin, Cout);
+    DPFT_REQUIRE(R >= 1 && S >= 1 && R <= 16 && S <= 16 && stride >= 1 && stride <= 8 && pad >= 0 && pad < 16,
+                 "conv2d: unsupported filter %dx%d stride %d pad %d", R, S, stride, pad);
+    DPFT_REQUIRE((((uintptr_t)x | (uintptr_t)w | (uintptr_t)y | (uintptr_t)residual) & 15) == 0, "conv2d: pointers must be 16-byte aligned");
+    int st = resolve_driver();
+    if (st) return st;
+    const int P = (H + 2 * pad - R) / stride + 1, Q = (W + 2 * pad - S) / stride + 1;
+    DPFT_REQUIRE(P > 0 && Q > 0, "conv2d: empty output");
+    ConvParams prm{};
+    prm.M = B * P * Q; prm.N = Cout; prm.P = P; prm.Q = Q; prm.taps_s = S; prm.cblocks = Cin / 64;
+    prm.kblocks = R * S * prm.cblocks; prm.stride = stride; prm.pad = pad; prm.relu = relu;
+    prm.bias = bias; prm.residual = (const __nv_bfloat16*)residual; prm.out = (__nv_bfloat16*)y;
+    prm.m_tiles = (prm.M + BLOCK_M - 1) / BLOCK_M; prm.q_tiles = 0;
+    const int bn = pick_block_n(Cout, prm.m_tiles, block_n);
+    prm.n_tiles = Cout / bn;
+
+    CUtensorMap ta, tb;
+    const bool pointwise = (R == 1 && S == 1 && stride == 1 && pad == 0);
+    if (pointwise) {
+        prm.mode = kTiled2D;
+        st = encode_2d(&ta, x, (uint64_t)Cin, (uint64_t)prm.M, (uint64_t)Cin * 2, BLOCK_K, BLOCK_M);
+        if (st) return st;
+    } else {
+        prm.mode = kIm2col;
+        cuuint64_t dims[4] = {(cuuint64_t)Cin, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
+        cuuint64_t strides[3] = {(cuuint64_t)Cin * 2, (cuuint64_t)W * Cin * 2, (cuuint64_t)H * W * Cin * 2};
+        int lower[2] = {-pad, -pad};
+        int upper[2] = {pad - (S - 1), pad - (R - 1)};
+        cuuint32_t estr[4] = {1, (cuuint32_t)stride, (cuuint32_t)stride, 1};
+        CUresult r = g_encode_im2col(&ta, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(x), dims, strides, lower, upper,
+                                     BLOCK_K, BLOCK_M, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                                     CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeIm2col failed with CUresult %d", (int)r); return DPFT_ERR_INVALID_ARGUMENT; }
+        // Same small-tensor fix-up CUTLASS applies for drivers <= 13.1 (cute/atom/copy_traits_sm90_im2col.hpp).
+        if (g_driver_version <= 13010 && (uint64_t)B * H * W * Cin * 2 < 131072)
+            reinterpret_cast<uint64_t*>(&ta)[1] &= ~(1ull << 21);
+    }
+    st = encode_2d(&tb, w, (uint64_t)R * S * Cin, (uint64_t)Cout, (uint64_t)R * S * Cin * 2, BLOCK_K, bn);
+    if (st) return st;
+    cudaStream_t s = (cudaStream_t)stream;
+    if (bn == 256) return launch<256, 4>(ta, tb, prm, s);
+    if (bn == 128) return launch<128, 6>(ta, tb, prm, s);
+    return launch<64, 8>(ta, tb, prm, s);
+}

@@ -78,6 +78,22 @@ DPFT_API int dpft_msda_backward(const void* value, const int64_t* shapes, const 
                        void* grad_attn, int B, int S, int M, int D, int N, int L, int P, int dtype,
                        void* stream);
 
+/*
+ * 2-d convolution + folded BatchNorm (+ residual) (+ ReLU), NHWC bf16, as a tcgen05 implicit GEMM.
+ * Replaces the Conv2d/BatchNorm2d/ReLU/add launches of the torchvision Bottleneck blocks the reference runs at
+ * src/dprt/models/backbones/resnet.py:101 (built at :54-55), in eval() form:
+ *   y[b,p,q,n] = act( sum_{r,s,c} x[b, p*stride-pad+r, q*stride-pad+s, c] * w[n,r,s,c] + bias[n] (+ residual[b,p,q,n]) )
+ *   x        (B, H, W, Cin)       bf16, Cin  % 64 == 0
+ *   w        (Cout, R, S, Cin)    bf16, Cout % 64 == 0   (BatchNorm scale already folded in)
+ *   bias     (Cout,)              f32                    (BatchNorm shift)
+ *   residual (B, P, Q, Cout)      bf16 or NULL
+ *   y        (B, P, Q, Cout)      bf16, P = (H+2*pad-R)/stride+1, Q likewise
+ * block_n: 0 = choose, or 64 / 128 / 256 (output-channel tile; tests sweep it).
+ */
+DPFT_API int dpft_conv2d_nhwc_bf16(const void* x, const void* w, const float* bias, const void* residual, void* y,
+                                   int B, int H, int W, int Cin, int Cout, int R, int S, int stride, int pad, int relu,
+                                   int block_n, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

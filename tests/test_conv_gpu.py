@@ -1,0 +1,85 @@
+"""tcgen05 convolution kernel vs a plain PyTorch fp32 reference of the same op (bf16-rounded operands, fp32 math).
+Floating-point kernel: tolerance 1e-2 rel (north_star's bf16 bar); the fp32 accumulation itself is checked tighter
+by comparing against the fp32 conv of the SAME bf16-rounded inputs (only the output rounding remains: 2^-8)."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+# (B, H, W, Cin, Cout, R, stride, pad) — the ResNet-50/101 bottleneck shapes at small spatial sizes + tails
+SHAPES = [
+    (2, 16, 24, 64, 64, 1, 1, 0),        # 1x1, tiled-2D path, M multiple of 128
+    (1, 9, 7, 64, 256, 1, 1, 0),         # M = 63: one partial tile
+    (2, 23, 40, 256, 64, 1, 1, 0),       # K = 256 (4 k-blocks), M tail
+    (1, 12, 20, 1024, 256, 1, 1, 0),     # deep K, wraps the stage ring
+    (2, 16, 24, 64, 64, 3, 1, 1),        # 3x3 im2col
+    (1, 9, 7, 128, 128, 3, 1, 1),        # 3x3, tiny map, tile spans rows and images
+    (3, 10, 27, 128, 128, 3, 2, 1),      # 3x3 stride 2, odd sizes (radar_front)
+    (2, 23, 40, 256, 512, 1, 2, 0),      # 1x1 stride 2 (downsample)
+    (1, 2, 4, 512, 512, 3, 1, 1),        # radar_front layer4: 2x4 map (< 128 KiB tensor: driver fix-up path)
+    (2, 8, 8, 512, 2048, 1, 1, 0),       # widest Cout
+]
+
+
+def _reference(x, w, bias, stride, pad, relu, residual):
+    y = F.conv2d(x.float().permute(0, 3, 1, 2), w.float().permute(0, 3, 1, 2), bias, stride=stride, padding=pad)
+    y = y.permute(0, 2, 3, 1)
+    if residual is not None:
+        y = y + residual.float()
+    return torch.relu(y) if relu else y
+
+
+@pytest.mark.parametrize("shape", SHAPES)
+@pytest.mark.parametrize("block_n", [0, 64, 128, 256])
+@pytest.mark.parametrize("relu,with_res", [(True, False), (True, True), (False, False)])
+def test_conv_matches_torch_fp32(shape, block_n, relu, with_res):
+    from dpft_b200 import conv
+    B, H, W, Cin, Cout, R, stride, pad = shape
+    if block_n and Cout % block_n:
+        pytest.skip("tile does not divide Cout")
+    dev = "cuda:0"
+    g = torch.Generator(device=dev).manual_seed(Cin + Cout + R)
+    x = torch.randn(B, H, W, Cin, generator=g, device=dev).bfloat16()
+    w = (torch.randn(Cout, R, R, Cin, generator=g, device=dev) / (R * R * Cin) ** 0.5).bfloat16()
+    bias = torch.randn(Cout, generator=g, device=dev)
+    P, Q = (H + 2 * pad - R) // stride + 1, (W + 2 * pad - R) // stride + 1
+    res = torch.randn(B, P, Q, Cout, generator=g, device=dev).bfloat16() if with_res else None
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    want = _reference(x, w, bias, stride, pad, relu, res)
+    got = conv.conv2d_nhwc_bf16(x, w, bias, stride, pad, relu, res, block_n=block_n)
+    torch.cuda.synchronize()
+    assert got.shape == (B, P, Q, Cout) and got.dtype == torch.bfloat16
+    err = (got.float() - want).abs().max().item()
+    scale = want.abs().max().item()
+    assert err <= 1e-2 * scale, (err, scale)                       # north_star bf16 bar
+    assert err <= 2.0 ** -7 * scale, (err, scale)                  # only the bf16 output rounding should remain
+
+
+def test_folded_bottleneck_matches_torch_block():
+    """conv+bn folding and the residual/ReLU epilogue reproduce a torchvision-style bottleneck in eval mode."""
+    from dpft_b200 import conv
+    from dpft_b200.models.backbone import Bottleneck
+    from torch import nn
+    dev = "cuda:0"
+    torch.manual_seed(0)
+    blk = Bottleneck(256, 128, stride=2, norm=nn.BatchNorm2d, project=True).to(dev).eval()
+    for m in blk.modules():
+        if isinstance(m, nn.BatchNorm2d):
+            m.running_mean.normal_(0, 0.2)
+            m.running_var.uniform_(0.5, 1.5)
+            m.weight.data.uniform_(0.5, 1.5)
+            m.bias.data.normal_(0, 0.2)
+    x = torch.randn(2, 256, 18, 30, device=dev)
+    with torch.no_grad():
+        want = blk(x).permute(0, 2, 3, 1)
+    xb = x.permute(0, 2, 3, 1).contiguous().bfloat16()
+    c1, c2, c3 = (conv.FoldedConv(blk.conv1, blk.bn1, dev), conv.FoldedConv(blk.conv2, blk.bn2, dev),
+                  conv.FoldedConv(blk.conv3, blk.bn3, dev))
+    ds = conv.FoldedConv(blk.downsample[0], blk.downsample[1], dev)
+    idn = ds(xb, relu=False)
+    y = c3(c2(c1(xb, relu=True), relu=True), relu=True, residual=idn)
+    torch.cuda.synchronize()
+    rel = (y.float() - want).abs().max().item() / want.abs().max().item()
+    assert rel < 2e-2, rel

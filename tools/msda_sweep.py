@@ -27,8 +27,8 @@ CASES = {
     "cfg3_300q_fp32_D2": (8, 300, 8, 2, CAM5, 4, torch.float32),
     "cfg5_bf16_D2": (16, 900, 8, 2, CAM5[:4], 4, torch.bfloat16),
     "cfg5_bf16_D8": (16, 900, 8, 8, CAM5[:4], 4, torch.bfloat16),
-    "cfg5_bf16_D32": (16, 900, 8, 32, CAM4, 4, torch.bfloat16),
-    "cfg5_fp32_D32": (16, 900, 8, 32, CAM4, 4, torch.float32),
+    "cfg5_bf16_D32": (16, 900, 8, 32, CAM5[:4], 4, torch.bfloat16),
+    "cfg5_fp32_D32": (16, 900, 8, 32, CAM5[:4], 4, torch.float32),
 }
 
 
