@@ -1,7 +1,151 @@
-"""Fused inference pipeline (placeholder until the fused kernels land)."""
+"""Fused inference pipeline behind ``DPRT.forward`` in ``eval()`` (reference src/dprt/models/dprt.py:200-244).
+
+Stages, all on the GPU through libdpft_b200.so:
+  1. per view: backbone + FPN neck + positional embedding -> one feature pyramid buffer (B, S, 16) fp32;
+  2. per iteration: ``dpft_decoder_layer_forward`` (all views in one launch) and ``dpft_decoder_head_forward``.
+There is no host synchronisation anywhere in the forward (the reference has >= 24).
+
+The engine is built lazily from the module's parameters (``FusedEngine.try_create``); configurations the fused
+kernels do not cover fall back to the composed GPU path in ``DPRT.forward_composed`` (never to the CPU).
+"""
+from __future__ import annotations
+
+from collections import OrderedDict
+from typing import Dict, List, Optional
+
+import torch
+
+from . import decoder as dec
+from . import native
+from .models.fuser import FeaturePyramid, IMPFusion
+from .models.querent import DataAgnosticStaticQueries
 
 
 class FusedEngine:
+    def __init__(self, model):
+        self.model = model
+        fuser: IMPFusion = model.fuser
+        self.device = fuser.query.device
+        self.V, self.N, self.I = fuser.m_views, fuser.n_queries, fuser.i_iter
+        layer0 = fuser.mpfusion["fusion0"].ml_fusion_layers["ms_deform_attn0"]
+        self.P = layer0.ms_deform_attn.n_points
+        self.d_ffn = layer0.d_ffn
+        self.act = dec.ACTIVATIONS[layer0.activation]
+        self.reduction = dec.REDUCTIONS[fuser.reduction]
+        self.n_cls = fuser.heads[0].num_classes
+        self.levels = [fuser.mpfusion["fusion0"].ml_fusion_layers[f"ms_deform_attn{v}"].ms_deform_attn.n_levels
+                       for v in range(self.V)]
+        # packed weights: one image per (iteration, view) and one per head
+        self.layer_w: List[List[torch.Tensor]] = []
+        self.head_w: List[torch.Tensor] = []
+        for it in range(self.I):
+            mp = fuser.mpfusion[f"fusion{it}"]
+            self.layer_w.append([dec.pack_layer(mp.ml_fusion_layers[f"ms_deform_attn{v}"]).to(self.device)
+                                 for v in range(self.V)])
+            self.head_w.append(dec.pack_head(mp.reduction_layer, fuser.heads[it], fuser.reduction).to(self.device))
+        self.query = fuser.query.detach().float().contiguous()
+        self.pos = fuser.query_embedding.weight.detach().float().contiguous()
+        self._param_version = self._version(model)
+
+    # -- construction ---------------------------------------------------------------------------------------------
     @staticmethod
-    def try_create(model):
+    def _version(model) -> int:
+        return sum(p._version for p in model.fuser.parameters())
+
+    @staticmethod
+    def ineligible_reason(model) -> Optional[str]:
+        fuser = model.fuser
+        if not isinstance(fuser, IMPFusion):
+            return "fuser is not IMPFusion"
+        if not isinstance(model.querent, DataAgnosticStaticQueries):
+            return "querent is not the static data-agnostic grid"
+        if fuser.query.device.type != "cuda":
+            return "model is not on a CUDA device"
+        if fuser.reduction not in dec.REDUCTIONS:
+            return f"reduction {fuser.reduction}"
+        if not 1 <= fuser.m_views <= 4:
+            return f"m_views={fuser.m_views}"
+        if len(set(fuser.n_levels)) != 1:
+            return "views with different level counts"
+        for mp in fuser.mpfusion.values():
+            for layer in mp.ml_fusion_layers.values():
+                why = dec.layer_eligible(layer, fuser.d_model)
+                if why:
+                    return why
+        for h in fuser.heads:
+            why = dec.head_eligible(h)
+            if why:
+                return why
+        native.load_library()          # raises loudly when the library is missing
         return None
+
+    @classmethod
+    def try_create(cls, model) -> Optional["FusedEngine"]:
+        if cls.ineligible_reason(model) is not None:
+            return None
+        return cls(model)
+
+    def accepts(self, batch: Dict[str, torch.Tensor]) -> bool:
+        if self._version(self.model) != self._param_version:     # parameters were updated: repack
+            self.__init__(self.model)
+        x = batch[self.model.inputs[0]]
+        return x.is_cuda and x.dtype == torch.float32
+
+    # -- stage 1: feature pyramids --------------------------------------------------------------------------------
+    def pyramids(self, batch: Dict[str, torch.Tensor]) -> List[FeaturePyramid]:
+        feats = self.model.extract_features(batch)
+        return [FeaturePyramid.from_levels(feats[name]) for name in self.model.inputs]
+
+    # -- stage 2: decoder -----------------------------------------------------------------------------------------
+    def decode(self, batch: Dict[str, torch.Tensor], pyramids: List[FeaturePyramid]) -> "OrderedDict[str, torch.Tensor]":
+        model, dev = self.model, self.device
+        B = pyramids[0].flat.shape[0]
+        N, V = self.N, self.V
+        keep = []                                  # keeps the small per-call device tensors alive
+        base_views = []
+        for name, pyr in zip(model.inputs, pyramids):
+            t = batch[f"label_to_{name}_t"].float().contiguous()
+            p = batch[f"label_to_{name}_p"].float()
+            if p.shape[1] == 3:                    # radar projections are 3x4 (dataset.py:271-293)
+                last = torch.tensor([0.0, 0.0, 0.0, 1.0], device=dev).expand(B, 1, 4)
+                p = torch.cat((p, last), dim=1)
+            p = p.contiguous()
+            shape_hw = batch[f"{name}_shape"][:, :2].float().contiguous()
+            flag = t.any().to(torch.int32).reshape(1)
+            flat = pyr.flat if pyr.flat.is_contiguous() else pyr.flat.contiguous()
+            keep += [t, p, shape_hw, flag, flat]
+            view = dec.DecoderView()
+            view.pyramid, view.transform, view.projection = flat.data_ptr(), t.data_ptr(), p.data_ptr()
+            view.shape_hw, view.use_transform, view.S = shape_hw.data_ptr(), flag.data_ptr(), flat.shape[1]
+            start = 0
+            for l, (h, w) in enumerate(pyr.shapes):
+                view.level_h[l], view.level_w[l], view.level_start[l] = h, w, start
+                start += h * w
+            base_views.append(view)
+
+        center = model.querent.grid(torch.float32, dev).contiguous()      # (N, 3): same for every sample
+        query = self.query                                                # (N, 16)
+        views_out = torch.empty((B, V, N, 16), dtype=torch.float32, device=dev)
+        out = None
+        with torch.cuda.device(dev):
+            for it in range(self.I):
+                for v, view in enumerate(base_views):
+                    view.weights = self.layer_w[it][v].data_ptr()
+                dec.layer_forward(base_views, query, self.pos, center, views_out, B, N, self.levels[0], self.P,
+                                  self.d_ffn, self.act, self.layer_w[it][0].numel())
+                last = it == self.I - 1
+                query_out = torch.empty((B, N, 16), dtype=torch.float32, device=dev)
+                center_out = torch.empty((B, N, 3), dtype=torch.float32, device=dev)
+                size = torch.empty((B, N, 3), dtype=torch.float32, device=dev) if last else None
+                angle = torch.empty((B, N, 2), dtype=torch.float32, device=dev) if last else None
+                klass = torch.empty((B, N, self.n_cls), dtype=torch.float32, device=dev) if last else None
+                dec.head_forward(views_out, self.head_w[it], center, query_out, center_out, size, angle, klass,
+                                 B, V, N, self.n_cls, self.reduction)
+                query, center = query_out, center_out
+                if last:
+                    out = OrderedDict(center=center_out, size=size, angle=angle)
+                    out["class"] = klass
+        return out
+
+    def forward(self, batch: Dict[str, torch.Tensor]) -> "OrderedDict[str, torch.Tensor]":
+        return self.decode(batch, self.pyramids(batch))

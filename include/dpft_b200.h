@@ -94,6 +94,56 @@ DPFT_API int dpft_conv2d_nhwc_bf16(const void* x, const void* w, const float* bi
                                    int B, int H, int W, int Cin, int Cout, int R, int S, int stride, int pad, int relu,
                                    int block_n, void* stream);
 
+/*
+ * Fused query decoder (inference), d_model = 16, 8 heads.
+ *
+ * dpft_decoder_layer_forward runs, for every (sample, view), one whole MLFusion layer of the reference
+ * (src/dprt/models/fusers/mpfusion.py:231-263): self-attention (:122-148), reference-point projection
+ * (IMPFusion.get_reference_points :617-696), multi-scale deformable cross-attention
+ * (src/dprt/models/layers/ms_deform_attn.py:138-217) and the feed-forward block (:210-229), each with its
+ * residual + LayerNorm.  It replaces MPFusion.forward's per-view loop (:496-509).
+ *   views[v]      per-view inputs: the FPN pyramid with positional embedding (B, S, 16) f32, finest level first
+ *                 (what mpfusion.py:179 concatenates), its level table, the calibration matrices of the batch
+ *                 (label_to_<input>_t / _p, src/dprt/models/dprt.py:188-198), the original input (H, W)
+ *                 (dprt.py:216) as f32, the device flag transformation.any() (mpfusion.py:647) and the packed
+ *                 layer weights (layout: dpft_b200/decoder.py::pack_layer).
+ *   query         (B, N, 16) f32, or (N, 16) with query_batch_stride = 0 (first iteration, mpfusion.py:727)
+ *   pos           (N, 16) f32   query_embedding.weight (mpfusion.py:730)
+ *   center        (B, N, 3) f32 current box centres, or (N, 3) with center_batch_stride = 0
+ *   out           (B, V, N, 16) f32
+ *   activation    0 = ReLU, 1 = Mish, 2 = GELU
+ */
+typedef struct dpft_decoder_view {
+    const float* pyramid;
+    const float* weights;
+    const float* transform;     /* (B, 4, 4) */
+    const float* projection;    /* (B, 4, 4); 3x4 matrices padded with the row [0 0 0 1] */
+    const float* shape_hw;      /* (B, 2) */
+    const int* use_transform;   /* 1 element */
+    long long S;
+    int level_h[8];
+    int level_w[8];
+    long long level_start[8];
+} dpft_decoder_view;
+
+DPFT_API int dpft_decoder_layer_forward(const dpft_decoder_view* views, int V, const float* query,
+                                        long long query_batch_stride, const float* pos, const float* center,
+                                        long long center_batch_stride, float* out, int B, int N, int L, int P,
+                                        int d_ffn, int activation, int weight_floats, void* stream);
+
+/*
+ * View reduction + detection head for one iteration: MPFusion.reduce (mpfusion.py:416-470; 0 = 'linear' with the
+ * channel-major/view-minor flattening of :438, 1 = 'mean', 2 = 'max') followed by LinearDetectionHead.forward
+ * (src/dprt/models/heads/detection.py:252-275; three bias-free Linear layers per branch, ReLU between, centre
+ * refinement center += previous centre at :273).  size/angle/class outputs may be NULL on intermediate iterations
+ * (only the centre feeds the next iteration, mpfusion.py:732-743).
+ *   views (B, V, N, 16); weights packed by dpft_b200/decoder.py::pack_head; outputs (B, N, 16|3|3|2|n_cls) f32.
+ */
+DPFT_API int dpft_decoder_head_forward(const float* views, const float* weights, const float* center_in,
+                                       long long center_batch_stride, float* query_out, float* center_out,
+                                       float* size_out, float* angle_out, float* class_out, int B, int V, int N,
+                                       int n_cls, int reduction, int weight_floats, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

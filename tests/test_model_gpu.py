@@ -14,6 +14,17 @@ CASES = ["radar_bev_native", "radar_bev_256", "radar_front_native", "camera_mono
 TOL_FP32 = 1e-3      # north_star: outputs within 1e-3 rel (fp32) of the reference forward
 
 
+@pytest.fixture(autouse=True)
+def _strict_fp32():
+    """PyTorch lets cuDNN/cuBLAS use TF32 for fp32 convs by default (1e-3-level deviations from the CPU reference);
+    the module-by-module path is checked with TF32 off so it is held to the fp32 bar."""
+    old = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32)
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    yield
+    torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = old
+
+
 def _model(cfg, seed):
     model = models.build("dprt", cfg).eval()
     model.load_state_dict(synthetic.seeded_state_dict(model.state_dict(), seed=seed), strict=True)
