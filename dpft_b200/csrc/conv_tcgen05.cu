@@ -48,7 +48,18 @@ struct ConvParams {
     const float* bias;      // [N]
     const __nv_bfloat16* residual;  // [M, N] or null
     __nv_bfloat16* out;     // [M, N]
+    // FPN lateral form: fp32 output of the first 16 channels (+ nearest-upsampled coarser level)
+    float* out_f32;         // [M, 16] or null
+    const float* coarse;    // (B, Hc, Wc, 16) or null
+    int Hc, Wc;
 };
+
+__device__ __forceinline__ int nearest_src(int dst, int in_size, int out_size) {
+    // torch 'nearest': src = min(floor(dst * (float(in) / out)), in - 1)
+    const float scale = (float)in_size / (float)out_size;
+    const int s = (int)floorf((float)dst * scale);
+    return s < in_size - 1 ? s : in_size - 1;
+}
 
 // ---- PTX wrappers -------------------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -307,6 +318,41 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                 row_ok = m < prm.M;
             }
             const int n0 = n_tile * BLOCK_N;
+            if (prm.out_f32) {
+                // FPN lateral: inner = conv1x1 + bias (+ top-down), 16 fp32 channels per pixel
+                uint32_t v[32];
+                tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * BLOCK_N), v);
+                tmem_ld_wait();
+                if (row_ok) {
+                    const float4* cp = nullptr;
+                    if (prm.coarse) {
+                        const int pq = prm.P * prm.Q;
+                        const int bi = (int)(m / pq);
+                        const int rem = (int)(m - (long long)bi * pq);
+                        const int p = rem / prm.Q, q = rem - p * prm.Q;
+                        const int hc = nearest_src(p, prm.Hc, prm.P), wc = nearest_src(q, prm.Wc, prm.Q);
+                        cp = reinterpret_cast<const float4*>(prm.coarse + (((long long)bi * prm.Hc + hc) * prm.Wc + wc) * 16);
+                    }
+                    float4* o = reinterpret_cast<float4*>(prm.out_f32 + m * 16);
+#pragma unroll
+                    for (int j4 = 0; j4 < 4; ++j4) {
+                        float4 r = make_float4(__uint_as_float(v[4 * j4]) + __ldg(prm.bias + 4 * j4),
+                                               __uint_as_float(v[4 * j4 + 1]) + __ldg(prm.bias + 4 * j4 + 1),
+                                               __uint_as_float(v[4 * j4 + 2]) + __ldg(prm.bias + 4 * j4 + 2),
+                                               __uint_as_float(v[4 * j4 + 3]) + __ldg(prm.bias + 4 * j4 + 3));
+                        if (cp) {
+                            const float4 c = __ldg(cp + j4);
+                            r.x += c.x; r.y += c.y; r.z += c.z; r.w += c.w;
+                        }
+                        o[j4] = r;
+                    }
+                }
+                tcgen05_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+                if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+                continue;
+            }
             __nv_bfloat16* orow = prm.out + m * prm.N + n0;
             const __nv_bfloat16* rrow = prm.residual ? prm.residual + m * prm.N + n0 : nullptr;
 #pragma unroll 1
@@ -436,6 +482,26 @@ int pick_block_n(int Cout, int m_tiles, int want) {
 }  // namespace dpft
 
 using namespace dpft;
+
+extern "C" int dpft_fpn_lateral_forward(const void* x, const void* w, const float* bias, const float* coarse, int Hc, int Wc,
+                                        float* out, int B, int H, int W, int Cin, void* stream) {
+    DPFT_REQUIRE(x && w && bias && out, "fpn_lateral: null pointer");
+    DPFT_REQUIRE(B > 0 && H > 0 && W > 0 && Cin % 64 == 0, "fpn_lateral: bad size B=%d H=%d W=%d Cin=%d", B, H, W, Cin);
+    DPFT_REQUIRE(coarse == nullptr || (Hc > 0 && Wc > 0), "fpn_lateral: bad coarse size");
+    int st = resolve_driver();
+    if (st) return st;
+    ConvParams prm{};
+    prm.M = B * H * W; prm.N = 64; prm.P = H; prm.Q = W; prm.taps_s = 1; prm.cblocks = Cin / 64; prm.kblocks = prm.cblocks;
+    prm.stride = 1; prm.pad = 0; prm.relu = 0; prm.mode = kTiled2D; prm.bias = bias;
+    prm.m_tiles = (prm.M + BLOCK_M - 1) / BLOCK_M; prm.n_tiles = 1;
+    prm.out_f32 = out; prm.coarse = coarse; prm.Hc = Hc; prm.Wc = Wc;
+    CUtensorMap ta, tb;
+    st = encode_2d(&ta, x, (uint64_t)Cin, (uint64_t)prm.M, (uint64_t)Cin * 2, BLOCK_K, BLOCK_M);
+    if (st) return st;
+    st = encode_2d(&tb, w, (uint64_t)Cin, 64, (uint64_t)Cin * 2, BLOCK_K, 64);
+    if (st) return st;
+    return launch<64, 8>(ta, tb, prm, (cudaStream_t)stream);
+}
 
 extern "C" int dpft_conv2d_nhwc_bf16(const void* x, const void* w, const float* bias, const void* residual, void* y,
                                      int B, int H, int W, int Cin, int Cout, int R, int S, int stride, int pad, int relu,

@@ -1,0 +1,318 @@
+// Dense feature path around the tcgen05 bottleneck convolutions, for sm_100a (inference):
+//
+//   stem_conv7x7     raw fp32 NHWC input -> 7x7/2 conv (+ folded BatchNorm, + folded 1x1 adjustment conv for the
+//                    6-channel radar cubes) + ReLU -> bf16 NHWC, 64 channels
+//                    (reference src/dprt/models/backbones/resnet.py:98-101: adjustment_layer, conv1, bn1, relu)
+//   maxpool3x3s2     torchvision ResNet maxpool (kernel 3, stride 2, padding 1) on bf16 NHWC
+//   fpn_output       the FPN output stage of one level (reference src/dprt/models/necks/fpn.py:70-83 over
+//                    torchvision FeaturePyramidNetwork): 3x3 conv (16 -> 16, zero padding) + bias, fused with the
+//                    sinusoidal positional embedding (src/dprt/models/embeddings/sinusoidal.py:107-108) and written
+//                    straight into the view's feature pyramid buffer (B, S, 16) — the tensor the reference builds with
+//                    torch.cat in every decoder layer (src/dprt/models/fusers/mpfusion.py:179).
+//                    For the finest level (the raw input, "skip link" dprt.py:222-225) the lateral 1x1 conv and the
+//                    top-down nearest-upsample-add are computed on the fly into the shared-memory halo tile, so the
+//                    full-resolution 16-channel "inner" map never touches HBM.
+//
+// All three are HBM-bound (N = 16 output channels, tiny K): coalesced 16-byte accesses, halo tiles in shared memory.
+#include "common.cuh"
+
+namespace dpft {
+namespace {
+
+// --------------------------------------------------------------------------------------------------------- stem
+constexpr int STEM_TH = 8, STEM_TW = 16;             // output tile
+constexpr int STEM_PH = STEM_TH * 2 + 5, STEM_PW = STEM_TW * 2 + 5;   // input patch
+constexpr int STEM_COUT = 64;
+
+template <int CIN>
+__global__ void __launch_bounds__(256)
+stem_conv7x7_kernel(const float* __restrict__ x, const float* __restrict__ w /* [49*CIN][64] */,
+                    const float* __restrict__ bias, __nv_bfloat16* __restrict__ y, int H, int W, int P, int Q) {
+    extern __shared__ __align__(16) float smem[];
+    float* s_w = smem;                               // [49*CIN][64]
+    float* s_x = smem + 49 * CIN * STEM_COUT;        // [PH][PW][CIN]
+    const int b = blockIdx.z;
+    const int p0 = blockIdx.y * STEM_TH, q0 = blockIdx.x * STEM_TW;
+    const int tid = threadIdx.x;
+    for (int i = tid; i < 49 * CIN * STEM_COUT / 4; i += 256)
+        reinterpret_cast<float4*>(s_w)[i] = __ldg(reinterpret_cast<const float4*>(w) + i);
+    const int h_base = p0 * 2 - 3, w_base = q0 * 2 - 3;
+    for (int i = tid; i < STEM_PH * STEM_PW * CIN; i += 256) {
+        const int c = i % CIN;
+        const int pw = (i / CIN) % STEM_PW;
+        const int ph = i / (CIN * STEM_PW);
+        const int hh = h_base + ph, ww = w_base + pw;
+        float v = 0.0f;
+        if (hh >= 0 && hh < H && ww >= 0 && ww < W) v = __ldg(x + (((long long)b * H + hh) * W + ww) * CIN + c);
+        s_x[i] = v;
+    }
+    __syncthreads();
+    const int lane = tid & 31, warp = tid >> 5;
+    const int half = warp & 1;                       // which 32 output channels
+    const int pix = (warp >> 1) * 32 + lane;         // 0..127
+    const int ty = pix / STEM_TW, tx = pix % STEM_TW;
+    float acc[32];
+#pragma unroll
+    for (int o = 0; o < 32; ++o) acc[o] = __ldg(bias + half * 32 + o);
+    for (int r = 0; r < 7; ++r) {
+        for (int s = 0; s < 7; ++s) {
+            const float* xp = s_x + ((2 * ty + r) * STEM_PW + 2 * tx + s) * CIN;
+            const float* wp = s_w + ((r * 7 + s) * CIN) * STEM_COUT + half * 32;
+#pragma unroll
+            for (int c = 0; c < CIN; ++c) {
+                const float xv = xp[c];
+                const float4* w4 = reinterpret_cast<const float4*>(wp + c * STEM_COUT);
+#pragma unroll
+                for (int o4 = 0; o4 < 8; ++o4) {
+                    const float4 wv = w4[o4];
+                    acc[4 * o4] = fmaf(xv, wv.x, acc[4 * o4]);
+                    acc[4 * o4 + 1] = fmaf(xv, wv.y, acc[4 * o4 + 1]);
+                    acc[4 * o4 + 2] = fmaf(xv, wv.z, acc[4 * o4 + 2]);
+                    acc[4 * o4 + 3] = fmaf(xv, wv.w, acc[4 * o4 + 3]);
+                }
+            }
+        }
+    }
+    const int p = p0 + ty, q = q0 + tx;
+    if (p < P && q < Q) {
+        __nv_bfloat16* o = y + (((long long)b * P + p) * Q + q) * STEM_COUT + half * 32;
+#pragma unroll
+        for (int o8 = 0; o8 < 4; ++o8) {
+            uint4 pk;
+            __nv_bfloat162* pb = reinterpret_cast<__nv_bfloat162*>(&pk);
+#pragma unroll
+            for (int t = 0; t < 4; ++t)
+                pb[t] = __floats2bfloat162_rn(fmaxf(acc[8 * o8 + 2 * t], 0.0f), fmaxf(acc[8 * o8 + 2 * t + 1], 0.0f));
+            reinterpret_cast<uint4*>(o)[o8] = pk;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------ maxpool
+__global__ void __launch_bounds__(256)
+maxpool3x3s2_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ y, int B, int H, int W, int C8,
+                    int P, int Q) {
+    const long long idx = (long long)blockIdx.x * 256 + threadIdx.x;
+    const long long total = (long long)B * P * Q * C8;
+    if (idx >= total) return;
+    const int c8 = (int)(idx % C8);
+    const int q = (int)((idx / C8) % Q);
+    const int p = (int)((idx / ((long long)C8 * Q)) % P);
+    const int b = (int)(idx / ((long long)C8 * Q * P));
+    __nv_bfloat162 m[4];
+    const __nv_bfloat162 ninf = __floats2bfloat162_rn(-INFINITY, -INFINITY);
+#pragma unroll
+    for (int t = 0; t < 4; ++t) m[t] = ninf;
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+        const int hh = 2 * p - 1 + r;
+        if (hh < 0 || hh >= H) continue;
+#pragma unroll
+        for (int s = 0; s < 3; ++s) {
+            const int ww = 2 * q - 1 + s;
+            if (ww < 0 || ww >= W) continue;
+            const uint4 v = __ldg(reinterpret_cast<const uint4*>(x + (((long long)b * H + hh) * W + ww) * C8 * 8) + c8);
+            const __nv_bfloat162* vb = reinterpret_cast<const __nv_bfloat162*>(&v);
+#pragma unroll
+            for (int t = 0; t < 4; ++t) m[t] = __hmax2(m[t], vb[t]);
+        }
+    }
+    uint4 o;
+    __nv_bfloat162* ob = reinterpret_cast<__nv_bfloat162*>(&o);
+#pragma unroll
+    for (int t = 0; t < 4; ++t) ob[t] = m[t];
+    reinterpret_cast<uint4*>(y + (((long long)b * P + p) * Q + q) * C8 * 8)[c8] = o;
+}
+
+// --------------------------------------------------------------------------------------------------- FPN output
+constexpr int FPN_TH = 8, FPN_TW = 32;
+constexpr int FPN_PH = FPN_TH + 2, FPN_PW = FPN_TW + 2;
+constexpr int FC = 16;
+
+struct FpnOutParams {
+    const float* inner;        // (B, H, W, 16) fp32 — levels fed by the lateral GEMM; null when from_raw
+    const float* raw;          // (B, H, W, CIN) fp32 raw input (finest level with skip link)
+    const float* lat_w;        // [16][CIN] lateral weights of the raw level
+    const float* lat_b;        // [16]
+    const float* coarse;       // (B, Hc, Wc, 16) fp32 inner map of the next coarser level (top-down), or null
+    const float* w;            // [9][16 out][16 in] 3x3 weights
+    const float* bias;         // [16]
+    const float* pos_y;        // (H, 16)
+    const float* pos_x;        // (W, 16)
+    float* pyramid;            // (B, S, 16)
+    long long S, start;
+    int H, W, Hc, Wc;
+};
+
+__device__ __forceinline__ int nearest_src(int dst, int in_size, int out_size) {
+    // torch 'nearest': src = min(floor(dst * (float(in) / out)), in - 1)
+    const float scale = (float)in_size / (float)out_size;
+    const int s = (int)floorf((float)dst * scale);
+    return s < in_size - 1 ? s : in_size - 1;
+}
+
+template <int CIN>   // CIN == 0: inner map comes from global memory
+__global__ void __launch_bounds__(256)
+fpn_output_kernel(const FpnOutParams prm) {
+    __shared__ float4 s_in[4][FPN_PH * FPN_PW];     // channel planes of the halo tile
+    __shared__ __align__(16) float s_w[9 * FC * FC];
+    __shared__ float s_lat[FC * (CIN > 0 ? CIN : 1) + FC];
+    const int b = blockIdx.z;
+    const int p0 = blockIdx.y * FPN_TH, q0 = blockIdx.x * FPN_TW;
+    const int tid = threadIdx.x;
+    const int H = prm.H, W = prm.W;
+    for (int i = tid; i < 9 * FC * FC / 4; i += 256)
+        reinterpret_cast<float4*>(s_w)[i] = __ldg(reinterpret_cast<const float4*>(prm.w) + i);
+    if (CIN > 0) {
+        for (int i = tid; i < FC * CIN; i += 256) s_lat[i] = __ldg(prm.lat_w + i);
+        if (tid < FC) s_lat[FC * CIN + tid] = __ldg(prm.lat_b + tid);
+        __syncthreads();
+    }
+    // halo tile of the "inner" map (zero outside the image: the 3x3 conv pads with zeros)
+    for (int i = tid; i < FPN_PH * FPN_PW; i += 256) {
+        const int ph = i / FPN_PW, pw = i % FPN_PW;
+        const int hh = p0 - 1 + ph, ww = q0 - 1 + pw;
+        float v[FC];
+#pragma unroll
+        for (int c = 0; c < FC; ++c) v[c] = 0.0f;
+        if (hh >= 0 && hh < H && ww >= 0 && ww < W) {
+            if (CIN > 0) {
+                float xin[CIN > 0 ? CIN : 1];
+                const float* xp = prm.raw + (((long long)b * H + hh) * W + ww) * CIN;
+#pragma unroll
+                for (int c = 0; c < CIN; ++c) xin[c] = __ldg(xp + c);
+#pragma unroll
+                for (int o = 0; o < FC; ++o) {
+                    float a = s_lat[FC * CIN + o];
+#pragma unroll
+                    for (int c = 0; c < CIN; ++c) a = fmaf(s_lat[o * CIN + c], xin[c], a);
+                    v[o] = a;
+                }
+                if (prm.coarse) {
+                    const int hc = nearest_src(hh, prm.Hc, H), wc = nearest_src(ww, prm.Wc, W);
+                    const float4* cp = reinterpret_cast<const float4*>(prm.coarse + (((long long)b * prm.Hc + hc) * prm.Wc + wc) * FC);
+#pragma unroll
+                    for (int c4 = 0; c4 < 4; ++c4) {
+                        const float4 f = __ldg(cp + c4);
+                        v[4 * c4] += f.x; v[4 * c4 + 1] += f.y; v[4 * c4 + 2] += f.z; v[4 * c4 + 3] += f.w;
+                    }
+                }
+            } else {
+                const float4* ip = reinterpret_cast<const float4*>(prm.inner + (((long long)b * H + hh) * W + ww) * FC);
+#pragma unroll
+                for (int c4 = 0; c4 < 4; ++c4) {
+                    const float4 f = __ldg(ip + c4);
+                    v[4 * c4] = f.x; v[4 * c4 + 1] = f.y; v[4 * c4 + 2] = f.z; v[4 * c4 + 3] = f.w;
+                }
+            }
+        }
+#pragma unroll
+        for (int c4 = 0; c4 < 4; ++c4) s_in[c4][i] = make_float4(v[4 * c4], v[4 * c4 + 1], v[4 * c4 + 2], v[4 * c4 + 3]);
+    }
+    __syncthreads();
+
+    const int ty = tid / FPN_TW, tx = tid % FPN_TW;
+    float acc[FC];
+#pragma unroll
+    for (int o = 0; o < FC; ++o) acc[o] = __ldg(prm.bias + o);
+#pragma unroll 1
+    for (int tap = 0; tap < 9; ++tap) {
+        const int r = tap / 3, s = tap % 3;
+        const int pi = (ty + r) * FPN_PW + tx + s;
+        float in[FC];
+#pragma unroll
+        for (int c4 = 0; c4 < 4; ++c4) {
+            const float4 f = s_in[c4][pi];
+            in[4 * c4] = f.x; in[4 * c4 + 1] = f.y; in[4 * c4 + 2] = f.z; in[4 * c4 + 3] = f.w;
+        }
+        const float4* w4 = reinterpret_cast<const float4*>(s_w + tap * FC * FC);
+#pragma unroll
+        for (int o = 0; o < FC; ++o) {
+            float a = acc[o];
+#pragma unroll
+            for (int c4 = 0; c4 < 4; ++c4) {
+                const float4 wv = w4[o * 4 + c4];
+                a = fmaf(wv.x, in[4 * c4], a);
+                a = fmaf(wv.y, in[4 * c4 + 1], a);
+                a = fmaf(wv.z, in[4 * c4 + 2], a);
+                a = fmaf(wv.w, in[4 * c4 + 3], a);
+            }
+            acc[o] = a;
+        }
+    }
+    const int p = p0 + ty, q = q0 + tx;
+    if (p < H && q < W) {
+        const float4* px = reinterpret_cast<const float4*>(prm.pos_x + (long long)q * FC);
+        const float4* py = reinterpret_cast<const float4*>(prm.pos_y + (long long)p * FC);
+        float4* o = reinterpret_cast<float4*>(prm.pyramid + ((long long)b * prm.S + prm.start + (long long)p * W + q) * FC);
+#pragma unroll
+        for (int c4 = 0; c4 < 4; ++c4) {
+            const float4 a = __ldg(px + c4), c = __ldg(py + c4);
+            // reference order: feat += pos_x; feat += pos_y (sinusoidal.py:107-108)
+            o[c4] = make_float4((acc[4 * c4] + a.x) + c.x, (acc[4 * c4 + 1] + a.y) + c.y,
+                                (acc[4 * c4 + 2] + a.z) + c.z, (acc[4 * c4 + 3] + a.w) + c.w);
+        }
+    }
+}
+
+}  // namespace
+}  // namespace dpft
+
+using namespace dpft;
+
+extern "C" int dpft_stem_conv7x7_forward(const float* x, const float* w, const float* bias, void* y, int B, int H, int W,
+                                         int Cin, void* stream) {
+    DPFT_REQUIRE(x && w && bias && y, "stem: null pointer");
+    DPFT_REQUIRE(Cin == 3 || Cin == 6, "stem: Cin=%d (3 or 6 supported)", Cin);
+    DPFT_REQUIRE(B > 0 && H > 0 && W > 0, "stem: bad size");
+    const int P = (H - 1) / 2 + 1, Q = (W - 1) / 2 + 1;
+    const dim3 grid((Q + STEM_TW - 1) / STEM_TW, (P + STEM_TH - 1) / STEM_TH, B);
+    const size_t smem = sizeof(float) * (49 * Cin * STEM_COUT + STEM_PH * STEM_PW * Cin);
+    cudaStream_t s = (cudaStream_t)stream;
+    int st;
+    if (Cin == 3) {
+        st = cuda_status(cudaFuncSetAttribute(stem_conv7x7_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "stem attr");
+        if (st) return st;
+        stem_conv7x7_kernel<3><<<grid, 256, smem, s>>>(x, w, bias, (__nv_bfloat16*)y, H, W, P, Q);
+    } else {
+        st = cuda_status(cudaFuncSetAttribute(stem_conv7x7_kernel<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "stem attr");
+        if (st) return st;
+        stem_conv7x7_kernel<6><<<grid, 256, smem, s>>>(x, w, bias, (__nv_bfloat16*)y, H, W, P, Q);
+    }
+    DPFT_LAUNCH_CHECK("stem_conv7x7_kernel");
+    return DPFT_OK;
+}
+
+extern "C" int dpft_maxpool3x3s2_nhwc_bf16(const void* x, void* y, int B, int H, int W, int C, void* stream) {
+    DPFT_REQUIRE(x && y, "maxpool: null pointer");
+    DPFT_REQUIRE(C % 8 == 0 && B > 0 && H > 0 && W > 0, "maxpool: C=%d must be a multiple of 8", C);
+    const int P = (H - 1) / 2 + 1, Q = (W - 1) / 2 + 1;
+    const long long total = (long long)B * P * Q * (C / 8);
+    maxpool3x3s2_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+        (const __nv_bfloat16*)x, (__nv_bfloat16*)y, B, H, W, C / 8, P, Q);
+    DPFT_LAUNCH_CHECK("maxpool3x3s2_kernel");
+    return DPFT_OK;
+}
+
+extern "C" int dpft_fpn_output_forward(const float* inner, const float* raw, int raw_channels, const float* lat_w,
+                                       const float* lat_b, const float* coarse, int Hc, int Wc, const float* w,
+                                       const float* bias, const float* pos_y, const float* pos_x, float* pyramid,
+                                       long long S, long long start, int B, int H, int W, void* stream) {
+    DPFT_REQUIRE(w && bias && pos_y && pos_x && pyramid, "fpn_output: null pointer");
+    DPFT_REQUIRE((inner != nullptr) != (raw != nullptr), "fpn_output: exactly one of inner / raw must be given");
+    DPFT_REQUIRE(B > 0 && H > 0 && W > 0, "fpn_output: bad size");
+    FpnOutParams prm{inner, raw, lat_w, lat_b, coarse, w, bias, pos_y, pos_x, pyramid, S, start, H, W, Hc, Wc};
+    const dim3 grid((W + FPN_TW - 1) / FPN_TW, (H + FPN_TH - 1) / FPN_TH, B);
+    cudaStream_t s = (cudaStream_t)stream;
+    if (inner) {
+        fpn_output_kernel<0><<<grid, 256, 0, s>>>(prm);
+    } else {
+        DPFT_REQUIRE(lat_w && lat_b, "fpn_output: lateral weights needed for the raw level");
+        DPFT_REQUIRE(coarse == nullptr || (Hc > 0 && Wc > 0), "fpn_output: bad coarse size");
+        if (raw_channels == 3) fpn_output_kernel<3><<<grid, 256, 0, s>>>(prm);
+        else if (raw_channels == 6) fpn_output_kernel<6><<<grid, 256, 0, s>>>(prm);
+        else { set_error("fpn_output: raw_channels=%d (3 or 6 supported)", raw_channels); return DPFT_ERR_UNSUPPORTED; }
+    }
+    DPFT_LAUNCH_CHECK("fpn_output_kernel");
+    return DPFT_OK;
+}

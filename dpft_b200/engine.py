@@ -17,6 +17,7 @@ import torch
 
 from . import decoder as dec
 from . import native
+from .features import NativeView
 from .models.fuser import FeaturePyramid, IMPFusion
 from .models.querent import DataAgnosticStaticQueries
 
@@ -43,6 +44,13 @@ class FusedEngine:
             self.layer_w.append([dec.pack_layer(mp.ml_fusion_layers[f"ms_deform_attn{v}"]).to(self.device)
                                  for v in range(self.V)])
             self.head_w.append(dec.pack_head(mp.reduction_layer, fuser.heads[it], fuser.reduction).to(self.device))
+        # native bf16 feature path per view where the configuration allows it (model.native_features switches it)
+        self.views: List[Optional[NativeView]] = []
+        for name in model.inputs:
+            why = NativeView.ineligible_reason(model.backbones[name], model.necks[name], model.embeddings[name],
+                                               model.skiplinks[name])
+            self.views.append(NativeView(model.backbones[name], model.necks[name], model.embeddings[name],
+                                         model.skiplinks[name], self.device) if why is None else None)
         self.query = fuser.query.detach().float().contiguous()
         self.pos = fuser.query_embedding.weight.detach().float().contiguous()
         self._param_version = self._version(model)
@@ -50,7 +58,7 @@ class FusedEngine:
     # -- construction ---------------------------------------------------------------------------------------------
     @staticmethod
     def _version(model) -> int:
-        return sum(p._version for p in model.fuser.parameters())
+        return sum(p._version for p in model.parameters()) + sum(b._version for b in model.buffers())
 
     @staticmethod
     def ineligible_reason(model) -> Optional[str]:
@@ -93,8 +101,18 @@ class FusedEngine:
 
     # -- stage 1: feature pyramids --------------------------------------------------------------------------------
     def pyramids(self, batch: Dict[str, torch.Tensor]) -> List[FeaturePyramid]:
-        feats = self.model.extract_features(batch)
-        return [FeaturePyramid.from_levels(feats[name]) for name in self.model.inputs]
+        model = self.model
+        use_native = getattr(model, "native_features", True)
+        out: List[Optional[FeaturePyramid]] = []
+        torch_views = [n for n, nv in zip(model.inputs, self.views) if nv is None or not use_native]
+        feats = model.extract_features(batch, only=torch_views) if torch_views else {}
+        for name, nv in zip(model.inputs, self.views):
+            if nv is not None and use_native:
+                flat, shapes = nv.pyramid(batch[name])
+                out.append(FeaturePyramid(flat, shapes))
+            else:
+                out.append(FeaturePyramid.from_levels(feats[name]))
+        return out
 
     # -- stage 2: decoder -----------------------------------------------------------------------------------------
     def decode(self, batch: Dict[str, torch.Tensor], pyramids: List[FeaturePyramid]) -> "OrderedDict[str, torch.Tensor]":

@@ -1,0 +1,183 @@
+"""Native (sm_100a) feature path of one view: ResNet backbone -> FPN neck -> positional embedding -> pyramid.
+
+Replaces, for inference, what ``DPRT.forward`` does per input at reference src/dprt/models/dprt.py:219-231
+(``backbones[input]`` resnet.py:80-107, skip link, ``necks[input]`` fpn.py:70-83, ``embeddings[input]``
+sinusoidal.py:137-153) and the per-layer ``torch.cat`` of mpfusion.py:179: the result is ONE buffer
+(B, S, 16) fp32 per view, finest level first.
+
+Arithmetic: activations NHWC bf16 with fp32 accumulation (tcgen05), BatchNorm folded into the convolutions,
+FPN / embedding / pyramid in fp32.  Weights are re-laid-out once when the engine is built.
+"""
+from __future__ import annotations
+
+from typing import Dict, List, Optional, Tuple
+
+import torch
+from torch import nn
+
+from . import native
+from .conv import FoldedConv, fold_conv_bn
+from .models.backbone import Backbone
+from .models.embedding import MultiLevelSinusoidalEmbedding
+from .models.neck import FPN
+
+FC = 16
+
+
+def _lib():
+    return native.load_library()
+
+
+def stem_forward(x: torch.Tensor, w: torch.Tensor, bias: torch.Tensor) -> torch.Tensor:
+    B, H, W, Cin = x.shape
+    y = torch.empty((B, (H - 1) // 2 + 1, (W - 1) // 2 + 1, 64), dtype=torch.bfloat16, device=x.device)
+    st = _lib().dpft_stem_conv7x7_forward(native.ptr(x), native.ptr(w), native.ptr(bias), native.ptr(y), B, H, W, Cin,
+                                          native.stream_ptr(x.device))
+    native.check(st, "dpft_stem_conv7x7_forward")
+    native.count_launch()
+    return y
+
+
+def maxpool_forward(x: torch.Tensor) -> torch.Tensor:
+    B, H, W, Cc = x.shape
+    y = torch.empty((B, (H - 1) // 2 + 1, (W - 1) // 2 + 1, Cc), dtype=torch.bfloat16, device=x.device)
+    st = _lib().dpft_maxpool3x3s2_nhwc_bf16(native.ptr(x), native.ptr(y), B, H, W, Cc, native.stream_ptr(x.device))
+    native.check(st, "dpft_maxpool3x3s2_nhwc_bf16")
+    native.count_launch()
+    return y
+
+
+def lateral_forward(x: torch.Tensor, w: torch.Tensor, bias: torch.Tensor, coarse: Optional[torch.Tensor]) -> torch.Tensor:
+    B, H, W, Cin = x.shape
+    out = torch.empty((B, H, W, FC), dtype=torch.float32, device=x.device)
+    hc, wc = (coarse.shape[1], coarse.shape[2]) if coarse is not None else (0, 0)
+    st = _lib().dpft_fpn_lateral_forward(native.ptr(x), native.ptr(w), native.ptr(bias), native.ptr(coarse), hc, wc,
+                                         native.ptr(out), B, H, W, Cin, native.stream_ptr(x.device))
+    native.check(st, "dpft_fpn_lateral_forward")
+    native.count_launch()
+    return out
+
+
+def fpn_output_forward(pyramid: torch.Tensor, start: int, H: int, W: int, w: torch.Tensor, bias: torch.Tensor,
+                       pos_y: torch.Tensor, pos_x: torch.Tensor, inner: Optional[torch.Tensor] = None,
+                       raw: Optional[torch.Tensor] = None, lat_w: Optional[torch.Tensor] = None,
+                       lat_b: Optional[torch.Tensor] = None, coarse: Optional[torch.Tensor] = None) -> None:
+    B, S, _ = pyramid.shape
+    hc, wc = (coarse.shape[1], coarse.shape[2]) if coarse is not None else (0, 0)
+    raw_c = raw.shape[-1] if raw is not None else 0
+    st = _lib().dpft_fpn_output_forward(native.ptr(inner), native.ptr(raw), raw_c, native.ptr(lat_w), native.ptr(lat_b),
+                                        native.ptr(coarse), hc, wc, native.ptr(w), native.ptr(bias), native.ptr(pos_y),
+                                        native.ptr(pos_x), native.ptr(pyramid), S, start, B, H, W,
+                                        native.stream_ptr(pyramid.device))
+    native.check(st, "dpft_fpn_output_forward")
+    native.count_launch()
+
+
+class NativeView:
+    """Prepared weights + launch sequence of one input view."""
+
+    @staticmethod
+    def ineligible_reason(backbone, neck, embedding, skiplink: bool) -> Optional[str]:
+        if not isinstance(backbone, Backbone):
+            return f"backbone {type(backbone).__name__}"
+        if backbone.in_channels not in (3, 6):
+            return f"in_channels={backbone.in_channels}"
+        if not isinstance(backbone.body.bn1, nn.BatchNorm2d):
+            return "norm layer is not BatchNorm2d"
+        if not isinstance(neck, FPN) or neck.out_channels != FC:
+            return "neck is not a 16-channel FPN"
+        if not isinstance(embedding, MultiLevelSinusoidalEmbedding):
+            return "embedding is not sinusoidal"
+        if any(e.num_feats != FC for e in embedding.embedding_layers.values()):
+            return "embedding num_feats != 16"
+        n_levels = backbone.multi_scale + (1 if skiplink else 0)
+        if len(neck.in_channels_list) != n_levels or embedding.n_levels < n_levels:
+            return "neck / embedding level count does not match the backbone"
+        return None
+
+    def __init__(self, backbone: Backbone, neck: FPN, embedding: MultiLevelSinusoidalEmbedding, skiplink: bool, device):
+        self.device = device
+        self.skiplink = skiplink
+        self.cin = backbone.in_channels
+        body = backbone.body
+        # stem: fold bn1, and the 1x1 adjustment conv (linear, bias-free, so it commutes with zero padding)
+        w, b = fold_conv_bn(body.conv1, body.bn1)                          # (64, 7, 7, 3)
+        if self.cin != 3:
+            adj = backbone.adjustment_layer.weight.detach().float()[:, :, 0, 0].to(w.device)   # (3, Cin)
+            w = torch.einsum("orsc,cd->orsd", w, adj)
+        self.stem_w = w.permute(1, 2, 3, 0).contiguous().to(device)        # [7][7][Cin][64]
+        self.stem_b = b.to(device)
+        self.stages: List[List[Tuple[FoldedConv, FoldedConv, FoldedConv, Optional[FoldedConv]]]] = []
+        for s in range(body.n_stages):
+            blocks = []
+            for blk in getattr(body, f"layer{s + 1}"):
+                ds = FoldedConv(blk.downsample[0], blk.downsample[1], device) if blk.downsample is not None else None
+                blocks.append((FoldedConv(blk.conv1, blk.bn1, device), FoldedConv(blk.conv2, blk.bn2, device),
+                               FoldedConv(blk.conv3, blk.bn3, device), ds))
+            self.stages.append(blocks)
+        # FPN
+        fpn = neck.fpn
+        self.n_levels = len(neck.in_channels_list)
+        self.out_w, self.out_b, self.lat_w, self.lat_b = [], [], [], []
+        for i in range(self.n_levels):
+            lat = fpn.inner_blocks[i][0]
+            out = fpn.layer_blocks[i][0]
+            self.out_w.append(out.weight.detach().float().permute(2, 3, 0, 1).contiguous().to(device))   # [3][3][o][c]
+            self.out_b.append(out.bias.detach().float().contiguous().to(device))
+            if skiplink and i == 0:
+                self.lat_w.append(lat.weight.detach().float()[:, :, 0, 0].contiguous().to(device))        # [16][Cin]
+                self.lat_b.append(lat.bias.detach().float().contiguous().to(device))
+            else:
+                cin = lat.weight.shape[1]
+                wpad = torch.zeros(64, cin, dtype=torch.float32)
+                wpad[:FC] = lat.weight.detach().float()[:, :, 0, 0].cpu()
+                bpad = torch.zeros(64, dtype=torch.float32)
+                bpad[:FC] = lat.bias.detach().float().cpu()
+                self.lat_w.append(wpad.to(device=device, dtype=torch.bfloat16).contiguous())
+                self.lat_b.append(bpad.to(device))
+        self.embeddings = list(embedding.embedding_layers.values())
+        self._pos: Dict[Tuple[int, int, int], Tuple[torch.Tensor, torch.Tensor]] = {}
+
+    def _tables(self, level: int, H: int, W: int):
+        key = (level, H, W)
+        if key not in self._pos:
+            py, px = self.embeddings[level].tables(H, W, torch.float32, self.device)
+            self._pos[key] = (py.contiguous(), px.contiguous())
+        return self._pos[key]
+
+    def backbone(self, x: torch.Tensor) -> List[torch.Tensor]:
+        """x (B,H,W,Cin) fp32 -> [layer1, ...] NHWC bf16."""
+        y = maxpool_forward(stem_forward(x, self.stem_w, self.stem_b))
+        feats = []
+        for blocks in self.stages:
+            for c1, c2, c3, ds in blocks:
+                identity = ds(y, relu=False) if ds is not None else y
+                y = c3(c2(c1(y, relu=True), relu=True), relu=True, residual=identity)
+            feats.append(y)
+        return feats
+
+    def pyramid(self, x: torch.Tensor) -> Tuple[torch.Tensor, List[Tuple[int, int]]]:
+        x = x.contiguous()
+        B = x.shape[0]
+        feats = self.backbone(x)
+        shapes = ([(x.shape[1], x.shape[2])] if self.skiplink else []) + [(f.shape[1], f.shape[2]) for f in feats]
+        sizes = [h * w for h, w in shapes]
+        starts = [sum(sizes[:i]) for i in range(len(sizes))]
+        S = sum(sizes)
+        pyr = torch.empty((B, S, FC), dtype=torch.float32, device=x.device)
+        first = 1 if self.skiplink else 0
+        coarse = None
+        # top-down: coarsest level first
+        for li in range(self.n_levels - 1, first - 1, -1):
+            f = feats[li - first]
+            inner = lateral_forward(f, self.lat_w[li], self.lat_b[li], coarse)
+            H, W = shapes[li]
+            py, px = self._tables(li, H, W)
+            fpn_output_forward(pyr, starts[li], H, W, self.out_w[li], self.out_b[li], py, px, inner=inner)
+            coarse = inner
+        if self.skiplink:
+            H, W = shapes[0]
+            py, px = self._tables(0, H, W)
+            fpn_output_forward(pyr, 0, H, W, self.out_w[0], self.out_b[0], py, px, raw=x, lat_w=self.lat_w[0],
+                               lat_b=self.lat_b[0], coarse=coarse)
+        return pyr, shapes

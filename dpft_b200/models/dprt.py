@@ -55,6 +55,7 @@ class DPRT(nn.Module):
         self.fuser = fuser if fuser is not None else nn.Identity()
         self.head = head if head is not None else nn.Identity()   # registered but unused, like the reference (dprt.py:112)
         self.use_fused = True          # eval-mode fused pipeline switch (tests flip it to compare the two paths)
+        self.native_features = True    # fused pipeline: bf16 tcgen05 backbone/FPN (True) or torch fp32 features (False)
         self._engine = None
 
     @classmethod
@@ -75,9 +76,9 @@ class DPRT(nn.Module):
         return state
 
     # -- composed (module by module) path -------------------------------------------------------------------
-    def extract_features(self, batch: Dict[str, torch.Tensor]) -> Dict[str, "OrderedDict[str, torch.Tensor]"]:
+    def extract_features(self, batch: Dict[str, torch.Tensor], only=None) -> Dict[str, "OrderedDict[str, torch.Tensor]"]:
         feats = {}
-        for name in self.inputs:
+        for name in (self.inputs if only is None else only):
             f = self.backbones[name](batch[name])
             if self.skiplinks[name]:
                 f = OrderedDict([("0", batch[name])] + list(f.items()))

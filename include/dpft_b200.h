@@ -95,6 +95,42 @@ DPFT_API int dpft_conv2d_nhwc_bf16(const void* x, const void* w, const float* bi
                                    int block_n, void* stream);
 
 /*
+ * ResNet stem: [1x1 adjustment conv (radar, 6 -> 3, resnet.py:47-51) folded into] conv1 7x7 stride 2 pad 3 + BatchNorm
+ * (folded) + ReLU, reference src/dprt/models/backbones/resnet.py:98-101 (torchvision conv1/bn1/relu).
+ *   x (B, H, W, Cin) f32 NHWC, Cin = 3 or 6, raw 0..255 values;  w [7][7][Cin][64] f32;  bias [64] f32
+ *   y (B, P, Q, 64) bf16, P = (H-1)/2+1, Q = (W-1)/2+1
+ */
+DPFT_API int dpft_stem_conv7x7_forward(const float* x, const float* w, const float* bias, void* y, int B, int H, int W,
+                                       int Cin, void* stream);
+
+/* torchvision ResNet maxpool (kernel 3, stride 2, padding 1), NHWC bf16, C % 8 == 0.  y (B, (H-1)/2+1, (W-1)/2+1, C). */
+DPFT_API int dpft_maxpool3x3s2_nhwc_bf16(const void* x, void* y, int B, int H, int W, int C, void* stream);
+
+/*
+ * FPN lateral stage of one backbone level (reference src/dprt/models/necks/fpn.py:77 -> torchvision
+ * FeaturePyramidNetwork.forward: inner = conv1x1(x) + bias, + nearest-upsampled inner of the coarser level), as a
+ * tcgen05 GEMM with a 16-channel fp32 epilogue.
+ *   x (B, H, W, Cin) bf16, Cin % 64 == 0;  w [64][Cin] bf16 (rows 16..63 zero);  bias [64] f32 (16 used)
+ *   coarse (B, Hc, Wc, 16) f32 or NULL;  out (B, H, W, 16) f32
+ */
+DPFT_API int dpft_fpn_lateral_forward(const void* x, const void* w, const float* bias, const float* coarse, int Hc, int Wc,
+                                      float* out, int B, int H, int W, int Cin, void* stream);
+
+/*
+ * FPN output stage of one level fused with the sinusoidal positional embedding, written into the view's pyramid:
+ *   pyramid[b, start + p*W + q, :] = conv3x3(inner)[b, p, q, :] + bias + pos_x[q, :] + pos_y[p, :]
+ * (fpn.py:77 layer_blocks; embeddings/sinusoidal.py:107-108; the (B, S, 16) layout of mpfusion.py:179).
+ * Either `inner` (B, H, W, 16) f32 is given (levels fed by dpft_fpn_lateral_forward), or `raw` (B, H, W, raw_channels)
+ * f32 with the lateral weights lat_w [16][raw_channels], lat_b [16] and the coarser inner map `coarse` (may be NULL):
+ * then inner = lat_w raw + lat_b + nearest-upsampled coarse is formed on the fly (skip-link level, dprt.py:222-225).
+ *   w [3][3][16 out][16 in] f32;  bias [16];  pos_y (H, 16), pos_x (W, 16) f32
+ */
+DPFT_API int dpft_fpn_output_forward(const float* inner, const float* raw, int raw_channels, const float* lat_w,
+                                     const float* lat_b, const float* coarse, int Hc, int Wc, const float* w,
+                                     const float* bias, const float* pos_y, const float* pos_x, float* pyramid,
+                                     long long S, long long start, int B, int H, int W, void* stream);
+
+/*
  * Fused query decoder (inference), d_model = 16, 8 heads.
  *
  * dpft_decoder_layer_forward runs, for every (sample, view), one whole MLFusion layer of the reference

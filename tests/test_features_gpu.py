@@ -1,0 +1,109 @@
+"""Native feature path (stem, maxpool, tcgen05 bottlenecks, FPN + positional embedding) against the plain PyTorch fp32
+modules of the same model.  bf16 activations: tolerance 1e-2 rel (north_star's bf16 bar) unless noted."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+from dpft_b200 import configs, models, synthetic
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+@pytest.fixture(autouse=True)
+def _strict_fp32():
+    old = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32)
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    yield
+    torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = old
+
+
+def _rel(a, b):
+    return float((a.float() - b.float()).abs().max() / b.float().abs().max().clamp_min(1e-12))
+
+
+def _model(name, seed=3):
+    cfg = synthetic.offline_config(configs.make_config(name))
+    m = models.build("dprt", cfg).eval()
+    m.load_state_dict(synthetic.seeded_state_dict(m.state_dict(), seed=seed))
+    return cfg, m.to(DEV)
+
+
+@pytest.mark.parametrize("name,view,size", [("kradar_camera_mono", "camera_mono", (2, 70, 101, 3)),
+                                            ("kradar_radar_bev", "radar_bev", (2, 64, 107, 6)),
+                                            ("kradar_radar_front", "radar_front", (1, 37, 107, 6))])
+def test_stem_and_maxpool(name, view, size):
+    from dpft_b200 import features
+    from dpft_b200.features import NativeView
+    cfg, m = _model(name)
+    nv = NativeView(m.backbones[view], m.necks[view], m.embeddings[view], True, DEV)
+    x = torch.rand(*size, device=DEV) * 255.0
+    bb = m.backbones[view]
+    with torch.no_grad():
+        t = bb.adjustment_layer(x.movedim(-1, 1))
+        t = F.relu(bb.body.bn1(bb.body.conv1(t)))
+        want_stem = t.movedim(1, -1)
+        want_pool = F.max_pool2d(t, 3, 2, 1).movedim(1, -1)
+    got_stem = features.stem_forward(x, nv.stem_w, nv.stem_b)
+    assert got_stem.shape == want_stem.shape
+    assert _rel(got_stem, want_stem) < 1e-2
+    got_pool = features.maxpool_forward(got_stem)
+    assert got_pool.shape == want_pool.shape
+    ref_pool = F.max_pool2d(got_stem.float().movedim(-1, 1), 3, 2, 1).movedim(1, -1)
+    assert torch.equal(got_pool.float(), ref_pool)                      # max is exact
+
+
+@pytest.mark.parametrize("name,view,size", [("kradar_radar_bev", "radar_bev", (2, 64, 107, 6)),
+                                            ("kradar_radar_front", "radar_front", (2, 37, 107, 6)),
+                                            ("kradar_camera_mono", "camera_mono", (1, 90, 160, 3))])
+def test_backbone_and_pyramid(name, view, size):
+    from dpft_b200.features import NativeView
+    from dpft_b200.models.fuser import FeaturePyramid
+    cfg, m = _model(name)
+    nv = NativeView(m.backbones[view], m.necks[view], m.embeddings[view], True, DEV)
+    x = torch.rand(*size, device=DEV) * 255.0
+    with torch.no_grad():
+        want_feats = m.backbones[view](x)
+        want_pyr = FeaturePyramid.from_levels(m.extract_features({view: x})[view])
+    got_feats = nv.backbone(x)
+    for g, (k, w) in zip(got_feats, want_feats.items()):
+        assert g.shape == w.shape, k
+        assert _rel(g, w) < 2e-2, (k, _rel(g, w))
+    flat, shapes = nv.pyramid(x)
+    assert shapes == want_pyr.shapes and flat.shape == want_pyr.flat.shape
+    assert _rel(flat, want_pyr.flat) < 2e-2, _rel(flat, want_pyr.flat)
+
+
+def test_fpn_stages_in_isolation():
+    """lateral GEMM + top-down + 3x3 + positional embedding against torch on the SAME bf16-rounded features (tight)."""
+    from dpft_b200 import features
+    from dpft_b200.features import NativeView
+    cfg, m = _model("kradar_radar_bev")
+    view = "radar_bev"
+    nv = NativeView(m.backbones[view], m.necks[view], m.embeddings[view], True, DEV)
+    g = torch.Generator(device=DEV).manual_seed(0)
+    B = 2
+    raw = torch.rand(B, 50, 37, 6, generator=g, device=DEV) * 255
+    f2 = torch.randn(B, 13, 10, 512, generator=g, device=DEV).bfloat16()
+    f3 = torch.randn(B, 7, 5, 1024, generator=g, device=DEV).bfloat16()
+    fpn = m.necks[view].fpn
+    with torch.no_grad():
+        i3 = fpn.inner_blocks[3](f3.float().movedim(-1, 1))
+        i2 = fpn.inner_blocks[2](f2.float().movedim(-1, 1)) + F.interpolate(i3, size=(13, 10), mode="nearest")
+        i0 = fpn.inner_blocks[0](raw.movedim(-1, 1)) + F.interpolate(i2, size=(50, 37), mode="nearest")
+        o2 = m.embeddings[view].embedding_layers["embedding2"](fpn.layer_blocks[2](i2).movedim(1, -1).contiguous())
+        o0 = m.embeddings[view].embedding_layers["embedding0"](fpn.layer_blocks[0](i0).movedim(1, -1).contiguous())
+    g3 = features.lateral_forward(f3, nv.lat_w[3], nv.lat_b[3], None)
+    g2 = features.lateral_forward(f2, nv.lat_w[2], nv.lat_b[2], g3)
+    assert _rel(g3, i3.movedim(1, -1)) < 1e-4
+    assert _rel(g2, i2.movedim(1, -1)) < 1e-4
+    S = 13 * 10 + 50 * 37
+    pyr = torch.zeros(B, S, 16, device=DEV)
+    py, px = nv._tables(2, 13, 10)
+    features.fpn_output_forward(pyr, 50 * 37, 13, 10, nv.out_w[2], nv.out_b[2], py, px, inner=g2)
+    py, px = nv._tables(0, 50, 37)
+    features.fpn_output_forward(pyr, 0, 50, 37, nv.out_w[0], nv.out_b[0], py, px, raw=raw, lat_w=nv.lat_w[0],
+                                lat_b=nv.lat_b[0], coarse=g2)
+    assert _rel(pyr[:, 50 * 37:], o2.flatten(1, 2)) < 1e-4
+    assert _rel(pyr[:, :50 * 37], o0.flatten(1, 2)) < 1e-4

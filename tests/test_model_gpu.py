@@ -31,19 +31,32 @@ def _model(cfg, seed):
     return model.to("cuda:0")
 
 
+TOL_BF16 = 1e-2      # north_star: 1e-2 rel for the bf16 path
+
+# (use_fused, native_features, tolerance): module-by-module fp32; fused decoder on fp32 torch features;
+# the full native pipeline (bf16 tcgen05 backbone + fused FPN + fused decoder)
+PATHS = {"composed_fp32": (False, False, TOL_FP32), "fused_decoder_fp32": (True, False, TOL_FP32),
+         "native_bf16": (True, True, TOL_BF16)}
+
+
 @pytest.mark.parametrize("name", CASES)
-@pytest.mark.parametrize("fused", [False, True])
-def test_eval_forward_matches_reference_golden(name, fused):
+@pytest.mark.parametrize("path", list(PATHS))
+def test_eval_forward_matches_reference_golden(name, path):
+    fused, native_feats, tol = PATHS[path]
     rec = load_golden(name)
     cfg, batch = case_setup(rec)
     model = _model(cfg, rec["weight_seed"])
-    model.use_fused = fused
+    model.use_fused, model.native_features = fused, native_feats
     with torch.no_grad():
         out = model({k: v.to("cuda:0") for k, v in batch.items()})
+    if fused:
+        assert model._engine is not None, "the fused engine was not built for a shipped configuration"
+        if native_feats:
+            assert all(v is not None for v in model._engine.views)
     assert list(out.keys()) == ["center", "size", "angle", "class"]
     for k, want in rec["outputs"].items():
         assert out[k].shape == want.shape
-        assert rel_err(out[k].cpu(), want) < TOL_FP32, (k, rel_err(out[k].cpu(), want))
+        assert rel_err(out[k].cpu(), want) < tol, (k, rel_err(out[k].cpu(), want))
 
 
 def test_train_step_gradients_match_oracle_path():
