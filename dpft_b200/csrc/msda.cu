@@ -98,10 +98,18 @@ msda_fwd_kernel(const T* __restrict__ value, const int64_t* __restrict__ shapes,
 #pragma unroll
     for (int k = 0; k < VEC; ++k) acc[k] = (A)0;
 
+    // The location / weight of sample i+split are fetched while sample i's four corner rows are in flight, so the
+    // dependent chain (location -> address -> corner load) is paid once, not per sample.
+    Pack<T, 2> xy_next = ldg_pack<T, 2>(locg + 2 * (sp < LP ? sp : 0));
+    T a_next = __ldg(attg + (sp < LP ? sp : 0));
     for (int i = sp; i < LP; i += split) {
         const int l = i / P;
-        const Pack<T, 2> xy = ldg_pack<T, 2>(locg + 2 * i);
-        const A a = to_acc<T>(__ldg(attg + i));
+        const Pack<T, 2> xy = xy_next;
+        const A a = to_acc<T>(a_next);
+        if (i + split < LP) {
+            xy_next = ldg_pack<T, 2>(locg + 2 * (i + split));
+            a_next = __ldg(attg + i + split);
+        }
         const int H = lv.h[l], W = lv.w[l];
         const Footprint<A> f = footprint<A>(to_acc<T>(xy.v[0]), to_acc<T>(xy.v[1]), H, W);
         const T* vl = vb + lv.start[l] * MD;
@@ -206,13 +214,20 @@ msda_bwd_kernel(const T* __restrict__ value, const int64_t* __restrict__ shapes,
 
     // Uniform trip count over the warp: the CH-lane shuffles below need every lane present.
     const int trips = (LP + split - 1) >> split_log2;
+    Pack<T, 2> xy_next = ldg_pack<T, 2>(locg + 2 * (sp < LP ? sp : LP - 1));
+    T a_next = __ldg(attg + (sp < LP ? sp : LP - 1));
     for (int it = 0; it < trips; ++it) {
         const int i = (it << split_log2) + sp;
         const bool have = active && (i < LP);
         const int ic = (i < LP) ? i : LP - 1;
         const int l = ic / P;
-        const Pack<T, 2> xy = ldg_pack<T, 2>(locg + 2 * ic);
-        const A a = to_acc<T>(__ldg(attg + ic));
+        const Pack<T, 2> xy = xy_next;
+        const A a = to_acc<T>(a_next);
+        {
+            const int in = i + split < LP ? i + split : LP - 1;     // prefetch the next sample's location / weight
+            xy_next = ldg_pack<T, 2>(locg + 2 * in);
+            a_next = __ldg(attg + in);
+        }
         const int H = lv.h[l], W = lv.w[l];
         Footprint<A> f = footprint<A>(to_acc<T>(xy.v[0]), to_acc<T>(xy.v[1]), H, W);
         f.k00 = f.k00 && have; f.k01 = f.k01 && have; f.k10 = f.k10 && have; f.k11 = f.k11 && have;
