@@ -1,7 +1,7 @@
 """Host side of the sm_100a convolution kernels: BatchNorm folding, weight re-layout, launch wrappers.
 
 Inference form of the torchvision ResNet blocks the reference runs (src/dprt/models/backbones/resnet.py:101):
-``conv -> BatchNorm2d(eval) [-> + identity] [-> ReLU]`` becomes one call of ``dpft_conv2d_nhwc_bf16`` with
+``conv -> BatchNorm2d(eval) [-> + identity] [-> ReLU]`` becomes one call of ``dpft_conv2d_nhwc`` with
 ``w' = w * gamma / sqrt(var + eps)`` and ``bias' = beta - mean * gamma / sqrt(var + eps)``.
 """
 from __future__ import annotations
@@ -29,9 +29,9 @@ def fold_conv_bn(conv: nn.Conv2d, bn: Optional[nn.Module]) -> Tuple[torch.Tensor
 class FoldedConv:
     """One ``conv+bn`` of the backbone prepared for the tcgen05 kernel (weights bf16 [Cout,R,S,Cin], bias fp32)."""
 
-    def __init__(self, conv: nn.Conv2d, bn: Optional[nn.Module], device):
+    def __init__(self, conv: nn.Conv2d, bn: Optional[nn.Module], device, dtype: torch.dtype = torch.bfloat16):
         w, b = fold_conv_bn(conv, bn)
-        self.weight = w.to(device=device, dtype=torch.bfloat16).contiguous()
+        self.weight = w.to(device=device, dtype=dtype).contiguous()
         self.bias = b.to(device=device, dtype=torch.float32).contiguous()
         self.cout, self.r, self.s, self.cin = self.weight.shape
         self.stride = conv.stride[0]
@@ -42,33 +42,33 @@ class FoldedConv:
 
     def __call__(self, x: torch.Tensor, relu: bool, residual: Optional[torch.Tensor] = None,
                  out: Optional[torch.Tensor] = None, block_n: int = 0) -> torch.Tensor:
-        return conv2d_nhwc_bf16(x, self.weight, self.bias, self.stride, self.pad, relu, residual, out, block_n)
+        return conv2d_nhwc(x, self.weight, self.bias, self.stride, self.pad, relu, residual, out, block_n)
 
 
-def conv2d_nhwc_bf16(x: torch.Tensor, weight: torch.Tensor, bias: torch.Tensor, stride: int, pad: int, relu: bool,
+def conv2d_nhwc(x: torch.Tensor, weight: torch.Tensor, bias: torch.Tensor, stride: int, pad: int, relu: bool,
                      residual: Optional[torch.Tensor] = None, out: Optional[torch.Tensor] = None,
                      block_n: int = 0) -> torch.Tensor:
-    """x (B,H,W,Cin) bf16 contiguous, weight (Cout,R,S,Cin) bf16, bias (Cout,) fp32 -> (B,P,Q,Cout) bf16."""
+    """x (B,H,W,Cin) bf16|f16 contiguous, weight (Cout,R,S,Cin) same dtype, bias (Cout,) fp32 -> (B,P,Q,Cout)."""
     native.require_cuda(x, weight, bias)
-    if x.dtype != torch.bfloat16 or weight.dtype != torch.bfloat16 or bias.dtype != torch.float32:
-        raise RuntimeError("conv2d_nhwc_bf16: x and weight must be bfloat16 and bias float32")
+    if x.dtype not in (torch.bfloat16, torch.float16) or weight.dtype != x.dtype or bias.dtype != torch.float32:
+        raise RuntimeError("conv2d_nhwc: x and weight must share bfloat16 or float16, bias must be float32")
     if not (x.is_contiguous() and weight.is_contiguous() and bias.is_contiguous()):
-        raise RuntimeError("conv2d_nhwc_bf16: tensors have to be contiguous")
+        raise RuntimeError("conv2d_nhwc: tensors have to be contiguous")
     B, H, W, Cin = x.shape
     Cout, R, S, Cin_w = weight.shape
     if Cin_w != Cin:
-        raise RuntimeError(f"conv2d_nhwc_bf16: weight expects {Cin_w} input channels, got {Cin}")
+        raise RuntimeError(f"conv2d_nhwc: weight expects {Cin_w} input channels, got {Cin}")
     P, Q = (H + 2 * pad - R) // stride + 1, (W + 2 * pad - S) // stride + 1
     if out is None:
-        out = torch.empty((B, P, Q, Cout), dtype=torch.bfloat16, device=x.device)
+        out = torch.empty((B, P, Q, Cout), dtype=x.dtype, device=x.device)
     if residual is not None and (residual.shape != out.shape or not residual.is_contiguous()
-                                 or residual.dtype != torch.bfloat16):
-        raise RuntimeError("conv2d_nhwc_bf16: residual must be a contiguous bf16 tensor of the output shape")
+                                 or residual.dtype != x.dtype):
+        raise RuntimeError("conv2d_nhwc: residual must be a contiguous tensor of the output shape and dtype")
     lib = native.load_library()
     with torch.cuda.device(x.device):
-        st = lib.dpft_conv2d_nhwc_bf16(native.ptr(x), native.ptr(weight), native.ptr(bias), native.ptr(residual),
-                                       native.ptr(out), B, H, W, Cin, Cout, R, S, stride, pad, int(relu), block_n,
-                                       native.stream_ptr(x.device))
-    native.check(st, "dpft_conv2d_nhwc_bf16")
+        st = lib.dpft_conv2d_nhwc(native.ptr(x), native.ptr(weight), native.ptr(bias), native.ptr(residual),
+                                  native.ptr(out), B, H, W, Cin, Cout, R, S, stride, pad, int(relu), block_n,
+                                  native.dtype_code(x), native.stream_ptr(x.device))
+    native.check(st, "dpft_conv2d_nhwc")
     native.count_launch()
     return out

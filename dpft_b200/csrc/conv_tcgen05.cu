@@ -43,6 +43,7 @@ struct ConvParams {
     int stride, pad;
     int relu;
     int mode;
+    int is_f16;            // activations / weights are IEEE half instead of bfloat16
     int m_tiles, n_tiles;
     int q_tiles;            // kRowTiled: tiles per output row
     const float* bias;      // [N]
@@ -127,9 +128,10 @@ __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
     d |= (uint64_t)2 << 61;                  // SWIZZLE_128B
     return d;
 }
-// kind::f16 instruction descriptor: D = f32, A = B = bf16, both K-major, M = 128, N = n.
-__host__ __device__ constexpr uint32_t umma_idesc_bf16(int n) {
-    return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(BLOCK_M >> 4) << 24);
+// kind::f16 instruction descriptor: D = f32, A = B = bf16 (format 1) or f16 (format 0), both K-major, M = 128, N = n.
+__host__ __device__ constexpr uint32_t umma_idesc_16bit(int n, bool is_f16) {
+    const uint32_t fmt = is_f16 ? 0u : 1u;
+    return (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(BLOCK_M >> 4) << 24);
 }
 __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
     asm volatile(
@@ -268,7 +270,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         }
     } else if (warp == 1) {
         // ====================================== MMA issuer ======================================
-        constexpr uint32_t idesc = umma_idesc_bf16(BLOCK_N);
+        const uint32_t idesc = umma_idesc_16bit(BLOCK_N, prm.is_f16 != 0);
         int stage = 0;
         uint32_t phase = 0;
         int acc = 0;
@@ -368,10 +370,10 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                         for (int t = 0; t < 8; ++t) f[t] = __uint_as_float(v[j + t]) + __ldg(prm.bias + n0 + c + j + t);
                         if (rrow) {
                             const uint4 rv = *reinterpret_cast<const uint4*>(rrow + c + j);
-                            const __nv_bfloat162* rb = reinterpret_cast<const __nv_bfloat162*>(&rv);
 #pragma unroll
                             for (int t = 0; t < 4; ++t) {
-                                const float2 rf = __bfloat1622float2(rb[t]);
+                                const float2 rf = prm.is_f16 ? __half22float2(reinterpret_cast<const __half2*>(&rv)[t])
+                                                             : __bfloat1622float2(reinterpret_cast<const __nv_bfloat162*>(&rv)[t]);
                                 f[2 * t] += rf.x;
                                 f[2 * t + 1] += rf.y;
                             }
@@ -381,9 +383,17 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                             for (int t = 0; t < 8; ++t) f[t] = fmaxf(f[t], 0.0f);
                         }
                         uint4 ov;
-                        __nv_bfloat162* ob = reinterpret_cast<__nv_bfloat162*>(&ov);
+                        if (prm.is_f16) {
+                            __half2* oh = reinterpret_cast<__half2*>(&ov);
 #pragma unroll
-                        for (int t = 0; t < 4; ++t) ob[t] = __floats2bfloat162_rn(f[2 * t], f[2 * t + 1]);
+                            for (int t = 0; t < 4; ++t)   // saturate instead of overflowing to inf
+                                oh[t] = __floats2half2_rn(fminf(fmaxf(f[2 * t], -65504.0f), 65504.0f),
+                                                          fminf(fmaxf(f[2 * t + 1], -65504.0f), 65504.0f));
+                        } else {
+                            __nv_bfloat162* ob = reinterpret_cast<__nv_bfloat162*>(&ov);
+#pragma unroll
+                            for (int t = 0; t < 4; ++t) ob[t] = __floats2bfloat162_rn(f[2 * t], f[2 * t + 1]);
+                        }
                         *reinterpret_cast<uint4*>(orow + c + j) = ov;
                     }
                 }
@@ -437,12 +447,12 @@ int resolve_driver() {
 }
 
 int encode_2d(CUtensorMap* map, const void* base, uint64_t inner, uint64_t outer, uint64_t row_bytes, uint32_t box_inner,
-              uint32_t box_outer) {
+              uint32_t box_outer, bool is_f16) {
     cuuint64_t dims[2] = {inner, outer};
     cuuint64_t strides[1] = {row_bytes};
     cuuint32_t box[2] = {box_inner, box_outer};
     cuuint32_t estr[2] = {1, 1};
-    CUresult r = g_encode_tiled(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+    CUresult r = g_encode_tiled(map, is_f16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
                                 CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                                 CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled(2d) failed with CUresult %d", (int)r); return DPFT_ERR_INVALID_ARGUMENT; }
@@ -484,7 +494,9 @@ int pick_block_n(int Cout, int m_tiles, int want) {
 using namespace dpft;
 
 extern "C" int dpft_fpn_lateral_forward(const void* x, const void* w, const float* bias, const float* coarse, int Hc, int Wc,
-                                        float* out, int B, int H, int W, int Cin, void* stream) {
+                                        float* out, int B, int H, int W, int Cin, int dtype, void* stream) {
+    DPFT_REQUIRE(dtype == DPFT_BF16 || dtype == DPFT_F16, "fpn_lateral: dtype must be DPFT_BF16 or DPFT_F16");
+    const bool is_f16 = dtype == DPFT_F16;
     DPFT_REQUIRE(x && w && bias && out, "fpn_lateral: null pointer");
     DPFT_REQUIRE(B > 0 && H > 0 && W > 0 && Cin % 64 == 0, "fpn_lateral: bad size B=%d H=%d W=%d Cin=%d", B, H, W, Cin);
     DPFT_REQUIRE(coarse == nullptr || (Hc > 0 && Wc > 0), "fpn_lateral: bad coarse size");
@@ -494,19 +506,21 @@ extern "C" int dpft_fpn_lateral_forward(const void* x, const void* w, const floa
     prm.M = B * H * W; prm.N = 64; prm.P = H; prm.Q = W; prm.taps_s = 1; prm.cblocks = Cin / 64; prm.kblocks = prm.cblocks;
     prm.stride = 1; prm.pad = 0; prm.relu = 0; prm.mode = kTiled2D; prm.bias = bias;
     prm.m_tiles = (prm.M + BLOCK_M - 1) / BLOCK_M; prm.n_tiles = 1;
-    prm.out_f32 = out; prm.coarse = coarse; prm.Hc = Hc; prm.Wc = Wc;
+    prm.out_f32 = out; prm.coarse = coarse; prm.Hc = Hc; prm.Wc = Wc; prm.is_f16 = is_f16;
     CUtensorMap ta, tb;
-    st = encode_2d(&ta, x, (uint64_t)Cin, (uint64_t)prm.M, (uint64_t)Cin * 2, BLOCK_K, BLOCK_M);
+    st = encode_2d(&ta, x, (uint64_t)Cin, (uint64_t)prm.M, (uint64_t)Cin * 2, BLOCK_K, BLOCK_M, is_f16);
     if (st) return st;
-    st = encode_2d(&tb, w, (uint64_t)Cin, 64, (uint64_t)Cin * 2, BLOCK_K, 64);
+    st = encode_2d(&tb, w, (uint64_t)Cin, 64, (uint64_t)Cin * 2, BLOCK_K, 64, is_f16);
     if (st) return st;
     return launch<64, 8>(ta, tb, prm, (cudaStream_t)stream);
 }
 
-extern "C" int dpft_conv2d_nhwc_bf16(const void* x, const void* w, const float* bias, const void* residual, void* y,
-                                     int B, int H, int W, int Cin, int Cout, int R, int S, int stride, int pad, int relu,
-                                     int block_n, void* stream) {
+extern "C" int dpft_conv2d_nhwc(const void* x, const void* w, const float* bias, const void* residual, void* y,
+                                int B, int H, int W, int Cin, int Cout, int R, int S, int stride, int pad, int relu,
+                                int block_n, int dtype, void* stream) {
     DPFT_REQUIRE(x && w && bias && y, "conv2d: null pointer");
+    DPFT_REQUIRE(dtype == DPFT_BF16 || dtype == DPFT_F16, "conv2d: dtype must be DPFT_BF16 or DPFT_F16");
+    const bool is_f16 = dtype == DPFT_F16;
     DPFT_REQUIRE(B > 0 && H > 0 && W > 0, "conv2d: bad input size %dx%dx%d", B, H, W);
     DPFT_REQUIRE(Cin % 64 == 0 && Cout % 64 == 0, "conv2d: Cin=%d and Cout=%d must be multiples of 64", Cin, Cout);
     DPFT_REQUIRE(R >= 1 && S >= 1 && R <= 16 && S <= 16 && stride >= 1 && stride <= 8 && pad >= 0 && pad < 16,
@@ -518,7 +532,7 @@ extern "C" int dpft_conv2d_nhwc_bf16(const void* x, const void* w, const float* 
     DPFT_REQUIRE(P > 0 && Q > 0, "conv2d: empty output");
     ConvParams prm{};
     prm.M = B * P * Q; prm.N = Cout; prm.P = P; prm.Q = Q; prm.taps_s = S; prm.cblocks = Cin / 64;
-    prm.kblocks = R * S * prm.cblocks; prm.stride = stride; prm.pad = pad; prm.relu = relu;
+    prm.kblocks = R * S * prm.cblocks; prm.stride = stride; prm.pad = pad; prm.relu = relu; prm.is_f16 = is_f16;
     prm.bias = bias; prm.residual = (const __nv_bfloat16*)residual; prm.out = (__nv_bfloat16*)y;
     prm.m_tiles = (prm.M + BLOCK_M - 1) / BLOCK_M; prm.q_tiles = 0;
     const int bn = pick_block_n(Cout, prm.m_tiles, block_n);
@@ -528,7 +542,7 @@ extern "C" int dpft_conv2d_nhwc_bf16(const void* x, const void* w, const float* 
     const bool pointwise = (R == 1 && S == 1 && stride == 1 && pad == 0);
     if (pointwise) {
         prm.mode = kTiled2D;
-        st = encode_2d(&ta, x, (uint64_t)Cin, (uint64_t)prm.M, (uint64_t)Cin * 2, BLOCK_K, BLOCK_M);
+        st = encode_2d(&ta, x, (uint64_t)Cin, (uint64_t)prm.M, (uint64_t)Cin * 2, BLOCK_K, BLOCK_M, is_f16);
         if (st) return st;
     } else {
         prm.mode = kIm2col;
@@ -537,7 +551,7 @@ extern "C" int dpft_conv2d_nhwc_bf16(const void* x, const void* w, const float* 
         int lower[2] = {-pad, -pad};
         int upper[2] = {pad - (S - 1), pad - (R - 1)};
         cuuint32_t estr[4] = {1, (cuuint32_t)stride, (cuuint32_t)stride, 1};
-        CUresult r = g_encode_im2col(&ta, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(x), dims, strides, lower, upper,
+        CUresult r = g_encode_im2col(&ta, is_f16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(x), dims, strides, lower, upper,
                                      BLOCK_K, BLOCK_M, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
                                      CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeIm2col failed with CUresult %d", (int)r); return DPFT_ERR_INVALID_ARGUMENT; }
@@ -545,7 +559,7 @@ extern "C" int dpft_conv2d_nhwc_bf16(const void* x, const void* w, const float* 
         if (g_driver_version <= 13010 && (uint64_t)B * H * W * Cin * 2 < 131072)
             reinterpret_cast<uint64_t*>(&ta)[1] &= ~(1ull << 21);
     }
-    st = encode_2d(&tb, w, (uint64_t)R * S * Cin, (uint64_t)Cout, (uint64_t)R * S * Cin * 2, BLOCK_K, bn);
+    st = encode_2d(&tb, w, (uint64_t)R * S * Cin, (uint64_t)Cout, (uint64_t)R * S * Cin * 2, BLOCK_K, bn, is_f16);
     if (st) return st;
     cudaStream_t s = (cudaStream_t)stream;
     if (bn == 256) return launch<256, 4>(ta, tb, prm, s);

@@ -14,6 +14,8 @@
 //                    full-resolution 16-channel "inner" map never touches HBM.
 //
 // All three are HBM-bound (N = 16 output channels, tiny K): coalesced 16-byte accesses, halo tiles in shared memory.
+#include <type_traits>
+
 #include "common.cuh"
 
 namespace dpft {
@@ -24,10 +26,10 @@ constexpr int STEM_TH = 8, STEM_TW = 16;             // output tile
 constexpr int STEM_PH = STEM_TH * 2 + 5, STEM_PW = STEM_TW * 2 + 5;   // input patch
 constexpr int STEM_COUT = 64;
 
-template <int CIN>
+template <int CIN, typename OT>
 __global__ void __launch_bounds__(256)
 stem_conv7x7_kernel(const float* __restrict__ x, const float* __restrict__ w /* [49*CIN][64] */,
-                    const float* __restrict__ bias, __nv_bfloat16* __restrict__ y, int H, int W, int P, int Q) {
+                    const float* __restrict__ bias, OT* __restrict__ y, int H, int W, int P, int Q) {
     extern __shared__ __align__(16) float smem[];
     float* s_w = smem;                               // [49*CIN][64]
     float* s_x = smem + 49 * CIN * STEM_COUT;        // [PH][PW][CIN]
@@ -75,22 +77,27 @@ stem_conv7x7_kernel(const float* __restrict__ x, const float* __restrict__ w /* 
     }
     const int p = p0 + ty, q = q0 + tx;
     if (p < P && q < Q) {
-        __nv_bfloat16* o = y + (((long long)b * P + p) * Q + q) * STEM_COUT + half * 32;
+        OT* o = y + (((long long)b * P + p) * Q + q) * STEM_COUT + half * 32;
 #pragma unroll
         for (int o8 = 0; o8 < 4; ++o8) {
             uint4 pk;
-            __nv_bfloat162* pb = reinterpret_cast<__nv_bfloat162*>(&pk);
 #pragma unroll
-            for (int t = 0; t < 4; ++t)
-                pb[t] = __floats2bfloat162_rn(fmaxf(acc[8 * o8 + 2 * t], 0.0f), fmaxf(acc[8 * o8 + 2 * t + 1], 0.0f));
+            for (int t = 0; t < 4; ++t) {
+                const float a0 = fmaxf(acc[8 * o8 + 2 * t], 0.0f), a1 = fmaxf(acc[8 * o8 + 2 * t + 1], 0.0f);
+                if constexpr (sizeof(OT) == 2 && std::is_same<OT, __half>::value)
+                    reinterpret_cast<__half2*>(&pk)[t] = __floats2half2_rn(fminf(a0, 65504.0f), fminf(a1, 65504.0f));
+                else
+                    reinterpret_cast<__nv_bfloat162*>(&pk)[t] = __floats2bfloat162_rn(a0, a1);
+            }
             reinterpret_cast<uint4*>(o)[o8] = pk;
         }
     }
 }
 
 // ------------------------------------------------------------------------------------------------------ maxpool
+template <typename T2>   // __nv_bfloat162 or __half2
 __global__ void __launch_bounds__(256)
-maxpool3x3s2_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ y, int B, int H, int W, int C8,
+maxpool3x3s2_kernel(const uint16_t* __restrict__ x, uint16_t* __restrict__ y, int B, int H, int W, int C8,
                     int P, int Q) {
     const long long idx = (long long)blockIdx.x * 256 + threadIdx.x;
     const long long total = (long long)B * P * Q * C8;
@@ -99,8 +106,10 @@ maxpool3x3s2_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restri
     const int q = (int)((idx / C8) % Q);
     const int p = (int)((idx / ((long long)C8 * Q)) % P);
     const int b = (int)(idx / ((long long)C8 * Q * P));
-    __nv_bfloat162 m[4];
-    const __nv_bfloat162 ninf = __floats2bfloat162_rn(-INFINITY, -INFINITY);
+    T2 m[4];
+    T2 ninf;
+    if constexpr (std::is_same<T2, __half2>::value) ninf = __floats2half2_rn(-INFINITY, -INFINITY);
+    else ninf = __floats2bfloat162_rn(-INFINITY, -INFINITY);
 #pragma unroll
     for (int t = 0; t < 4; ++t) m[t] = ninf;
 #pragma unroll
@@ -112,13 +121,13 @@ maxpool3x3s2_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restri
             const int ww = 2 * q - 1 + s;
             if (ww < 0 || ww >= W) continue;
             const uint4 v = __ldg(reinterpret_cast<const uint4*>(x + (((long long)b * H + hh) * W + ww) * C8 * 8) + c8);
-            const __nv_bfloat162* vb = reinterpret_cast<const __nv_bfloat162*>(&v);
+            const T2* vb = reinterpret_cast<const T2*>(&v);
 #pragma unroll
             for (int t = 0; t < 4; ++t) m[t] = __hmax2(m[t], vb[t]);
         }
     }
     uint4 o;
-    __nv_bfloat162* ob = reinterpret_cast<__nv_bfloat162*>(&o);
+    T2* ob = reinterpret_cast<T2*>(&o);
 #pragma unroll
     for (int t = 0; t < 4; ++t) ob[t] = m[t];
     reinterpret_cast<uint4*>(y + (((long long)b * P + p) * Q + q) * C8 * 8)[c8] = o;
@@ -260,9 +269,20 @@ fpn_output_kernel(const FpnOutParams prm) {
 
 using namespace dpft;
 
+template <int CIN, typename OT>
+static int launch_stem(const float* x, const float* w, const float* bias, void* y, int H, int W, int P, int Q, dim3 grid,
+                       size_t smem, cudaStream_t s) {
+    auto kern = stem_conv7x7_kernel<CIN, OT>;
+    int st = cuda_status(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "stem attr");
+    if (st) return st;
+    kern<<<grid, 256, smem, s>>>(x, w, bias, (OT*)y, H, W, P, Q);
+    return 0;
+}
+
 extern "C" int dpft_stem_conv7x7_forward(const float* x, const float* w, const float* bias, void* y, int B, int H, int W,
-                                         int Cin, void* stream) {
+                                         int Cin, int dtype, void* stream) {
     DPFT_REQUIRE(x && w && bias && y, "stem: null pointer");
+    DPFT_REQUIRE(dtype == DPFT_BF16 || dtype == DPFT_F16, "stem: output dtype must be DPFT_BF16 or DPFT_F16");
     DPFT_REQUIRE(Cin == 3 || Cin == 6, "stem: Cin=%d (3 or 6 supported)", Cin);
     DPFT_REQUIRE(B > 0 && H > 0 && W > 0, "stem: bad size");
     const int P = (H - 1) / 2 + 1, Q = (W - 1) / 2 + 1;
@@ -270,26 +290,26 @@ extern "C" int dpft_stem_conv7x7_forward(const float* x, const float* w, const f
     const size_t smem = sizeof(float) * (49 * Cin * STEM_COUT + STEM_PH * STEM_PW * Cin);
     cudaStream_t s = (cudaStream_t)stream;
     int st;
-    if (Cin == 3) {
-        st = cuda_status(cudaFuncSetAttribute(stem_conv7x7_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "stem attr");
-        if (st) return st;
-        stem_conv7x7_kernel<3><<<grid, 256, smem, s>>>(x, w, bias, (__nv_bfloat16*)y, H, W, P, Q);
-    } else {
-        st = cuda_status(cudaFuncSetAttribute(stem_conv7x7_kernel<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "stem attr");
-        if (st) return st;
-        stem_conv7x7_kernel<6><<<grid, 256, smem, s>>>(x, w, bias, (__nv_bfloat16*)y, H, W, P, Q);
-    }
+    if (Cin == 3) st = dtype == DPFT_F16 ? launch_stem<3, __half>(x, w, bias, y, H, W, P, Q, grid, smem, s)
+                                         : launch_stem<3, __nv_bfloat16>(x, w, bias, y, H, W, P, Q, grid, smem, s);
+    else st = dtype == DPFT_F16 ? launch_stem<6, __half>(x, w, bias, y, H, W, P, Q, grid, smem, s)
+                                : launch_stem<6, __nv_bfloat16>(x, w, bias, y, H, W, P, Q, grid, smem, s);
+    if (st) return st;
     DPFT_LAUNCH_CHECK("stem_conv7x7_kernel");
     return DPFT_OK;
 }
 
-extern "C" int dpft_maxpool3x3s2_nhwc_bf16(const void* x, void* y, int B, int H, int W, int C, void* stream) {
+extern "C" int dpft_maxpool3x3s2_nhwc(const void* x, void* y, int B, int H, int W, int C, int dtype, void* stream) {
+    DPFT_REQUIRE(dtype == DPFT_BF16 || dtype == DPFT_F16, "maxpool: dtype must be DPFT_BF16 or DPFT_F16");
     DPFT_REQUIRE(x && y, "maxpool: null pointer");
     DPFT_REQUIRE(C % 8 == 0 && B > 0 && H > 0 && W > 0, "maxpool: C=%d must be a multiple of 8", C);
     const int P = (H - 1) / 2 + 1, Q = (W - 1) / 2 + 1;
     const long long total = (long long)B * P * Q * (C / 8);
-    maxpool3x3s2_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
-        (const __nv_bfloat16*)x, (__nv_bfloat16*)y, B, H, W, C / 8, P, Q);
+    const unsigned grid = (unsigned)((total + 255) / 256);
+    if (dtype == DPFT_F16)
+        maxpool3x3s2_kernel<__half2><<<grid, 256, 0, (cudaStream_t)stream>>>((const uint16_t*)x, (uint16_t*)y, B, H, W, C / 8, P, Q);
+    else
+        maxpool3x3s2_kernel<__nv_bfloat162><<<grid, 256, 0, (cudaStream_t)stream>>>((const uint16_t*)x, (uint16_t*)y, B, H, W, C / 8, P, Q);
     DPFT_LAUNCH_CHECK("maxpool3x3s2_kernel");
     return DPFT_OK;
 }

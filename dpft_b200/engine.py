@@ -44,13 +44,15 @@ class FusedEngine:
             self.layer_w.append([dec.pack_layer(mp.ml_fusion_layers[f"ms_deform_attn{v}"]).to(self.device)
                                  for v in range(self.V)])
             self.head_w.append(dec.pack_head(mp.reduction_layer, fuser.heads[it], fuser.reduction).to(self.device))
-        # native bf16 feature path per view where the configuration allows it (model.native_features switches it)
+        self.feature_dtype = getattr(model, "feature_dtype", torch.bfloat16)
+        # native 16-bit feature path per view where the configuration allows it (model.native_features switches it)
         self.views: List[Optional[NativeView]] = []
         for name in model.inputs:
             why = NativeView.ineligible_reason(model.backbones[name], model.necks[name], model.embeddings[name],
                                                model.skiplinks[name])
             self.views.append(NativeView(model.backbones[name], model.necks[name], model.embeddings[name],
-                                         model.skiplinks[name], self.device) if why is None else None)
+                                         model.skiplinks[name], self.device, self.feature_dtype)
+                              if why is None else None)
         self.query = fuser.query.detach().float().contiguous()
         self.pos = fuser.query_embedding.weight.detach().float().contiguous()
         self._param_version = self._version(model)
@@ -94,7 +96,8 @@ class FusedEngine:
         return cls(model)
 
     def accepts(self, batch: Dict[str, torch.Tensor]) -> bool:
-        if self._version(self.model) != self._param_version:     # parameters were updated: repack
+        if (self._version(self.model) != self._param_version
+                or getattr(self.model, "feature_dtype", torch.bfloat16) != self.feature_dtype):   # repack
             self.__init__(self.model)
         x = batch[self.model.inputs[0]]
         return x.is_cuda and x.dtype == torch.float32

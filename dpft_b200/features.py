@@ -28,11 +28,11 @@ def _lib():
     return native.load_library()
 
 
-def stem_forward(x: torch.Tensor, w: torch.Tensor, bias: torch.Tensor) -> torch.Tensor:
+def stem_forward(x: torch.Tensor, w: torch.Tensor, bias: torch.Tensor, dtype: torch.dtype = torch.bfloat16) -> torch.Tensor:
     B, H, W, Cin = x.shape
-    y = torch.empty((B, (H - 1) // 2 + 1, (W - 1) // 2 + 1, 64), dtype=torch.bfloat16, device=x.device)
+    y = torch.empty((B, (H - 1) // 2 + 1, (W - 1) // 2 + 1, 64), dtype=dtype, device=x.device)
     st = _lib().dpft_stem_conv7x7_forward(native.ptr(x), native.ptr(w), native.ptr(bias), native.ptr(y), B, H, W, Cin,
-                                          native.stream_ptr(x.device))
+                                          native.dtype_code(y), native.stream_ptr(x.device))
     native.check(st, "dpft_stem_conv7x7_forward")
     native.count_launch()
     return y
@@ -40,9 +40,10 @@ def stem_forward(x: torch.Tensor, w: torch.Tensor, bias: torch.Tensor) -> torch.
 
 def maxpool_forward(x: torch.Tensor) -> torch.Tensor:
     B, H, W, Cc = x.shape
-    y = torch.empty((B, (H - 1) // 2 + 1, (W - 1) // 2 + 1, Cc), dtype=torch.bfloat16, device=x.device)
-    st = _lib().dpft_maxpool3x3s2_nhwc_bf16(native.ptr(x), native.ptr(y), B, H, W, Cc, native.stream_ptr(x.device))
-    native.check(st, "dpft_maxpool3x3s2_nhwc_bf16")
+    y = torch.empty((B, (H - 1) // 2 + 1, (W - 1) // 2 + 1, Cc), dtype=x.dtype, device=x.device)
+    st = _lib().dpft_maxpool3x3s2_nhwc(native.ptr(x), native.ptr(y), B, H, W, Cc, native.dtype_code(x),
+                                       native.stream_ptr(x.device))
+    native.check(st, "dpft_maxpool3x3s2_nhwc")
     native.count_launch()
     return y
 
@@ -52,7 +53,7 @@ def lateral_forward(x: torch.Tensor, w: torch.Tensor, bias: torch.Tensor, coarse
     out = torch.empty((B, H, W, FC), dtype=torch.float32, device=x.device)
     hc, wc = (coarse.shape[1], coarse.shape[2]) if coarse is not None else (0, 0)
     st = _lib().dpft_fpn_lateral_forward(native.ptr(x), native.ptr(w), native.ptr(bias), native.ptr(coarse), hc, wc,
-                                         native.ptr(out), B, H, W, Cin, native.stream_ptr(x.device))
+                                         native.ptr(out), B, H, W, Cin, native.dtype_code(x), native.stream_ptr(x.device))
     native.check(st, "dpft_fpn_lateral_forward")
     native.count_launch()
     return out
@@ -95,8 +96,10 @@ class NativeView:
             return "neck / embedding level count does not match the backbone"
         return None
 
-    def __init__(self, backbone: Backbone, neck: FPN, embedding: MultiLevelSinusoidalEmbedding, skiplink: bool, device):
+    def __init__(self, backbone: Backbone, neck: FPN, embedding: MultiLevelSinusoidalEmbedding, skiplink: bool, device,
+                 dtype: torch.dtype = torch.bfloat16):
         self.device = device
+        self.dtype = dtype                                                 # activation / weight type of the backbone
         self.skiplink = skiplink
         self.cin = backbone.in_channels
         body = backbone.body
@@ -111,9 +114,10 @@ class NativeView:
         for s in range(body.n_stages):
             blocks = []
             for blk in getattr(body, f"layer{s + 1}"):
-                ds = FoldedConv(blk.downsample[0], blk.downsample[1], device) if blk.downsample is not None else None
-                blocks.append((FoldedConv(blk.conv1, blk.bn1, device), FoldedConv(blk.conv2, blk.bn2, device),
-                               FoldedConv(blk.conv3, blk.bn3, device), ds))
+                ds = (FoldedConv(blk.downsample[0], blk.downsample[1], device, dtype)
+                      if blk.downsample is not None else None)
+                blocks.append((FoldedConv(blk.conv1, blk.bn1, device, dtype), FoldedConv(blk.conv2, blk.bn2, device, dtype),
+                               FoldedConv(blk.conv3, blk.bn3, device, dtype), ds))
             self.stages.append(blocks)
         # FPN
         fpn = neck.fpn
@@ -133,7 +137,7 @@ class NativeView:
                 wpad[:FC] = lat.weight.detach().float()[:, :, 0, 0].cpu()
                 bpad = torch.zeros(64, dtype=torch.float32)
                 bpad[:FC] = lat.bias.detach().float().cpu()
-                self.lat_w.append(wpad.to(device=device, dtype=torch.bfloat16).contiguous())
+                self.lat_w.append(wpad.to(device=device, dtype=dtype).contiguous())
                 self.lat_b.append(bpad.to(device))
         self.embeddings = list(embedding.embedding_layers.values())
         self._pos: Dict[Tuple[int, int, int], Tuple[torch.Tensor, torch.Tensor]] = {}
@@ -147,7 +151,7 @@ class NativeView:
 
     def backbone(self, x: torch.Tensor) -> List[torch.Tensor]:
         """x (B,H,W,Cin) fp32 -> [layer1, ...] NHWC bf16."""
-        y = maxpool_forward(stem_forward(x, self.stem_w, self.stem_b))
+        y = maxpool_forward(stem_forward(x, self.stem_w, self.stem_b, self.dtype))
         feats = []
         for blocks in self.stages:
             for c1, c2, c3, ds in blocks:

@@ -55,7 +55,8 @@ class DPRT(nn.Module):
         self.fuser = fuser if fuser is not None else nn.Identity()
         self.head = head if head is not None else nn.Identity()   # registered but unused, like the reference (dprt.py:112)
         self.use_fused = True          # eval-mode fused pipeline switch (tests flip it to compare the two paths)
-        self.native_features = True    # fused pipeline: bf16 tcgen05 backbone/FPN (True) or torch fp32 features (False)
+        self.native_features = True    # fused pipeline: 16-bit tcgen05 backbone/FPN (True) or torch fp32 features (False)
+        self.feature_dtype = torch.bfloat16   # activation type of the native backbone: torch.bfloat16 or torch.float16
         self._engine = None
 
     @classmethod

@@ -79,7 +79,8 @@ DPFT_API int dpft_msda_backward(const void* value, const int64_t* shapes, const 
                        void* stream);
 
 /*
- * 2-d convolution + folded BatchNorm (+ residual) (+ ReLU), NHWC bf16, as a tcgen05 implicit GEMM.
+ * 2-d convolution + folded BatchNorm (+ residual) (+ ReLU), NHWC 16-bit (dtype = DPFT_BF16 or DPFT_F16; f16 outputs
+ * saturate at +-65504), fp32 accumulation, as a tcgen05 implicit GEMM.
  * Replaces the Conv2d/BatchNorm2d/ReLU/add launches of the torchvision Bottleneck blocks the reference runs at
  * src/dprt/models/backbones/resnet.py:101 (built at :54-55), in eval() form:
  *   y[b,p,q,n] = act( sum_{r,s,c} x[b, p*stride-pad+r, q*stride-pad+s, c] * w[n,r,s,c] + bias[n] (+ residual[b,p,q,n]) )
@@ -90,9 +91,9 @@ DPFT_API int dpft_msda_backward(const void* value, const int64_t* shapes, const 
  *   y        (B, P, Q, Cout)      bf16, P = (H+2*pad-R)/stride+1, Q likewise
  * block_n: 0 = choose, or 64 / 128 / 256 (output-channel tile; tests sweep it).
  */
-DPFT_API int dpft_conv2d_nhwc_bf16(const void* x, const void* w, const float* bias, const void* residual, void* y,
-                                   int B, int H, int W, int Cin, int Cout, int R, int S, int stride, int pad, int relu,
-                                   int block_n, void* stream);
+DPFT_API int dpft_conv2d_nhwc(const void* x, const void* w, const float* bias, const void* residual, void* y,
+                              int B, int H, int W, int Cin, int Cout, int R, int S, int stride, int pad, int relu,
+                              int block_n, int dtype, void* stream);
 
 /*
  * ResNet stem: [1x1 adjustment conv (radar, 6 -> 3, resnet.py:47-51) folded into] conv1 7x7 stride 2 pad 3 + BatchNorm
@@ -101,10 +102,10 @@ DPFT_API int dpft_conv2d_nhwc_bf16(const void* x, const void* w, const float* bi
  *   y (B, P, Q, 64) bf16, P = (H-1)/2+1, Q = (W-1)/2+1
  */
 DPFT_API int dpft_stem_conv7x7_forward(const float* x, const float* w, const float* bias, void* y, int B, int H, int W,
-                                       int Cin, void* stream);
+                                       int Cin, int dtype, void* stream);
 
 /* torchvision ResNet maxpool (kernel 3, stride 2, padding 1), NHWC bf16, C % 8 == 0.  y (B, (H-1)/2+1, (W-1)/2+1, C). */
-DPFT_API int dpft_maxpool3x3s2_nhwc_bf16(const void* x, void* y, int B, int H, int W, int C, void* stream);
+DPFT_API int dpft_maxpool3x3s2_nhwc(const void* x, void* y, int B, int H, int W, int C, int dtype, void* stream);
 
 /*
  * FPN lateral stage of one backbone level (reference src/dprt/models/necks/fpn.py:77 -> torchvision
@@ -114,7 +115,7 @@ DPFT_API int dpft_maxpool3x3s2_nhwc_bf16(const void* x, void* y, int B, int H, i
  *   coarse (B, Hc, Wc, 16) f32 or NULL;  out (B, H, W, 16) f32
  */
 DPFT_API int dpft_fpn_lateral_forward(const void* x, const void* w, const float* bias, const float* coarse, int Hc, int Wc,
-                                      float* out, int B, int H, int W, int Cin, void* stream);
+                                      float* out, int B, int H, int W, int Cin, int dtype, void* stream);
 
 /*
  * FPN output stage of one level fused with the sinusoidal positional embedding, written into the view's pyramid:

@@ -48,7 +48,7 @@ def test_conv_matches_torch_fp32(shape, block_n, relu, with_res):
     torch.backends.cudnn.allow_tf32 = False
     torch.backends.cuda.matmul.allow_tf32 = False
     want = _reference(x, w, bias, stride, pad, relu, res)
-    got = conv.conv2d_nhwc_bf16(x, w, bias, stride, pad, relu, res, block_n=block_n)
+    got = conv.conv2d_nhwc(x, w, bias, stride, pad, relu, res, block_n=block_n)
     torch.cuda.synchronize()
     assert got.shape == (B, P, Q, Cout) and got.dtype == torch.bfloat16
     err = (got.float() - want).abs().max().item()

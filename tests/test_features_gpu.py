@@ -88,16 +88,18 @@ def test_fpn_stages_in_isolation():
     f2 = torch.randn(B, 13, 10, 512, generator=g, device=DEV).bfloat16()
     f3 = torch.randn(B, 7, 5, 1024, generator=g, device=DEV).bfloat16()
     fpn = m.necks[view].fpn
+    g3 = features.lateral_forward(f3, nv.lat_w[3], nv.lat_b[3], None)
+    g2 = features.lateral_forward(f2, nv.lat_w[2], nv.lat_b[2], g3)
     with torch.no_grad():
         i3 = fpn.inner_blocks[3](f3.float().movedim(-1, 1))
         i2 = fpn.inner_blocks[2](f2.float().movedim(-1, 1)) + F.interpolate(i3, size=(13, 10), mode="nearest")
-        i0 = fpn.inner_blocks[0](raw.movedim(-1, 1)) + F.interpolate(i2, size=(50, 37), mode="nearest")
-        o2 = m.embeddings[view].embedding_layers["embedding2"](fpn.layer_blocks[2](i2).movedim(1, -1).contiguous())
+        # the 3x3 / raw-level stages are fp32: check them tightly on the kernel's own inner map
+        i2k = g2.movedim(-1, 1)
+        i0 = fpn.inner_blocks[0](raw.movedim(-1, 1)) + F.interpolate(i2k, size=(50, 37), mode="nearest")
+        o2 = m.embeddings[view].embedding_layers["embedding2"](fpn.layer_blocks[2](i2k).movedim(1, -1).contiguous())
         o0 = m.embeddings[view].embedding_layers["embedding0"](fpn.layer_blocks[0](i0).movedim(1, -1).contiguous())
-    g3 = features.lateral_forward(f3, nv.lat_w[3], nv.lat_b[3], None)
-    g2 = features.lateral_forward(f2, nv.lat_w[2], nv.lat_b[2], g3)
-    assert _rel(g3, i3.movedim(1, -1)) < 1e-4
-    assert _rel(g2, i2.movedim(1, -1)) < 1e-4
+    assert _rel(g3, i3.movedim(1, -1)) < 5e-3          # lateral weights are rounded to bf16 for the tensor cores
+    assert _rel(g2, i2.movedim(1, -1)) < 5e-3
     S = 13 * 10 + 50 * 37
     pyr = torch.zeros(B, S, 16, device=DEV)
     py, px = nv._tables(2, 13, 10)

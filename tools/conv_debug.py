@@ -32,7 +32,7 @@ x = torch.randn(B, H, W, Cin, generator=g, device=dev).bfloat16()
 w = (torch.randn(Cout, R, R, Cin, generator=g, device=dev) / (R * R * Cin) ** 0.5).bfloat16()
 bias = torch.randn(Cout, generator=g, device=dev)
 want = F.conv2d(x.float().permute(0, 3, 1, 2), w.float().permute(0, 3, 1, 2), bias, stride=stride, padding=pad).permute(0, 2, 3, 1)
-got = conv.conv2d_nhwc_bf16(x, w, bias, stride, pad, False, None, block_n=bn)
+got = conv.conv2d_nhwc(x, w, bias, stride, pad, False, None, block_n=bn)
 torch.cuda.synchronize()
 d = (got.float() - want).abs()
 res = {"case": name, "max_err": d.max().item(), "scale": want.abs().max().item(), "mean_err": d.mean().item(),
@@ -44,11 +44,11 @@ if res["frac_bad"] > 0:
     res["got0"] = got.flatten(0, 2)[0, :6].float().tolist(); res["want0"] = want.flatten(0, 2)[0, :6].tolist()
 # timing
 import time
-for _ in range(3): conv.conv2d_nhwc_bf16(x, w, bias, stride, pad, True, None, block_n=bn)
+for _ in range(3): conv.conv2d_nhwc(x, w, bias, stride, pad, True, None, block_n=bn)
 torch.cuda.synchronize()
 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 e0.record()
-for _ in range(10): conv.conv2d_nhwc_bf16(x, w, bias, stride, pad, True, None, block_n=bn)
+for _ in range(10): conv.conv2d_nhwc(x, w, bias, stride, pad, True, None, block_n=bn)
 e1.record(); e1.synchronize()
 ms = e0.elapsed_time(e1) / 10
 P = (H + 2 * pad - R) // stride + 1; Q = (W + 2 * pad - R) // stride + 1
