@@ -468,10 +468,14 @@ int launch_layer(const LayerParams& prm, cudaStream_t stream) {
     const int expected = IMG::fixed + prm.d_ffn * C + prm.d_ffn + C * prm.d_ffn + C;
     DPFT_REQUIRE(prm.weight_floats == expected, "decoder: packed layer image has %d floats, expected %d",
                  prm.weight_floats, expected);
-    auto kern_attr = decoder_layer_kernel<L, P>;
-    int st = cuda_status(cudaFuncSetAttribute(kern_attr, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem),
-                         "cudaFuncSetAttribute(decoder_layer_kernel)");
-    if (st) return st;
+    static size_t configured = 0;                      // raise the limit only when needed (never inside a graph replay)
+    if (smem > configured) {
+        auto kern_attr = decoder_layer_kernel<L, P>;
+        int st = cuda_status(cudaFuncSetAttribute(kern_attr, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem),
+                             "cudaFuncSetAttribute(decoder_layer_kernel)");
+        if (st) return st;
+        configured = smem;
+    }
     const int tiles = (prm.N + TQ - 1) / TQ;
     auto kern = decoder_layer_kernel<L, P>;
     kern<<<prm.B * prm.V * tiles, kThreads, smem, stream>>>(prm);
@@ -531,9 +535,13 @@ extern "C" int dpft_decoder_head_forward(const float* views, const float* weight
     HeadParams prm{views, weights, center_in, query_out, center_out, size_out, angle_out, class_out,
                    center_batch_stride, B, V, N, n_cls, reduction, weight_floats};
     const size_t smem = (size_t)weight_floats * 4;
-    int st = cuda_status(cudaFuncSetAttribute(decoder_head_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem),
-                         "cudaFuncSetAttribute(decoder_head_kernel)");
-    if (st) return st;
+    static size_t configured = 0;
+    if (smem > configured) {
+        int st = cuda_status(cudaFuncSetAttribute(decoder_head_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem),
+                             "cudaFuncSetAttribute(decoder_head_kernel)");
+        if (st) return st;
+        configured = smem;
+    }
     const long long total = (long long)B * N;
     decoder_head_kernel<<<(unsigned)((total + 127) / 128), 128, smem, (cudaStream_t)stream>>>(prm);
     DPFT_LAUNCH_CHECK("decoder_head_kernel");

@@ -273,8 +273,12 @@ template <int CIN, typename OT>
 static int launch_stem(const float* x, const float* w, const float* bias, void* y, int H, int W, int P, int Q, dim3 grid,
                        size_t smem, cudaStream_t s) {
     auto kern = stem_conv7x7_kernel<CIN, OT>;
-    int st = cuda_status(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "stem attr");
-    if (st) return st;
+    static bool configured = false;
+    if (!configured) {
+        int st = cuda_status(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "stem attr");
+        if (st) return st;
+        configured = true;
+    }
     kern<<<grid, 256, smem, s>>>(x, w, bias, (OT*)y, H, W, P, Q);
     return 0;
 }

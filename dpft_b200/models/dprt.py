@@ -56,7 +56,9 @@ class DPRT(nn.Module):
         self.head = head if head is not None else nn.Identity()   # registered but unused, like the reference (dprt.py:112)
         self.use_fused = True          # eval-mode fused pipeline switch (tests flip it to compare the two paths)
         self.native_features = True    # fused pipeline: 16-bit tcgen05 backbone/FPN (True) or torch fp32 features (False)
-        self.feature_dtype = torch.bfloat16   # activation type of the native backbone: torch.bfloat16 or torch.float16
+        self.feature_dtype = torch.float16    # activation type of the native backbone: torch.float16 (10-bit mantissa,
+                                              # outputs saturate at +-65504) or torch.bfloat16
+        self.use_cuda_graph = True     # fused pipeline: replay a captured graph once an input shape repeats
         self._engine = None
 
     @classmethod
