@@ -47,6 +47,10 @@ def parse():
     ap.add_argument("--cpu-sample", type=int, default=1, help="frames per CPU-baseline forward")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--small", action="store_true", help="debug: tiny inputs (NOT a valid bench number)")
+    ap.add_argument("--mode", default="infer", choices=["infer", "train"],
+                    help="infer: eval forward (headline).  train: fwd+bwd+gradient all-reduce+AdamW (BASELINE config 4)")
+    ap.add_argument("--dtype", default="f16", choices=["f16", "bf16", "f32"],
+                    help="activation type of the native backbone (f32 = fused decoder on torch fp32 features)")
     return ap.parse_args()
 
 
@@ -192,6 +196,66 @@ def msda_roofline(model, feats_flat, dev, hbm_peak, peak_src, reps=20):
             "shape": {"B": B, "N": N, "M": M, "D": D, "L": L, "P": P, "S": S, "dtype": str(value.dtype)}}
 
 
+def run_train(args, cfg, sizes, rank, world, dev):
+    """BASELINE config 4: data-parallel training step (fwd + bwd + flat-bucket NCCL all-reduce + AdamW), fp32 master
+    weights, module-by-module path with the native deformable-attention fwd/bwd; fixed scalar loss sum_k mean(out_k^2)
+    because the reference loss needs pytorch3d (absent)."""
+    import torch.distributed as dist
+    from dpft_b200 import ddp, models, native, synthetic
+    torch.manual_seed(42)
+    cfg_t = synthetic.offline_config(cfg, n_queries=N_QUERIES)
+    model = models.build("dprt", cfg_t)
+    model.load_state_dict(synthetic.seeded_state_dict(model.state_dict(), seed=1))
+    model = model.to(dev).train()
+    if world > 1:
+        ddp.broadcast_parameters(model, src=0)
+    bucket = ddp.GradientBucket(model, n_chunks=6)
+    opt = torch.optim.AdamW(bucket.params, lr=1e-4)
+    B = args.batch
+    batch = synthetic.synthetic_batch(cfg_t, B, seed=42 + rank, sizes=sizes, device=dev)
+
+    def step():
+        bucket.zero()
+        out = model(batch)
+        loss = sum((v ** 2).mean() for v in out.values())
+        loss.backward()
+        bucket.finish()
+        opt.step()
+        return loss
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    l0 = native.launches()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        loss = step()
+    e1.record()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    t = torch.tensor([e0.elapsed_time(e1) * 1e-3], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    if rank == 0:
+        secs = float(t.item())
+        print(json.dumps({"metric": "train_frames_per_sec", "value": B * world * args.steps / secs, "unit": UNIT,
+                          "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+                          "ms_per_step": 1e3 * secs / args.steps, "higher_is_better": True, "scaling": "weak",
+                          "vs_baseline": None, "dtype": "f32 (torch TF32 convs allowed, as the reference's default)",
+                          "data": "synthetic",
+                          "config": {"workload": WORKLOAD.replace("eval forward", "training step (fwd+bwd+all-reduce+AdamW)"),
+                                     "frames_per_gpu": B, "parallelism": f"dp{world}", "loss": "sum_k mean(out_k^2)",
+                                     "gradient_bucket_bytes": bucket.bytes(), "bucket_chunks": bucket.n_chunks},
+                          "gpu_launches": native.launches() - l0, "final_loss": float(loss)}), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
 def main():
     args = parse()
     if args.impl == "reference":
@@ -210,10 +274,17 @@ def main():
 
     from dpft_b200 import models, native, synthetic
     cfg, sizes = build_case(args)
+    if args.mode == "train":
+        run_train(args, cfg, sizes, rank, world, dev)
+        return
     model = models.build("dprt", cfg).eval()
     sd = synthetic.seeded_state_dict(model.state_dict(), seed=1)
     model.load_state_dict(sd)
     model = model.to(dev)
+    if args.dtype == "f32":
+        model.native_features = False
+    else:
+        model.feature_dtype = torch.float16 if args.dtype == "f16" else torch.bfloat16
 
     B = args.batch
     host = synthetic.synthetic_batch(cfg, B, seed=1000 + rank, sizes=sizes)
@@ -286,8 +357,9 @@ def main():
             del feats, pyr
         line = {"metric": METRIC, "value": frames / t_res, "unit": UNIT, "n_gpus": world, "steps": args.steps,
                 "warmup": max(args.warmup, 3), "ms_per_step": 1e3 * t_res / args.steps, "higher_is_better": True,
-                "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-                "config": {"workload": WORKLOAD, "frames_per_gpu": B, "l2": "flushed between timed steps (256 MiB write)",
+                "scaling": "weak", "vs_baseline": None, "dtype": args.dtype, "data": "synthetic",
+                "config": {"workload": WORKLOAD, "frames_per_gpu": B,
+                           "arithmetic": "backbone convs: %s operands, f32 accumulate (tcgen05); FPN/decoder f32" % args.dtype, "l2": "flushed between timed steps (256 MiB write)",
                            "sizes": {k: list(v) for k, v in sizes.items()}, "parallelism": f"replicas x{world}",
                            "valid": not args.small},
                 "roofline": roof, "clocks": clocks,

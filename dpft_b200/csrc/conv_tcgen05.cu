@@ -33,7 +33,7 @@ constexpr int UMMA_K = 16;
 constexpr int kNumThreads = 192;
 constexpr int kEpilogueWarp0 = 2;
 
-enum ConvMode : int { kTiled2D = 0, kIm2col = 1, kRowTiled = 2 };
+enum ConvMode : int { kTiled2D = 0, kIm2col = 1 };
 
 struct ConvParams {
     int M, N;               // output pixels, output channels
@@ -46,7 +46,6 @@ struct ConvParams {
     int mode;
     int is_f16;            // activations / weights are IEEE half instead of bfloat16
     int m_tiles, n_tiles;
-    int q_tiles;            // kRowTiled: tiles per output row
     const float* bias;      // [N]
     const __nv_bfloat16* residual;  // [M, N] or null
     __nv_bfloat16* out;     // [M, N]
@@ -70,29 +69,48 @@ __host__ __device__ constexpr uint32_t umma_idesc_16bit(int n, bool is_f16) {
 }
 using namespace tc;
 
+constexpr int EPI_COLS = 64;                       // columns per epilogue item: one 128-byte swizzle row of 16-bit outputs
+constexpr int EPI_BUF_BYTES = 32 * EPI_COLS * 2;   // one warp's [32 rows x 64 cols] sub-tile
+constexpr int EPI_RES_BUFS = 3;                    // residual sub-tiles in flight per warp (two prefetched + one in use)
+constexpr int EPI_OUT_BUFS = 2;
+
 template <int BLOCK_N, int STAGES> struct SmemLayout {
     static constexpr int kABytes = BLOCK_M * BLOCK_K * 2;
     static constexpr int kBBytes = BLOCK_N * BLOCK_K * 2;
     static constexpr int kStageBytes = kABytes + kBBytes;
-    static constexpr int kBarrierBytes = (2 * STAGES + 4) * 8 + 16;
-    static constexpr int kTotal = STAGES * kStageBytes + kBarrierBytes + 1024;   // +1024: manual alignment slack
+    static constexpr int kEpiBytes = 4 * (EPI_RES_BUFS + EPI_OUT_BUFS) * EPI_BUF_BYTES;     // 80 KB
+    static constexpr int kBarrierBytes = (2 * STAGES + 4 + 4 * EPI_RES_BUFS) * 8 + 16;
+    static constexpr int kTotal = STAGES * kStageBytes + kEpiBytes + kBarrierBytes + 1024;  // +1024: alignment slack
 };
+
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, const void* src, int c0, int c1) {
+    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(map), "r"(smem_u32(src)),
+                 "r"(c0), "r"(c1)
+                 : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void bulk_wait_read() {
+    asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
+}
 
 // ---- the kernel -------------------------------------------------------------------------------------------------
 template <int BLOCK_N, int STAGES>
 __global__ void __launch_bounds__(kNumThreads, 1)
 conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+                 const __grid_constant__ CUtensorMap tmap_d, const __grid_constant__ CUtensorMap tmap_r,
                  const ConvParams prm) {
     using L = SmemLayout<BLOCK_N, STAGES>;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     uint8_t* smem_a = smem;
     uint8_t* smem_b = smem + STAGES * L::kABytes;
-    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * L::kStageBytes);
+    uint8_t* smem_epi = smem + STAGES * L::kStageBytes;                  // per warp: 3 residual + 2 output sub-tiles
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem_epi + L::kEpiBytes);
     uint64_t* empty_bar = full_bar + STAGES;
     uint64_t* tmem_full = empty_bar + STAGES;
     uint64_t* tmem_empty = tmem_full + 2;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+    uint64_t* res_bar = tmem_empty + 2;                                  // [4 warps][EPI_RES_BUFS]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(res_bar + 4 * EPI_RES_BUFS);
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -101,6 +119,8 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     if (warp == 0 && elect_one()) {
         prefetch_tmap(&tmap_a);
         prefetch_tmap(&tmap_b);
+        prefetch_tmap(&tmap_d);
+        prefetch_tmap(&tmap_r);
         for (int i = 0; i < STAGES; ++i) {
             mbar_init(&full_bar[i], 1);
             mbar_init(&empty_bar[i], 1);
@@ -109,12 +129,10 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
             mbar_init(&tmem_full[i], 1);
             mbar_init(&tmem_empty[i], 4);             // one arrive per epilogue warp
         }
+        for (int i = 0; i < 4 * EPI_RES_BUFS; ++i) mbar_init(&res_bar[i], 1);
         fence_barrier_init();
     } else if (warp == 1) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
-                     "r"(kTmemCols)
-                     : "memory");
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+        tmem_alloc(tmem_slot, kTmemCols);
     }
     tcgen05_fence_before();
     __syncthreads();
@@ -130,7 +148,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
             uint32_t phase = 0;
             for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
                 const int m_tile = tile / prm.n_tiles, n_tile = tile % prm.n_tiles;
-                int cw = 0, ch = 0, cn = 0;           // first pixel of the tile in tensor-map coordinates
+                int cw = 0, ch = 0, cn = 0;           // first pixel of the tile in im2col tensor-map coordinates
                 if (prm.mode == kIm2col) {
                     const int m0 = m_tile * BLOCK_M;
                     const int pq = prm.P * prm.Q;
@@ -139,11 +157,6 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                     const int p = rem / prm.Q, q = rem - p * prm.Q;
                     cw = q * prm.stride - prm.pad;
                     ch = p * prm.stride - prm.pad;
-                } else if (prm.mode == kRowTiled) {
-                    const int row = m_tile / prm.q_tiles;          // (b, p)
-                    cw = (m_tile - row * prm.q_tiles) * BLOCK_M;   // q0
-                    cn = row / prm.P;
-                    ch = (row - cn * prm.P) * prm.stride;          // first input row of the window (pre-padded input)
                 }
                 for (int kb = 0; kb < prm.kblocks; ++kb) {
                     mbar_wait(&empty_bar[stage], phase ^ 1);
@@ -154,12 +167,9 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                     const int c0 = (kb - tap * prm.cblocks) * BLOCK_K;
                     if (prm.mode == kTiled2D) {
                         tma_load_2d(&tmap_a, &full_bar[stage], a_dst, c0, m_tile * BLOCK_M);
-                    } else if (prm.mode == kIm2col) {
+                    } else {
                         const int r = tap / prm.taps_s, s = tap - r * prm.taps_s;
                         tma_load_im2col_4d(&tmap_a, &full_bar[stage], a_dst, c0, cw, ch, cn, (uint16_t)s, (uint16_t)r);
-                    } else {
-                        // kRowTiled (stem): k-block = one filter row r; 64 contiguous elements = 8 taps x 8 channels
-                        tma_load_4d(&tmap_a, &full_bar[stage], a_dst, 0, cw, ch + tap, cn);
                     }
                     tma_load_2d(&tmap_b, &full_bar[stage], b_dst, kb * BLOCK_K, n_tile * BLOCK_N);
                     if (++stage == STAGES) { stage = 0; phase ^= 1; }
@@ -198,32 +208,49 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         }
     } else {
         // ======================================= epilogue =======================================
-        const int quad = warp & 3;                    // TMEM lane quadrant this warp may read
+        // Each warp owns the TMEM lane quadrant warp%4 = 32 rows of the tile and walks it in [32 x 64] "items".
+        // Output items are staged in shared memory (128-byte swizzle) and written by TMA; residual items are
+        // prefetched by TMA two items ahead so the loads overlap the arithmetic.
+        const int quad = warp & 3;
+        uint8_t* my_smem = smem_epi + quad * (EPI_RES_BUFS + EPI_OUT_BUFS) * EPI_BUF_BYTES;
+        uint8_t* res_buf = my_smem;
+        uint8_t* out_buf = my_smem + EPI_RES_BUFS * EPI_BUF_BYTES;
+        uint64_t* my_res_bar = res_bar + quad * EPI_RES_BUFS;
+        constexpr int kChunks = BLOCK_N / EPI_COLS;
+        const bool has_res = prm.residual != nullptr;
+        const int my_tiles = blockIdx.x < num_tiles ? (num_tiles - 1 - blockIdx.x) / gridDim.x + 1 : 0;
+        const int total_items = my_tiles * kChunks;
+
+        auto prefetch_residual = [&](int item) {
+            if (!has_res || item >= total_items) return;
+            const int tile = blockIdx.x + (item / kChunks) * gridDim.x;
+            const int m_tile = tile / prm.n_tiles, n_tile = tile % prm.n_tiles;
+            const int b = item % EPI_RES_BUFS;
+            if (lane == 0) {
+                mbar_expect_tx(&my_res_bar[b], EPI_BUF_BYTES);
+                tma_load_2d(&tmap_r, &my_res_bar[b], res_buf + b * EPI_BUF_BYTES, n_tile * BLOCK_N + (item % kChunks) * EPI_COLS,
+                            m_tile * BLOCK_M + quad * 32);
+            }
+        };
+
         int acc = 0;
         uint32_t acc_phase = 0;
+        int item = 0;
+        prefetch_residual(0);
+        prefetch_residual(1);
+        const int sw = lane & 7;                      // swizzle phase of this thread's row
         for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
             const int m_tile = tile / prm.n_tiles, n_tile = tile % prm.n_tiles;
             mbar_wait(&tmem_full[acc], acc_phase);
             tcgen05_fence_after();
-            const int r_in_tile = quad * 32 + lane;
-            long long m;
-            bool row_ok;
-            if (prm.mode == kRowTiled) {
-                const int row = m_tile / prm.q_tiles;
-                const int q = (m_tile - row * prm.q_tiles) * BLOCK_M + r_in_tile;
-                m = (long long)row * prm.Q + q;
-                row_ok = q < prm.Q;
-            } else {
-                m = (long long)m_tile * BLOCK_M + r_in_tile;
-                row_ok = m < prm.M;
-            }
             const int n0 = n_tile * BLOCK_N;
             if (prm.out_f32) {
-                // FPN lateral: inner = conv1x1 + bias (+ top-down), 16 fp32 channels per pixel
+                // FPN lateral: inner = conv1x1 + bias (+ top-down), 16 fp32 channels per pixel, written directly
+                const long long m = (long long)m_tile * BLOCK_M + quad * 32 + lane;
                 uint32_t v[32];
                 tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * BLOCK_N), v);
                 tmem_ld_wait();
-                if (row_ok) {
+                if (m < prm.M) {
                     const float4* cp = nullptr;
                     if (prm.coarse) {
                         const int pq = prm.P * prm.Q;
@@ -236,10 +263,9 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                     float4* o = reinterpret_cast<float4*>(prm.out_f32 + m * 16);
 #pragma unroll
                     for (int j4 = 0; j4 < 4; ++j4) {
-                        float4 r = make_float4(__uint_as_float(v[4 * j4]) + __ldg(prm.bias + 4 * j4),
-                                               __uint_as_float(v[4 * j4 + 1]) + __ldg(prm.bias + 4 * j4 + 1),
-                                               __uint_as_float(v[4 * j4 + 2]) + __ldg(prm.bias + 4 * j4 + 2),
-                                               __uint_as_float(v[4 * j4 + 3]) + __ldg(prm.bias + 4 * j4 + 3));
+                        const float4 bv = __ldg(reinterpret_cast<const float4*>(prm.bias) + j4);
+                        float4 r = make_float4(__uint_as_float(v[4 * j4]) + bv.x, __uint_as_float(v[4 * j4 + 1]) + bv.y,
+                                               __uint_as_float(v[4 * j4 + 2]) + bv.z, __uint_as_float(v[4 * j4 + 3]) + bv.w);
                         if (cp) {
                             const float4 c = __ldg(cp + j4);
                             r.x += c.x; r.y += c.y; r.z += c.z; r.w += c.w;
@@ -247,27 +273,32 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                         o[j4] = r;
                     }
                 }
-                tcgen05_fence_before();
-                __syncwarp();
-                if (lane == 0) mbar_arrive(&tmem_empty[acc]);
-                if (++acc == 2) { acc = 0; acc_phase ^= 1; }
-                continue;
-            }
-            __nv_bfloat16* orow = prm.out + m * prm.N + n0;
-            const __nv_bfloat16* rrow = prm.residual ? prm.residual + m * prm.N + n0 : nullptr;
+            } else {
 #pragma unroll 1
-            for (int c = 0; c < BLOCK_N; c += 32) {
-                uint32_t v[32];
-                tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * BLOCK_N + c), v);
-                tmem_ld_wait();
-                if (row_ok) {
+                for (int c = 0; c < kChunks; ++c, ++item) {
+                    uint32_t v[EPI_COLS];
+                    const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * BLOCK_N + c * EPI_COLS);
+                    tmem_ld_32x32b_x32(taddr, v);
+                    tmem_ld_32x32b_x32(taddr + 32, v + 32);
+                    tmem_ld_wait();
+                    const float4* bias4 = reinterpret_cast<const float4*>(prm.bias + n0 + c * EPI_COLS);
+                    const uint8_t* rrow = res_buf + (item % EPI_RES_BUFS) * EPI_BUF_BYTES + lane * 128;
+                    if (has_res) mbar_wait(&my_res_bar[item % EPI_RES_BUFS], (uint32_t)((item / EPI_RES_BUFS) & 1));
+                    // the output buffer of item-2 must have been read by its TMA store before it is overwritten
+                    if (lane == 0) bulk_wait_read<EPI_OUT_BUFS - 1>();
+                    __syncwarp();
+                    uint8_t* orow = out_buf + (item % EPI_OUT_BUFS) * EPI_BUF_BYTES + lane * 128;
 #pragma unroll
-                    for (int j = 0; j < 32; j += 8) {
+                    for (int j = 0; j < EPI_COLS / 8; ++j) {       // 8 columns = one 16-byte chunk of the row
                         float f[8];
-#pragma unroll
-                        for (int t = 0; t < 8; ++t) f[t] = __uint_as_float(v[j + t]) + __ldg(prm.bias + n0 + c + j + t);
-                        if (rrow) {
-                            const uint4 rv = *reinterpret_cast<const uint4*>(rrow + c + j);
+                        const float4 b0 = __ldg(bias4 + 2 * j), b1 = __ldg(bias4 + 2 * j + 1);
+                        f[0] = __uint_as_float(v[8 * j]) + b0.x;     f[1] = __uint_as_float(v[8 * j + 1]) + b0.y;
+                        f[2] = __uint_as_float(v[8 * j + 2]) + b0.z; f[3] = __uint_as_float(v[8 * j + 3]) + b0.w;
+                        f[4] = __uint_as_float(v[8 * j + 4]) + b1.x; f[5] = __uint_as_float(v[8 * j + 5]) + b1.y;
+                        f[6] = __uint_as_float(v[8 * j + 6]) + b1.z; f[7] = __uint_as_float(v[8 * j + 7]) + b1.w;
+                        const int phys = (j ^ sw) << 4;             // 128-byte swizzle: chunk index xor (row % 8)
+                        if (has_res) {
+                            const uint4 rv = *reinterpret_cast<const uint4*>(rrow + phys);
 #pragma unroll
                             for (int t = 0; t < 4; ++t) {
                                 const float2 rf = prm.is_f16 ? __half22float2(reinterpret_cast<const __half2*>(&rv)[t])
@@ -292,8 +323,16 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
 #pragma unroll
                             for (int t = 0; t < 4; ++t) ob[t] = __floats2bfloat162_rn(f[2 * t], f[2 * t + 1]);
                         }
-                        *reinterpret_cast<uint4*>(orow + c + j) = ov;
+                        *reinterpret_cast<uint4*>(orow + phys) = ov;
                     }
+                    fence_proxy_async();              // make the generic-proxy smem writes visible to the TMA engine
+                    __syncwarp();                     // all rows written (and this item's residual rows consumed)
+                    if (lane == 0) {
+                        tma_store_2d(&tmap_d, out_buf + (item % EPI_OUT_BUFS) * EPI_BUF_BYTES, n0 + c * EPI_COLS,
+                                     m_tile * BLOCK_M + quad * 32);
+                        bulk_commit();
+                    }
+                    prefetch_residual(item + 2);      // refills the buffer consumed by item-1
                 }
             }
             tcgen05_fence_before();
@@ -301,13 +340,14 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
             if (lane == 0) mbar_arrive(&tmem_empty[acc]);
             if (++acc == 2) { acc = 0; acc_phase ^= 1; }
         }
+        if (lane == 0) bulk_wait_read<0>();           // smem must stay valid until the last stores have read it
     }
 
     tcgen05_fence_before();
     __syncthreads();
     if (warp == 1) {
         tcgen05_fence_after();
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemCols) : "memory");
+        tmem_dealloc(tmem_base, kTmemCols);
     }
 }
 
@@ -358,7 +398,8 @@ int encode_2d(CUtensorMap* map, const void* base, uint64_t inner, uint64_t outer
 }
 
 template <int BLOCK_N, int STAGES>
-int launch(const CUtensorMap& ta, const CUtensorMap& tb, const ConvParams& prm, cudaStream_t stream) {
+int launch(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& td, const CUtensorMap& tr, const ConvParams& prm,
+           cudaStream_t stream) {
     using L = SmemLayout<BLOCK_N, STAGES>;
     static bool configured = false;
     if (!configured) {
@@ -369,7 +410,7 @@ int launch(const CUtensorMap& ta, const CUtensorMap& tb, const ConvParams& prm, 
     }
     const int tiles = prm.m_tiles * prm.n_tiles;
     const int grid = tiles < g_sm_count ? tiles : g_sm_count;
-    conv_gemm_kernel<BLOCK_N, STAGES><<<grid, kNumThreads, L::kTotal, stream>>>(ta, tb, prm);
+    conv_gemm_kernel<BLOCK_N, STAGES><<<grid, kNumThreads, L::kTotal, stream>>>(ta, tb, td, tr, prm);
     DPFT_LAUNCH_CHECK("conv_gemm_kernel");
     return DPFT_OK;
 }
@@ -410,7 +451,7 @@ extern "C" int dpft_fpn_lateral_forward(const void* x, const void* w, const floa
     if (st) return st;
     st = encode_2d(&tb, w, (uint64_t)Cin, 64, (uint64_t)Cin * 2, BLOCK_K, 64, is_f16);
     if (st) return st;
-    return launch<64, 8>(ta, tb, prm, (cudaStream_t)stream);
+    return launch<64, 6>(ta, tb, ta, ta, prm, (cudaStream_t)stream);   // d / r maps unused in the fp32 lateral form
 }
 
 extern "C" int dpft_conv2d_nhwc(const void* x, const void* w, const float* bias, const void* residual, void* y,
@@ -432,7 +473,7 @@ extern "C" int dpft_conv2d_nhwc(const void* x, const void* w, const float* bias,
     prm.M = B * P * Q; prm.N = Cout; prm.P = P; prm.Q = Q; prm.taps_s = S; prm.cblocks = Cin / 64;
     prm.kblocks = R * S * prm.cblocks; prm.stride = stride; prm.pad = pad; prm.relu = relu; prm.is_f16 = is_f16;
     prm.bias = bias; prm.residual = (const __nv_bfloat16*)residual; prm.out = (__nv_bfloat16*)y;
-    prm.m_tiles = (prm.M + BLOCK_M - 1) / BLOCK_M; prm.q_tiles = 0;
+    prm.m_tiles = (prm.M + BLOCK_M - 1) / BLOCK_M;
     const int bn = pick_block_n(Cout, prm.m_tiles, block_n);
     prm.n_tiles = Cout / bn;
 
@@ -459,8 +500,14 @@ extern "C" int dpft_conv2d_nhwc(const void* x, const void* w, const float* bias,
     }
     st = encode_2d(&tb, w, (uint64_t)R * S * Cin, (uint64_t)Cout, (uint64_t)R * S * Cin * 2, BLOCK_K, bn, is_f16);
     if (st) return st;
+    // output / residual as [M, Cout] matrices, written / read in [32 rows x 64 cols] boxes (128-byte swizzle)
+    CUtensorMap td, tr;
+    st = encode_2d(&td, y, (uint64_t)Cout, (uint64_t)prm.M, (uint64_t)Cout * 2, EPI_COLS, 32, is_f16);
+    if (st) return st;
+    st = encode_2d(&tr, residual ? residual : y, (uint64_t)Cout, (uint64_t)prm.M, (uint64_t)Cout * 2, EPI_COLS, 32, is_f16);
+    if (st) return st;
     cudaStream_t s = (cudaStream_t)stream;
-    if (bn == 256) return launch<256, 4>(ta, tb, prm, s);
-    if (bn == 128) return launch<128, 6>(ta, tb, prm, s);
-    return launch<64, 8>(ta, tb, prm, s);
+    if (bn == 256) return launch<256, 3>(ta, tb, td, tr, prm, s);
+    if (bn == 128) return launch<128, 4>(ta, tb, td, tr, prm, s);
+    return launch<64, 6>(ta, tb, td, tr, prm, s);
 }
