@@ -17,6 +17,7 @@
 #include <type_traits>
 
 #include "common.cuh"
+#include "tcgen05.cuh"
 
 namespace dpft {
 namespace {
@@ -264,6 +265,160 @@ fpn_output_kernel(const FpnOutParams prm) {
     }
 }
 
+
+// ------------------------------------------------------------------------------- FPN output on the tensor cores
+// Same computation as fpn_output_kernel, as an implicit GEMM per output row: M = 128 pixels of one image row,
+// N = 16 output channels, K = 9 taps x 16 input channels.  The inner halo tile ((TH+2) rows x 130 pixels x 16 channels)
+// is built by the threads in f16 and laid out as the canonical un-swizzled K-major UMMA operand: two channel-half
+// planes per row, 16 bytes per pixel, so that for tap (dr, ds) the A operand of output row r is simply the smem
+// window starting at inner row r+dr, pixel ds (start address + ds*16 B; 8-pixel core matrices 128 B apart, the two
+// K halves one plane apart).  One thread issues the TH x 9 tcgen05.mma (each output row has its own 16 TMEM columns
+// and its own mbarrier); 128 threads then read row after row from TMEM, add bias + positional embedding and write
+// 64 contiguous bytes per pixel.
+constexpr int TC_TH = 8, TC_TW = 128;
+constexpr int TC_PW = 136;                           // padded pixels per inner row (>= TC_TW + 2)
+constexpr int TC_PLANE = TC_PW * 16;                 // bytes of one channel-half plane of one inner row
+constexpr int TC_ROWB = 2 * TC_PLANE;
+constexpr int TC_A_BYTES = (TC_TH + 2) * TC_ROWB;    // 43,520
+constexpr int TC_B_BYTES = 9 * 512;                  // 9 taps x [2 K-halves][2 N-groups][8 rows][16 B]
+
+template <int CIN>   // CIN == 0: inner map comes from global memory
+__global__ void __launch_bounds__(128)
+fpn_output_tc_kernel(const FpnOutParams prm) {
+    extern __shared__ __align__(128) uint8_t tsm[];
+    uint8_t* s_a = tsm;
+    uint8_t* s_b = tsm + TC_A_BYTES;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(s_b + TC_B_BYTES);
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + TC_TH);
+    float* s_lat = reinterpret_cast<float*>(tmem_slot + 4);          // [16][CIN] + [16]
+    const int b = blockIdx.z;
+    const int p0 = blockIdx.y * TC_TH, q0 = blockIdx.x * TC_TW;
+    const int tid = threadIdx.x, warp = tid >> 5;
+    const int H = prm.H, W = prm.W;
+
+    if (warp == 0) {
+        tc::tmem_alloc(tmem_slot, 128);
+    } else if (tid == 32) {
+        for (int r = 0; r < TC_TH; ++r) tc::mbar_init(&bars[r], 1);
+        tc::fence_barrier_init();
+    }
+    // 3x3 weights -> f16, [tap][khalf][ngroup][8 rows][8 elems]   (w is [tap][o][c] fp32)
+    for (int i = tid; i < 9 * 16 * 16; i += 128) {
+        const int c = i & 15, o = (i >> 4) & 15, tap = i >> 8;
+        const int off = tap * 512 + (c >> 3) * 256 + (o >> 3) * 128 + (o & 7) * 16 + (c & 7) * 2;
+        *reinterpret_cast<__half*>(s_b + off) = __float2half_rn(__ldg(prm.w + i));
+    }
+    if (CIN > 0) {
+        for (int i = tid; i < FC * CIN; i += 128) s_lat[i] = __ldg(prm.lat_w + i);
+        if (tid < FC) s_lat[FC * CIN + tid] = __ldg(prm.lat_b + tid);
+        __syncthreads();
+    }
+    // inner halo tile (zero outside the image), f16
+    for (int i = tid; i < (TC_TH + 2) * TC_PW; i += 128) {
+        const int rr = i / TC_PW, px = i - rr * TC_PW;
+        const int hh = p0 - 1 + rr, ww = q0 - 1 + px;
+        float v[FC];
+#pragma unroll
+        for (int c = 0; c < FC; ++c) v[c] = 0.0f;
+        if (px < TC_TW + 2 && hh >= 0 && hh < H && ww >= 0 && ww < W) {
+            if (CIN > 0) {
+                float xin[CIN > 0 ? CIN : 1];
+                const float* xp = prm.raw + (((long long)b * H + hh) * W + ww) * CIN;
+#pragma unroll
+                for (int c = 0; c < CIN; ++c) xin[c] = __ldg(xp + c);
+#pragma unroll
+                for (int o = 0; o < FC; ++o) {
+                    float a = s_lat[FC * CIN + o];
+#pragma unroll
+                    for (int c = 0; c < CIN; ++c) a = fmaf(s_lat[o * CIN + c], xin[c], a);
+                    v[o] = a;
+                }
+                if (prm.coarse) {
+                    const int hc = nearest_src(hh, prm.Hc, H), wc = nearest_src(ww, prm.Wc, W);
+                    const float4* cp = reinterpret_cast<const float4*>(prm.coarse + (((long long)b * prm.Hc + hc) * prm.Wc + wc) * FC);
+#pragma unroll
+                    for (int c4 = 0; c4 < 4; ++c4) {
+                        const float4 f = __ldg(cp + c4);
+                        v[4 * c4] += f.x; v[4 * c4 + 1] += f.y; v[4 * c4 + 2] += f.z; v[4 * c4 + 3] += f.w;
+                    }
+                }
+            } else {
+                const float4* ip = reinterpret_cast<const float4*>(prm.inner + (((long long)b * H + hh) * W + ww) * FC);
+#pragma unroll
+                for (int c4 = 0; c4 < 4; ++c4) {
+                    const float4 f = __ldg(ip + c4);
+                    v[4 * c4] = f.x; v[4 * c4 + 1] = f.y; v[4 * c4 + 2] = f.z; v[4 * c4 + 3] = f.w;
+                }
+            }
+        }
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+            uint4 pk;
+            __half2* ph = reinterpret_cast<__half2*>(&pk);
+#pragma unroll
+            for (int t = 0; t < 4; ++t)
+                ph[t] = __floats2half2_rn(fminf(fmaxf(v[half * 8 + 2 * t], -65504.f), 65504.f),
+                                          fminf(fmaxf(v[half * 8 + 2 * t + 1], -65504.f), 65504.f));
+            *reinterpret_cast<uint4*>(s_a + rr * TC_ROWB + half * TC_PLANE + px * 16) = pk;
+        }
+    }
+    tc::fence_proxy_async();                 // generic-proxy smem writes -> visible to the tensor core (async proxy)
+    tc::tcgen05_fence_before();
+    __syncthreads();
+    tc::tcgen05_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (tid == 0) {
+        constexpr uint32_t idesc = tc::umma_idesc_16bit(128, 16, true);
+        const uint32_t a0 = tc::smem_u32(s_a), b0 = tc::smem_u32(s_b);
+        for (int r = 0; r < TC_TH; ++r) {
+#pragma unroll
+            for (int tap = 0; tap < 9; ++tap) {
+                const int dr = tap / 3, ds = tap % 3;
+                const uint64_t adesc = tc::umma_desc_noswizzle(a0 + (r + dr) * TC_ROWB + ds * 16, TC_PLANE, 128);
+                const uint64_t bdesc = tc::umma_desc_noswizzle(b0 + tap * 512, 256, 128);
+                tc::umma_bf16(tmem_base + r * 16, adesc, bdesc, idesc, tap ? 1u : 0u);
+            }
+            tc::umma_commit(&bars[r]);
+        }
+    }
+    __syncwarp();
+    // epilogue: thread t <-> pixel q0 + t <-> TMEM lane t
+    const int q = q0 + tid;
+    float4 px4[4], bias4[4];
+#pragma unroll
+    for (int c4 = 0; c4 < 4; ++c4) {
+        px4[c4] = q < W ? __ldg(reinterpret_cast<const float4*>(prm.pos_x + (long long)q * FC) + c4) : make_float4(0, 0, 0, 0);
+        bias4[c4] = __ldg(reinterpret_cast<const float4*>(prm.bias) + c4);
+    }
+    for (int r = 0; r < TC_TH; ++r) {
+        tc::mbar_wait(&bars[r], 0);
+        tc::tcgen05_fence_after();
+        uint32_t v[16];
+        tc::tmem_ld_32x32b_x16(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(r * 16), v);
+        tc::tmem_ld_wait();
+        const int p = p0 + r;
+        if (p < H && q < W) {
+            const float4* py = reinterpret_cast<const float4*>(prm.pos_y + (long long)p * FC);
+            float4* o = reinterpret_cast<float4*>(prm.pyramid + ((long long)b * prm.S + prm.start + (long long)p * W + q) * FC);
+#pragma unroll
+            for (int c4 = 0; c4 < 4; ++c4) {
+                const float4 c = __ldg(py + c4);
+                o[c4] = make_float4(((__uint_as_float(v[4 * c4]) + bias4[c4].x) + px4[c4].x) + c.x,
+                                    ((__uint_as_float(v[4 * c4 + 1]) + bias4[c4].y) + px4[c4].y) + c.y,
+                                    ((__uint_as_float(v[4 * c4 + 2]) + bias4[c4].z) + px4[c4].z) + c.z,
+                                    ((__uint_as_float(v[4 * c4 + 3]) + bias4[c4].w) + px4[c4].w) + c.w);
+            }
+        }
+    }
+    tc::tcgen05_fence_before();
+    __syncthreads();
+    if (warp == 0) {
+        tc::tcgen05_fence_after();
+        tc::tmem_dealloc(tmem_base, 128);
+    }
+}
+
 }  // namespace
 }  // namespace dpft
 
@@ -321,18 +476,39 @@ extern "C" int dpft_maxpool3x3s2_nhwc(const void* x, void* y, int B, int H, int 
 extern "C" int dpft_fpn_output_forward(const float* inner, const float* raw, int raw_channels, const float* lat_w,
                                        const float* lat_b, const float* coarse, int Hc, int Wc, const float* w,
                                        const float* bias, const float* pos_y, const float* pos_x, float* pyramid,
-                                       long long S, long long start, int B, int H, int W, void* stream) {
+                                       long long S, long long start, int B, int H, int W, int impl, void* stream) {
     DPFT_REQUIRE(w && bias && pos_y && pos_x && pyramid, "fpn_output: null pointer");
     DPFT_REQUIRE((inner != nullptr) != (raw != nullptr), "fpn_output: exactly one of inner / raw must be given");
     DPFT_REQUIRE(B > 0 && H > 0 && W > 0, "fpn_output: bad size");
     FpnOutParams prm{inner, raw, lat_w, lat_b, coarse, w, bias, pos_y, pos_x, pyramid, S, start, H, W, Hc, Wc};
-    const dim3 grid((W + FPN_TW - 1) / FPN_TW, (H + FPN_TH - 1) / FPN_TH, B);
     cudaStream_t s = (cudaStream_t)stream;
+    DPFT_REQUIRE(impl >= 0 && impl <= 2, "fpn_output: impl must be 0 (auto), 1 (CUDA cores) or 2 (tensor cores)");
+    if (!inner) {
+        DPFT_REQUIRE(lat_w && lat_b, "fpn_output: lateral weights needed for the raw level");
+        DPFT_REQUIRE(coarse == nullptr || (Hc > 0 && Wc > 0), "fpn_output: bad coarse size");
+        DPFT_REQUIRE(raw_channels == 3 || raw_channels == 6, "fpn_output: raw_channels=%d (3 or 6 supported)", raw_channels);
+    }
+    if (impl == 2 || (impl == 0 && W >= 96)) {          // wide levels: 128-pixel row strips on the tensor cores
+        const dim3 tgrid((W + TC_TW - 1) / TC_TW, (H + TC_TH - 1) / TC_TH, B);
+        const size_t smem = TC_A_BYTES + TC_B_BYTES + TC_TH * 8 + 16 + sizeof(float) * (FC * 6 + FC);
+        static bool configured = false;
+        if (!configured) {
+            int st = cuda_status(cudaFuncSetAttribute(fpn_output_tc_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "fpn tc attr");
+            if (!st) st = cuda_status(cudaFuncSetAttribute(fpn_output_tc_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "fpn tc attr");
+            if (!st) st = cuda_status(cudaFuncSetAttribute(fpn_output_tc_kernel<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "fpn tc attr");
+            if (st) return st;
+            configured = true;
+        }
+        if (inner) fpn_output_tc_kernel<0><<<tgrid, 128, smem, s>>>(prm);
+        else if (raw_channels == 3) fpn_output_tc_kernel<3><<<tgrid, 128, smem, s>>>(prm);
+        else fpn_output_tc_kernel<6><<<tgrid, 128, smem, s>>>(prm);
+        DPFT_LAUNCH_CHECK("fpn_output_tc_kernel");
+        return DPFT_OK;
+    }
+    const dim3 grid((W + FPN_TW - 1) / FPN_TW, (H + FPN_TH - 1) / FPN_TH, B);
     if (inner) {
         fpn_output_kernel<0><<<grid, 256, 0, s>>>(prm);
     } else {
-        DPFT_REQUIRE(lat_w && lat_b, "fpn_output: lateral weights needed for the raw level");
-        DPFT_REQUIRE(coarse == nullptr || (Hc > 0 && Wc > 0), "fpn_output: bad coarse size");
         if (raw_channels == 3) fpn_output_kernel<3><<<grid, 256, 0, s>>>(prm);
         else if (raw_channels == 6) fpn_output_kernel<6><<<grid, 256, 0, s>>>(prm);
         else { set_error("fpn_output: raw_channels=%d (3 or 6 supported)", raw_channels); return DPFT_ERR_UNSUPPORTED; }

@@ -62,13 +62,13 @@ def lateral_forward(x: torch.Tensor, w: torch.Tensor, bias: torch.Tensor, coarse
 def fpn_output_forward(pyramid: torch.Tensor, start: int, H: int, W: int, w: torch.Tensor, bias: torch.Tensor,
                        pos_y: torch.Tensor, pos_x: torch.Tensor, inner: Optional[torch.Tensor] = None,
                        raw: Optional[torch.Tensor] = None, lat_w: Optional[torch.Tensor] = None,
-                       lat_b: Optional[torch.Tensor] = None, coarse: Optional[torch.Tensor] = None) -> None:
+                       lat_b: Optional[torch.Tensor] = None, coarse: Optional[torch.Tensor] = None, impl: int = 0) -> None:
     B, S, _ = pyramid.shape
     hc, wc = (coarse.shape[1], coarse.shape[2]) if coarse is not None else (0, 0)
     raw_c = raw.shape[-1] if raw is not None else 0
     st = _lib().dpft_fpn_output_forward(native.ptr(inner), native.ptr(raw), raw_c, native.ptr(lat_w), native.ptr(lat_b),
                                         native.ptr(coarse), hc, wc, native.ptr(w), native.ptr(bias), native.ptr(pos_y),
-                                        native.ptr(pos_x), native.ptr(pyramid), S, start, B, H, W,
+                                        native.ptr(pos_x), native.ptr(pyramid), S, start, B, H, W, impl,
                                         native.stream_ptr(pyramid.device))
     native.check(st, "dpft_fpn_output_forward")
     native.count_launch()

@@ -125,11 +125,12 @@ DPFT_API int dpft_fpn_lateral_forward(const void* x, const void* w, const float*
  * f32 with the lateral weights lat_w [16][raw_channels], lat_b [16] and the coarser inner map `coarse` (may be NULL):
  * then inner = lat_w raw + lat_b + nearest-upsampled coarse is formed on the fly (skip-link level, dprt.py:222-225).
  *   w [3][3][16 out][16 in] f32;  bias [16];  pos_y (H, 16), pos_x (W, 16) f32
+ * impl: 0 = choose (tcgen05 row-strip kernel with an f16 inner tile for W >= 96, else the fp32 CUDA-core kernel), 1 / 2 = force.
  */
 DPFT_API int dpft_fpn_output_forward(const float* inner, const float* raw, int raw_channels, const float* lat_w,
                                      const float* lat_b, const float* coarse, int Hc, int Wc, const float* w,
                                      const float* bias, const float* pos_y, const float* pos_x, float* pyramid,
-                                     long long S, long long start, int B, int H, int W, void* stream);
+                                     long long S, long long start, int B, int H, int W, int impl, void* stream);
 
 /*
  * Fused query decoder (inference), d_model = 16, 8 heads.

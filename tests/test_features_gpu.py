@@ -61,7 +61,7 @@ def test_backbone_and_pyramid(name, view, size):
     from dpft_b200.features import NativeView
     from dpft_b200.models.fuser import FeaturePyramid
     cfg, m = _model(name)
-    nv = NativeView(m.backbones[view], m.necks[view], m.embeddings[view], True, DEV)
+    nv = NativeView(m.backbones[view], m.necks[view], m.embeddings[view], True, DEV, torch.float16)
     x = torch.rand(*size, device=DEV) * 255.0
     with torch.no_grad():
         want_feats = m.backbones[view](x)
@@ -69,10 +69,10 @@ def test_backbone_and_pyramid(name, view, size):
     got_feats = nv.backbone(x)
     for g, (k, w) in zip(got_feats, want_feats.items()):
         assert g.shape == w.shape, k
-        assert _rel(g, w) < 2e-2, (k, _rel(g, w))
+        assert _rel(g, w) < 5e-3, (k, _rel(g, w))          # f16 activations through up to 33 blocks
     flat, shapes = nv.pyramid(x)
     assert shapes == want_pyr.shapes and flat.shape == want_pyr.flat.shape
-    assert _rel(flat, want_pyr.flat) < 2e-2, _rel(flat, want_pyr.flat)
+    assert _rel(flat, want_pyr.flat) < 5e-3, _rel(flat, want_pyr.flat)
 
 
 def test_fpn_stages_in_isolation():
@@ -101,11 +101,40 @@ def test_fpn_stages_in_isolation():
     assert _rel(g3, i3.movedim(1, -1)) < 5e-3          # lateral weights are rounded to bf16 for the tensor cores
     assert _rel(g2, i2.movedim(1, -1)) < 5e-3
     S = 13 * 10 + 50 * 37
-    pyr = torch.zeros(B, S, 16, device=DEV)
-    py, px = nv._tables(2, 13, 10)
-    features.fpn_output_forward(pyr, 50 * 37, 13, 10, nv.out_w[2], nv.out_b[2], py, px, inner=g2)
-    py, px = nv._tables(0, 50, 37)
-    features.fpn_output_forward(pyr, 0, 50, 37, nv.out_w[0], nv.out_b[0], py, px, raw=raw, lat_w=nv.lat_w[0],
-                                lat_b=nv.lat_b[0], coarse=g2)
-    assert _rel(pyr[:, 50 * 37:], o2.flatten(1, 2)) < 1e-4
-    assert _rel(pyr[:, :50 * 37], o0.flatten(1, 2)) < 1e-4
+    # impl 1 = fp32 CUDA-core kernel (tight), impl 2 = tcgen05 row-strip kernel with an f16 inner tile (f16 rounding)
+    for impl, tol in ((1, 1e-4), (2, 2e-3)):
+        pyr = torch.zeros(B, S, 16, device=DEV)
+        py, px = nv._tables(2, 13, 10)
+        features.fpn_output_forward(pyr, 50 * 37, 13, 10, nv.out_w[2], nv.out_b[2], py, px, inner=g2, impl=impl)
+        py, px = nv._tables(0, 50, 37)
+        features.fpn_output_forward(pyr, 0, 50, 37, nv.out_w[0], nv.out_b[0], py, px, raw=raw, lat_w=nv.lat_w[0],
+                                    lat_b=nv.lat_b[0], coarse=g2, impl=impl)
+        assert _rel(pyr[:, 50 * 37:], o2.flatten(1, 2)) < tol, (impl, _rel(pyr[:, 50 * 37:], o2.flatten(1, 2)))
+        assert _rel(pyr[:, :50 * 37], o0.flatten(1, 2)) < tol, (impl, _rel(pyr[:, :50 * 37], o0.flatten(1, 2)))
+
+
+@pytest.mark.parametrize("cin,H,W", [(3, 45, 300), (6, 17, 129), (0, 23, 256)])
+def test_fpn_output_tensor_core_matches_cuda_core(cin, H, W):
+    """Wide levels: the tcgen05 row-strip kernel against the fp32 CUDA-core kernel on the same inputs."""
+    from dpft_b200 import features
+    g = torch.Generator(device=DEV).manual_seed(cin + H)
+    B = 2
+    w = torch.randn(3, 3, 16, 16, generator=g, device=DEV) * 0.1
+    bias = torch.randn(16, generator=g, device=DEV)
+    py = torch.randn(H, 16, generator=g, device=DEV)
+    px = torch.randn(W, 16, generator=g, device=DEV)
+    coarse = torch.randn(B, (H + 3) // 4, (W + 3) // 4, 16, generator=g, device=DEV)
+    kw = {}
+    if cin:
+        kw = dict(raw=torch.rand(B, H, W, cin, generator=g, device=DEV) * 255, coarse=coarse,
+                  lat_w=torch.randn(16, cin, generator=g, device=DEV) * 0.01, lat_b=torch.randn(16, generator=g, device=DEV))
+    else:
+        kw = dict(inner=torch.randn(B, H, W, 16, generator=g, device=DEV) * 3)
+    S = H * W + 7
+    a = torch.zeros(B, S, 16, device=DEV)
+    b = torch.zeros(B, S, 16, device=DEV)
+    features.fpn_output_forward(a, 7, H, W, w, bias, py, px, impl=1, **kw)
+    features.fpn_output_forward(b, 7, H, W, w, bias, py, px, impl=2, **kw)
+    torch.cuda.synchronize()
+    assert float(b[:, :7].abs().max()) == 0.0                      # nothing written before `start`
+    assert _rel(b, a) < 2e-3, _rel(b, a)
