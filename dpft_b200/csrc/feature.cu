@@ -419,6 +419,148 @@ fpn_output_tc_kernel(const FpnOutParams prm) {
     }
 }
 
+
+// --------------------------------------------------------------------------------------- stem on the tensor cores
+// conv 7x7 / stride 2 as an implicit GEMM per output row: M = 128 output pixels, N = 64 channels, K = 7 filter rows x
+// 8 taps (7 + one zero tap) x 8 channels (Cin + zero padding).  The stride-2 window is made contiguous by splitting
+// every input row into an even-column and an odd-column plane of 16-byte (8 x f16) entries: for tap s the operand of
+// output pixels q0..q0+127 is plane (s & 1) starting at entry (s >> 1), so taps (2j, 2j+1) form one K = 16 MMA whose
+// two K halves are exactly one plane apart (LBO) — again the canonical un-swizzled K-major UMMA layout, built by the
+// threads while they convert the raw fp32 input.  Operands are always f16 (0..255 inputs are exact); 4 output rows per
+// CTA, 64 TMEM columns and one mbarrier per row.
+constexpr int ST_TH = 4, ST_TW = 128;
+constexpr int ST_ROWS = 2 * ST_TH + 5;               // input rows per tile
+constexpr int ST_PLANE_ENTRIES = 136;                // >= 128 + 4
+constexpr int ST_PLANE = ST_PLANE_ENTRIES * 16;
+constexpr int ST_ROWB = 2 * ST_PLANE;
+constexpr int ST_A_BYTES = ST_ROWS * ST_ROWB;        // 56,576
+constexpr int ST_B_BYTES = 7 * 4 * 2048;             // (r, tap pair) x [2 K-halves][8 N-groups][8 rows][16 B] = 57,344
+
+template <int CIN, typename OT>
+__global__ void __launch_bounds__(128)
+stem_tc_kernel(const float* __restrict__ x, const float* __restrict__ w /* [7][7][CIN][64] */, const float* __restrict__ bias,
+               OT* __restrict__ y, int H, int W, int P, int Q) {
+    extern __shared__ __align__(128) uint8_t tsm[];
+    uint8_t* s_a = tsm;
+    uint8_t* s_b = tsm + ST_A_BYTES;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(s_b + ST_B_BYTES);
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + ST_TH);
+    const int b = blockIdx.z;
+    const int p0 = blockIdx.y * ST_TH, q0 = blockIdx.x * ST_TW;
+    const int tid = threadIdx.x, warp = tid >> 5;
+
+    if (warp == 0) {
+        tc::tmem_alloc(tmem_slot, ST_TH * 64);
+    } else if (tid == 32) {
+        for (int r = 0; r < ST_TH; ++r) tc::mbar_init(&bars[r], 1);
+        tc::fence_barrier_init();
+    }
+    // weights: zero fill, then scatter w[r][s][c][o] into [(r*4 + s/2)][s&1][o/8][o%8][c]
+    for (int i = tid; i < ST_B_BYTES / 16; i += 128) reinterpret_cast<uint4*>(s_b)[i] = make_uint4(0, 0, 0, 0);
+    __syncthreads();
+    for (int i = tid; i < 49 * CIN * 64; i += 128) {
+        const int o = i & 63;
+        const int c = (i >> 6) % CIN;
+        const int tap = (i >> 6) / CIN;
+        const int r = tap / 7, s2 = tap - r * 7;
+        const int off = (r * 4 + (s2 >> 1)) * 2048 + (s2 & 1) * 1024 + (o >> 3) * 128 + (o & 7) * 16 + c * 2;
+        *reinterpret_cast<__half*>(s_b + off) = __float2half_rn(__ldg(w + i));
+    }
+    // input tile: rows 2*p0-3 .. 2*p0-3+ST_ROWS-1, columns 2*q0-3 .. (+2*ST_PLANE_ENTRIES-1), even/odd planes
+    const int h_base = 2 * p0 - 3, w_base = 2 * q0 - 3;
+    for (int i = tid; i < ST_ROWS * 2 * ST_PLANE_ENTRIES; i += 128) {
+        const int rr = i / (2 * ST_PLANE_ENTRIES);
+        const int xl = i - rr * (2 * ST_PLANE_ENTRIES);          // local column
+        const int hh = h_base + rr, ww = w_base + xl;
+        uint4 pk = make_uint4(0, 0, 0, 0);
+        if (hh >= 0 && hh < H && ww >= 0 && ww < W) {
+            const float* xp = x + (((long long)b * H + hh) * W + ww) * CIN;
+            __align__(16) __half hv[8];
+#pragma unroll
+            for (int c = 0; c < 8; ++c) hv[c] = __float2half_rn(c < CIN ? __ldg(xp + (c < CIN ? c : 0)) : 0.0f);
+            pk = *reinterpret_cast<uint4*>(hv);
+        }
+        *reinterpret_cast<uint4*>(s_a + rr * ST_ROWB + (xl & 1) * ST_PLANE + (xl >> 1) * 16) = pk;
+    }
+    tc::fence_proxy_async();
+    tc::tcgen05_fence_before();
+    __syncthreads();
+    tc::tcgen05_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (tid == 0) {
+        constexpr uint32_t idesc = tc::umma_idesc_16bit(128, 64, true);
+        const uint32_t a0 = tc::smem_u32(s_a), b0 = tc::smem_u32(s_b);
+        for (int pr = 0; pr < ST_TH; ++pr) {
+#pragma unroll 1
+            for (int r = 0; r < 7; ++r) {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const uint64_t adesc = tc::umma_desc_noswizzle(a0 + (2 * pr + r) * ST_ROWB + j * 16, ST_PLANE, 128);
+                    const uint64_t bdesc = tc::umma_desc_noswizzle(b0 + (r * 4 + j) * 2048, 1024, 128);
+                    tc::umma_bf16(tmem_base + pr * 64, adesc, bdesc, idesc, (r | j) ? 1u : 0u);
+                }
+            }
+            tc::umma_commit(&bars[pr]);
+        }
+    }
+    __syncwarp();
+    const int q = q0 + tid;
+    for (int pr = 0; pr < ST_TH; ++pr) {
+        tc::mbar_wait(&bars[pr], 0);
+        tc::tcgen05_fence_after();
+        const int p = p0 + pr;
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+            uint32_t v[32];
+            tc::tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(pr * 64 + half * 32), v);
+            tc::tmem_ld_wait();
+            if (p < P && q < Q) {
+                OT* o = y + (((long long)b * P + p) * Q + q) * STEM_COUT + half * 32;
+#pragma unroll
+                for (int o8 = 0; o8 < 4; ++o8) {
+                    uint4 pk;
+                    const float4 b0v = __ldg(reinterpret_cast<const float4*>(bias + half * 32 + o8 * 8));
+                    const float4 b1v = __ldg(reinterpret_cast<const float4*>(bias + half * 32 + o8 * 8 + 4));
+                    const float bb[8] = {b0v.x, b0v.y, b0v.z, b0v.w, b1v.x, b1v.y, b1v.z, b1v.w};
+#pragma unroll
+                    for (int t = 0; t < 4; ++t) {
+                        const float a0f = fmaxf(__uint_as_float(v[8 * o8 + 2 * t]) + bb[2 * t], 0.0f);
+                        const float a1f = fmaxf(__uint_as_float(v[8 * o8 + 2 * t + 1]) + bb[2 * t + 1], 0.0f);
+                        if constexpr (std::is_same<OT, __half>::value)
+                            reinterpret_cast<__half2*>(&pk)[t] = __floats2half2_rn(fminf(a0f, 65504.0f), fminf(a1f, 65504.0f));
+                        else
+                            reinterpret_cast<__nv_bfloat162*>(&pk)[t] = __floats2bfloat162_rn(a0f, a1f);
+                    }
+                    reinterpret_cast<uint4*>(o)[o8] = pk;
+                }
+            }
+        }
+    }
+    tc::tcgen05_fence_before();
+    __syncthreads();
+    if (warp == 0) {
+        tc::tcgen05_fence_after();
+        tc::tmem_dealloc(tmem_base, ST_TH * 64);
+    }
+}
+
+template <int CIN, typename OT>
+static int launch_stem_tc(const float* x, const float* w, const float* bias, void* y, int B, int H, int W, int P, int Q,
+                          cudaStream_t s) {
+    auto kern = stem_tc_kernel<CIN, OT>;
+    const size_t smem = ST_A_BYTES + ST_B_BYTES + ST_TH * 8 + 16;
+    static bool configured = false;
+    if (!configured) {
+        int st = cuda_status(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "stem tc attr");
+        if (st) return st;
+        configured = true;
+    }
+    const dim3 grid((Q + ST_TW - 1) / ST_TW, (P + ST_TH - 1) / ST_TH, B);
+    kern<<<grid, 128, smem, s>>>(x, w, bias, (OT*)y, H, W, P, Q);
+    return 0;
+}
+
 }  // namespace
 }  // namespace dpft
 
@@ -439,7 +581,8 @@ static int launch_stem(const float* x, const float* w, const float* bias, void* 
 }
 
 extern "C" int dpft_stem_conv7x7_forward(const float* x, const float* w, const float* bias, void* y, int B, int H, int W,
-                                         int Cin, int dtype, void* stream) {
+                                         int Cin, int dtype, int impl, void* stream) {
+    DPFT_REQUIRE(impl >= 0 && impl <= 2, "stem: impl must be 0 (auto), 1 (CUDA cores) or 2 (tensor cores)");
     DPFT_REQUIRE(x && w && bias && y, "stem: null pointer");
     DPFT_REQUIRE(dtype == DPFT_BF16 || dtype == DPFT_F16, "stem: output dtype must be DPFT_BF16 or DPFT_F16");
     DPFT_REQUIRE(Cin == 3 || Cin == 6, "stem: Cin=%d (3 or 6 supported)", Cin);
@@ -449,6 +592,15 @@ extern "C" int dpft_stem_conv7x7_forward(const float* x, const float* w, const f
     const size_t smem = sizeof(float) * (49 * Cin * STEM_COUT + STEM_PH * STEM_PW * Cin);
     cudaStream_t s = (cudaStream_t)stream;
     int st;
+    if (impl == 2 || (impl == 0 && Q >= 64)) {
+        if (Cin == 3) st = dtype == DPFT_F16 ? launch_stem_tc<3, __half>(x, w, bias, y, B, H, W, P, Q, s)
+                                             : launch_stem_tc<3, __nv_bfloat16>(x, w, bias, y, B, H, W, P, Q, s);
+        else st = dtype == DPFT_F16 ? launch_stem_tc<6, __half>(x, w, bias, y, B, H, W, P, Q, s)
+                                    : launch_stem_tc<6, __nv_bfloat16>(x, w, bias, y, B, H, W, P, Q, s);
+        if (st) return st;
+        DPFT_LAUNCH_CHECK("stem_tc_kernel");
+        return DPFT_OK;
+    }
     if (Cin == 3) st = dtype == DPFT_F16 ? launch_stem<3, __half>(x, w, bias, y, H, W, P, Q, grid, smem, s)
                                          : launch_stem<3, __nv_bfloat16>(x, w, bias, y, H, W, P, Q, grid, smem, s);
     else st = dtype == DPFT_F16 ? launch_stem<6, __half>(x, w, bias, y, H, W, P, Q, grid, smem, s)

@@ -28,11 +28,12 @@ def _lib():
     return native.load_library()
 
 
-def stem_forward(x: torch.Tensor, w: torch.Tensor, bias: torch.Tensor, dtype: torch.dtype = torch.bfloat16) -> torch.Tensor:
+def stem_forward(x: torch.Tensor, w: torch.Tensor, bias: torch.Tensor, dtype: torch.dtype = torch.bfloat16,
+                 impl: int = 0) -> torch.Tensor:
     B, H, W, Cin = x.shape
     y = torch.empty((B, (H - 1) // 2 + 1, (W - 1) // 2 + 1, 64), dtype=dtype, device=x.device)
     st = _lib().dpft_stem_conv7x7_forward(native.ptr(x), native.ptr(w), native.ptr(bias), native.ptr(y), B, H, W, Cin,
-                                          native.dtype_code(y), native.stream_ptr(x.device))
+                                          native.dtype_code(y), impl, native.stream_ptr(x.device))
     native.check(st, "dpft_stem_conv7x7_forward")
     native.count_launch()
     return y

@@ -99,10 +99,11 @@ DPFT_API int dpft_conv2d_nhwc(const void* x, const void* w, const float* bias, c
  * ResNet stem: [1x1 adjustment conv (radar, 6 -> 3, resnet.py:47-51) folded into] conv1 7x7 stride 2 pad 3 + BatchNorm
  * (folded) + ReLU, reference src/dprt/models/backbones/resnet.py:98-101 (torchvision conv1/bn1/relu).
  *   x (B, H, W, Cin) f32 NHWC, Cin = 3 or 6, raw 0..255 values;  w [7][7][Cin][64] f32;  bias [64] f32
- *   y (B, P, Q, 64) bf16, P = (H-1)/2+1, Q = (W-1)/2+1
+ *   y (B, P, Q, 64) dtype (DPFT_F16 | DPFT_BF16), P = (H-1)/2+1, Q = (W-1)/2+1
+ * impl: 0 = choose (tcgen05 implicit GEMM with f16 operands for Q >= 64, else the fp32 CUDA-core kernel), 1 / 2 = force.
  */
 DPFT_API int dpft_stem_conv7x7_forward(const float* x, const float* w, const float* bias, void* y, int B, int H, int W,
-                                       int Cin, int dtype, void* stream);
+                                       int Cin, int dtype, int impl, void* stream);
 
 /* torchvision ResNet maxpool (kernel 3, stride 2, padding 1), NHWC bf16, C % 8 == 0.  y (B, (H-1)/2+1, (W-1)/2+1, C). */
 DPFT_API int dpft_maxpool3x3s2_nhwc(const void* x, void* y, int B, int H, int W, int C, int dtype, void* stream);

@@ -45,9 +45,11 @@ def test_stem_and_maxpool(name, view, size):
         t = F.relu(bb.body.bn1(bb.body.conv1(t)))
         want_stem = t.movedim(1, -1)
         want_pool = F.max_pool2d(t, 3, 2, 1).movedim(1, -1)
-    got_stem = features.stem_forward(x, nv.stem_w, nv.stem_b)
-    assert got_stem.shape == want_stem.shape
-    assert _rel(got_stem, want_stem) < 1e-2
+    for impl in (1, 2):                                 # fp32 CUDA-core kernel, tcgen05 kernel with f16 operands
+        for dt in (torch.float16, torch.bfloat16):
+            got_stem = features.stem_forward(x, nv.stem_w, nv.stem_b, dt, impl=impl)
+            assert got_stem.shape == want_stem.shape and got_stem.dtype == dt
+            assert _rel(got_stem, want_stem) < (2e-3 if dt == torch.float16 else 1e-2), (impl, dt, _rel(got_stem, want_stem))
     got_pool = features.maxpool_forward(got_stem)
     assert got_pool.shape == want_pool.shape
     ref_pool = F.max_pool2d(got_stem.float().movedim(-1, 1), 3, 2, 1).movedim(1, -1)
