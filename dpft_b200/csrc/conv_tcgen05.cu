@@ -71,10 +71,12 @@ using namespace tc;
 
 constexpr int EPI_COLS = 64;                       // columns per epilogue item: one 128-byte swizzle row of 16-bit outputs
 constexpr int EPI_BUF_BYTES = 32 * EPI_COLS * 2;   // one warp's [32 rows x 64 cols] sub-tile
-constexpr int EPI_RES_BUFS = 3;                    // residual sub-tiles in flight per warp (two prefetched + one in use)
 constexpr int EPI_OUT_BUFS = 2;
 
-template <int BLOCK_N, int STAGES> struct SmemLayout {
+// EPI_RES_BUFS = residual sub-tiles per warp (EPI_RES_BUFS - 1 prefetched + one in use).  Layers with a short K loop
+// and a residual (the 1x1 "expand" convs) are bound by the residual/output streams, not by the operand pipeline, so
+// they trade operand stages for a deeper residual prefetch.
+template <int BLOCK_N, int STAGES, int EPI_RES_BUFS> struct SmemLayout {
     static constexpr int kABytes = BLOCK_M * BLOCK_K * 2;
     static constexpr int kBBytes = BLOCK_N * BLOCK_K * 2;
     static constexpr int kStageBytes = kABytes + kBBytes;
@@ -94,12 +96,12 @@ template <int N> __device__ __forceinline__ void bulk_wait_read() {
 }
 
 // ---- the kernel -------------------------------------------------------------------------------------------------
-template <int BLOCK_N, int STAGES>
+template <int BLOCK_N, int STAGES, int EPI_RES_BUFS>
 __global__ void __launch_bounds__(kNumThreads, 1)
 conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                  const __grid_constant__ CUtensorMap tmap_d, const __grid_constant__ CUtensorMap tmap_r,
                  const ConvParams prm) {
-    using L = SmemLayout<BLOCK_N, STAGES>;
+    using L = SmemLayout<BLOCK_N, STAGES, EPI_RES_BUFS>;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     uint8_t* smem_a = smem;
@@ -236,8 +238,8 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         int acc = 0;
         uint32_t acc_phase = 0;
         int item = 0;
-        prefetch_residual(0);
-        prefetch_residual(1);
+#pragma unroll
+        for (int i = 0; i < EPI_RES_BUFS - 1; ++i) prefetch_residual(i);
         const int sw = lane & 7;                      // swizzle phase of this thread's row
         for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
             const int m_tile = tile / prm.n_tiles, n_tile = tile % prm.n_tiles;
@@ -332,7 +334,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                                      m_tile * BLOCK_M + quad * 32);
                         bulk_commit();
                     }
-                    prefetch_residual(item + 2);      // refills the buffer consumed by item-1
+                    prefetch_residual(item + EPI_RES_BUFS - 1);   // refills the buffer consumed by item-1
                 }
             }
             tcgen05_fence_before();
@@ -397,20 +399,22 @@ int encode_2d(CUtensorMap* map, const void* base, uint64_t inner, uint64_t outer
     return 0;
 }
 
-template <int BLOCK_N, int STAGES>
+template <int BLOCK_N, int STAGES, int RES_BUFS>
 int launch(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& td, const CUtensorMap& tr, const ConvParams& prm,
            cudaStream_t stream) {
-    using L = SmemLayout<BLOCK_N, STAGES>;
+    using L = SmemLayout<BLOCK_N, STAGES, RES_BUFS>;
+    static_assert(L::kTotal <= 232448, "shared memory budget of one CTA exceeded");
     static bool configured = false;
     if (!configured) {
-        int st = cuda_status(cudaFuncSetAttribute(conv_gemm_kernel<BLOCK_N, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        auto kern = conv_gemm_kernel<BLOCK_N, STAGES, RES_BUFS>;
+        int st = cuda_status(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                                   L::kTotal), "cudaFuncSetAttribute(conv_gemm_kernel)");
         if (st) return st;
         configured = true;
     }
     const int tiles = prm.m_tiles * prm.n_tiles;
     const int grid = tiles < g_sm_count ? tiles : g_sm_count;
-    conv_gemm_kernel<BLOCK_N, STAGES><<<grid, kNumThreads, L::kTotal, stream>>>(ta, tb, td, tr, prm);
+    conv_gemm_kernel<BLOCK_N, STAGES, RES_BUFS><<<grid, kNumThreads, L::kTotal, stream>>>(ta, tb, td, tr, prm);
     DPFT_LAUNCH_CHECK("conv_gemm_kernel");
     return DPFT_OK;
 }
@@ -451,7 +455,7 @@ extern "C" int dpft_fpn_lateral_forward(const void* x, const void* w, const floa
     if (st) return st;
     st = encode_2d(&tb, w, (uint64_t)Cin, 64, (uint64_t)Cin * 2, BLOCK_K, 64, is_f16);
     if (st) return st;
-    return launch<64, 6>(ta, tb, ta, ta, prm, (cudaStream_t)stream);   // d / r maps unused in the fp32 lateral form
+    return launch<64, 6, 3>(ta, tb, ta, ta, prm, (cudaStream_t)stream);   // d / r maps unused in the fp32 lateral form
 }
 
 extern "C" int dpft_conv2d_nhwc(const void* x, const void* w, const float* bias, const void* residual, void* y,
@@ -507,7 +511,8 @@ extern "C" int dpft_conv2d_nhwc(const void* x, const void* w, const float* bias,
     st = encode_2d(&tr, residual ? residual : y, (uint64_t)Cout, (uint64_t)prm.M, (uint64_t)Cout * 2, EPI_COLS, 32, is_f16);
     if (st) return st;
     cudaStream_t s = (cudaStream_t)stream;
-    if (bn == 256) return launch<256, 3>(ta, tb, td, tr, prm, s);
-    if (bn == 128) return launch<128, 4>(ta, tb, td, tr, prm, s);
-    return launch<64, 6>(ta, tb, td, tr, prm, s);
+    const bool stream_bound = residual != nullptr && prm.kblocks <= 4;   // 1x1 expand convs: deep residual prefetch
+    if (bn == 256) return stream_bound ? launch<256, 2, 6>(ta, tb, td, tr, prm, s) : launch<256, 3, 3>(ta, tb, td, tr, prm, s);
+    if (bn == 128) return stream_bound ? launch<128, 2, 7>(ta, tb, td, tr, prm, s) : launch<128, 4, 3>(ta, tb, td, tr, prm, s);
+    return stream_bound ? launch<64, 3, 7>(ta, tb, td, tr, prm, s) : launch<64, 6, 3>(ta, tb, td, tr, prm, s);
 }

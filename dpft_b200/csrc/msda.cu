@@ -98,33 +98,46 @@ msda_fwd_kernel(const T* __restrict__ value, const int64_t* __restrict__ shapes,
 #pragma unroll
     for (int k = 0; k < VEC; ++k) acc[k] = (A)0;
 
-    // The location / weight of sample i+split are fetched while sample i's four corner rows are in flight, so the
-    // dependent chain (location -> address -> corner load) is paid once, not per sample.
-    Pack<T, 2> xy_next = ldg_pack<T, 2>(locg + 2 * (sp < LP ? sp : 0));
-    T a_next = __ldg(attg + (sp < LP ? sp : 0));
-    for (int i = sp; i < LP; i += split) {
-        const int l = i / P;
-        const Pack<T, 2> xy = xy_next;
-        const A a = to_acc<T>(a_next);
-        if (i + split < LP) {
-            xy_next = ldg_pack<T, 2>(locg + 2 * (i + split));
-            a_next = __ldg(attg + i + split);
+    // Two samples per trip: their eight corner-row requests are issued back to back before any of them is consumed, so
+    // each thread keeps 8 x 16 B in flight (the op is bound by memory-level parallelism, not by arithmetic).
+    Pack<T, VEC> z;
+#pragma unroll
+    for (int k = 0; k < VEC; ++k) z.v[k] = from_acc<T>((A)0);
+    for (int i = sp; i < LP; i += 2 * split) {
+        const int i2 = i + split;
+        const bool two = i2 < LP;
+        const int j2 = two ? i2 : i;
+        const int l1 = i / P, l2 = j2 / P;
+        const Pack<T, 2> xy1 = ldg_pack<T, 2>(locg + 2 * i);
+        const Pack<T, 2> xy2 = ldg_pack<T, 2>(locg + 2 * j2);
+        const A a1 = to_acc<T>(__ldg(attg + i));
+        const A a2 = two ? to_acc<T>(__ldg(attg + j2)) : (A)0;
+        const Footprint<A> f1 = footprint<A>(to_acc<T>(xy1.v[0]), to_acc<T>(xy1.v[1]), lv.h[l1], lv.w[l1]);
+        Footprint<A> f2 = footprint<A>(to_acc<T>(xy2.v[0]), to_acc<T>(xy2.v[1]), lv.h[l2], lv.w[l2]);
+        f2.k00 = f2.k00 && two; f2.k01 = f2.k01 && two; f2.k10 = f2.k10 && two; f2.k11 = f2.k11 && two;
+        const T* v1 = vb + lv.start[l1] * MD;
+        const T* v2 = vb + lv.start[l2] * MD;
+        const Pack<T, VEC> p00 = f1.k00 ? ldg_pack<T, VEC>(v1 + (long long)f1.o00 * MD) : z;
+        const Pack<T, VEC> p01 = f1.k01 ? ldg_pack<T, VEC>(v1 + (long long)f1.o01 * MD) : z;
+        const Pack<T, VEC> p10 = f1.k10 ? ldg_pack<T, VEC>(v1 + (long long)f1.o10 * MD) : z;
+        const Pack<T, VEC> p11 = f1.k11 ? ldg_pack<T, VEC>(v1 + (long long)f1.o11 * MD) : z;
+        const Pack<T, VEC> r00 = f2.k00 ? ldg_pack<T, VEC>(v2 + (long long)f2.o00 * MD) : z;
+        const Pack<T, VEC> r01 = f2.k01 ? ldg_pack<T, VEC>(v2 + (long long)f2.o01 * MD) : z;
+        const Pack<T, VEC> r10 = f2.k10 ? ldg_pack<T, VEC>(v2 + (long long)f2.o10 * MD) : z;
+        const Pack<T, VEC> r11 = f2.k11 ? ldg_pack<T, VEC>(v2 + (long long)f2.o11 * MD) : z;
+        {
+            const A w00 = f1.hh * f1.hw, w01 = f1.hh * f1.lw, w10 = f1.lh * f1.hw, w11 = f1.lh * f1.lw;
+#pragma unroll
+            for (int k = 0; k < VEC; ++k)
+                acc[k] += a1 * (w00 * to_acc<T>(p00.v[k]) + w01 * to_acc<T>(p01.v[k]) +
+                                w10 * to_acc<T>(p10.v[k]) + w11 * to_acc<T>(p11.v[k]));
         }
-        const int H = lv.h[l], W = lv.w[l];
-        const Footprint<A> f = footprint<A>(to_acc<T>(xy.v[0]), to_acc<T>(xy.v[1]), H, W);
-        const T* vl = vb + lv.start[l] * MD;
-        Pack<T, VEC> z;
+        {
+            const A w00 = f2.hh * f2.hw, w01 = f2.hh * f2.lw, w10 = f2.lh * f2.hw, w11 = f2.lh * f2.lw;
 #pragma unroll
-        for (int k = 0; k < VEC; ++k) z.v[k] = from_acc<T>((A)0);
-        const Pack<T, VEC> v00 = f.k00 ? ldg_pack<T, VEC>(vl + (long long)f.o00 * MD) : z;
-        const Pack<T, VEC> v01 = f.k01 ? ldg_pack<T, VEC>(vl + (long long)f.o01 * MD) : z;
-        const Pack<T, VEC> v10 = f.k10 ? ldg_pack<T, VEC>(vl + (long long)f.o10 * MD) : z;
-        const Pack<T, VEC> v11 = f.k11 ? ldg_pack<T, VEC>(vl + (long long)f.o11 * MD) : z;
-        const A w00 = f.hh * f.hw, w01 = f.hh * f.lw, w10 = f.lh * f.hw, w11 = f.lh * f.lw;
-#pragma unroll
-        for (int k = 0; k < VEC; ++k) {
-            acc[k] += a * (w00 * to_acc<T>(v00.v[k]) + w01 * to_acc<T>(v01.v[k]) +
-                           w10 * to_acc<T>(v10.v[k]) + w11 * to_acc<T>(v11.v[k]));
+            for (int k = 0; k < VEC; ++k)
+                acc[k] += a2 * (w00 * to_acc<T>(r00.v[k]) + w01 * to_acc<T>(r01.v[k]) +
+                                w10 * to_acc<T>(r10.v[k]) + w11 * to_acc<T>(r11.v[k]));
         }
     }
     // head-weighted reduce across the SPLIT lanes of the group

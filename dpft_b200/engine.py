@@ -57,8 +57,11 @@ class FusedEngine:
         self.pos = fuser.query_embedding.weight.detach().float().contiguous()
         self._row_0001 = torch.tensor([0.0, 0.0, 0.0, 1.0], device=self.device)
         self._param_version = self._version(model)
-        self._graphs: Dict[tuple, "_CapturedForward"] = {}
+        self._graphs: Dict[tuple, List["_CapturedForward"]] = {}
         self._seen: Dict[tuple, int] = {}
+        self._slot = 0
+        self._side_streams = [torch.cuda.Stream(device=self.device) for _ in range(max(0, len(model.inputs) - 1))]
+        self._copy_stream = torch.cuda.Stream(device=self.device)
 
     # -- construction ---------------------------------------------------------------------------------------------
     @staticmethod
@@ -103,7 +106,7 @@ class FusedEngine:
                 or getattr(self.model, "feature_dtype", torch.float16) != self.feature_dtype):   # repack
             self.__init__(self.model)
         x = batch[self.model.inputs[0]]
-        return x.is_cuda and x.dtype == torch.float32
+        return x.dtype == torch.float32 and (x.is_cuda or x.device.type == "cpu")
 
     # -- stage 1: feature pyramids --------------------------------------------------------------------------------
     def pyramids(self, batch: Dict[str, torch.Tensor]) -> List[FeaturePyramid]:
@@ -112,12 +115,37 @@ class FusedEngine:
         out: List[Optional[FeaturePyramid]] = []
         torch_views = [n for n, nv in zip(model.inputs, self.views) if nv is None or not use_native]
         feats = model.extract_features(batch, only=torch_views) if torch_views else {}
-        for name, nv in zip(model.inputs, self.views):
-            if nv is not None and use_native:
-                flat, shapes = nv.pyramid(batch[name])
-                out.append(FeaturePyramid(flat, shapes))
-            else:
-                out.append(FeaturePyramid.from_levels(feats[name]))
+        native_idx = [i for i, nv in enumerate(self.views) if nv is not None and use_native]
+        results: Dict[int, FeaturePyramid] = {}
+        if len(native_idx) > 1 and getattr(model, "parallel_views", True):
+            # the views are independent until the decoder: fork one stream per extra view (the small radar backbones
+            # fill the tails of the camera's kernels), join before decoding
+            main = torch.cuda.current_stream(self.device)
+            fork = torch.cuda.Event()
+            fork.record(main)
+            joins = []
+            for k, i in enumerate(native_idx):
+                name = model.inputs[i]
+                if k == 0:
+                    flat, shapes = self.views[i].pyramid(batch[name])
+                else:
+                    side = self._side_streams[k - 1]
+                    side.wait_event(fork)
+                    with torch.cuda.stream(side):
+                        flat, shapes = self.views[i].pyramid(batch[name])
+                        done = torch.cuda.Event()
+                        done.record(side)
+                    flat.record_stream(main)
+                    joins.append(done)
+                results[i] = FeaturePyramid(flat, shapes)
+            for done in joins:
+                main.wait_event(done)
+        else:
+            for i in native_idx:
+                flat, shapes = self.views[i].pyramid(batch[model.inputs[i]])
+                results[i] = FeaturePyramid(flat, shapes)
+        for i, name in enumerate(model.inputs):
+            out.append(results[i] if i in results else FeaturePyramid.from_levels(feats[name]))
         return out
 
     # -- stage 2: decoder -----------------------------------------------------------------------------------------
@@ -181,22 +209,32 @@ class FusedEngine:
         return keys
 
     def forward(self, batch: Dict[str, torch.Tensor]) -> "OrderedDict[str, torch.Tensor]":
+        """``batch`` may live on the device or on the host (pinned host tensors are uploaded on a copy stream into
+        one of two captured input slots, so the upload of step k+1 overlaps the compute of step k)."""
+        on_host = not batch[self.model.inputs[0]].is_cuda
         if not getattr(self.model, "use_cuda_graph", True) or torch.cuda.is_current_stream_capturing():
-            return self.forward_eager(batch)
+            return self.forward_eager(self._to_device(batch) if on_host else batch)
         sig = tuple((k, tuple(batch[k].shape), batch[k].dtype) for k in self._keys())
-        cap = self._graphs.get(sig)
-        if cap is None:
+        caps = self._graphs.get(sig)
+        if caps is None:
             self._seen[sig] = self._seen.get(sig, 0) + 1
             if self._seen[sig] < 2:                      # first sighting of these shapes: run eagerly (fills the caches)
-                return self.forward_eager(batch)
-            cap = self._graphs[sig] = _CapturedForward(self, batch)
-        return cap.replay(batch)
+                return self.forward_eager(self._to_device(batch) if on_host else batch)
+            dev_batch = self._to_device(batch) if on_host else batch
+            first = _CapturedForward(self, dev_batch, None)
+            caps = self._graphs[sig] = [first, _CapturedForward(self, dev_batch, first.graph.pool())]
+        self._slot ^= 1
+        return caps[self._slot].replay(batch, self._copy_stream if on_host else None)
+
+    def _to_device(self, batch: Dict[str, torch.Tensor]) -> Dict[str, torch.Tensor]:
+        return {k: batch[k].to(self.device, non_blocking=True) for k in self._keys()}
 
 
 class _CapturedForward:
     """One captured forward for one set of input shapes: static input buffers -> graph -> static outputs."""
 
-    def __init__(self, engine: FusedEngine, batch: Dict[str, torch.Tensor]):
+    def __init__(self, engine: FusedEngine, batch: Dict[str, torch.Tensor], pool):
+        self.device = engine.device
         self.keys = engine._keys()
         self.static_in = {k: torch.empty_like(batch[k], device=engine.device) for k in self.keys}
         for k in self.keys:
@@ -208,13 +246,26 @@ class _CapturedForward:
         torch.cuda.current_stream(engine.device).wait_stream(side)
         before = native.launches()
         self.graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(self.graph):
+        with torch.cuda.graph(self.graph, pool=pool):
             self.static_out = engine.forward_eager(self.static_in)
         self.n_launches = native.launches() - before
+        self.consumed = torch.cuda.Event()           # the last replay has finished reading static_in
+        self.consumed.record(torch.cuda.current_stream(self.device))
 
-    def replay(self, batch: Dict[str, torch.Tensor]) -> "OrderedDict[str, torch.Tensor]":
-        for k in self.keys:
-            self.static_in[k].copy_(batch[k], non_blocking=True)
+    def replay(self, batch: Dict[str, torch.Tensor], copy_stream) -> "OrderedDict[str, torch.Tensor]":
+        main = torch.cuda.current_stream(self.device)
+        if copy_stream is None:
+            for k in self.keys:
+                self.static_in[k].copy_(batch[k], non_blocking=True)
+        else:
+            copy_stream.wait_event(self.consumed)
+            with torch.cuda.stream(copy_stream):
+                for k in self.keys:
+                    self.static_in[k].copy_(batch[k], non_blocking=True)
+                uploaded = torch.cuda.Event()
+                uploaded.record(copy_stream)
+            main.wait_event(uploaded)
         self.graph.replay()
+        self.consumed.record(main)
         native.count_launch(self.n_launches)
         return OrderedDict((k, v.clone()) for k, v in self.static_out.items())
