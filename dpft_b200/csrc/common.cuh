@@ -55,6 +55,26 @@ template <typename T, int VEC> __device__ __forceinline__ Pack<T, VEC> ldg_pack(
     u.r = __ldg(reinterpret_cast<const Raw*>(p));
     return u.k;
 }
+// Raw (untyped) variant + a scheduling pin: `pin_loaded` emits no instruction but makes the compiler treat the loaded
+// registers as consumed/redefined at that point, so every conversion of the loaded bits is scheduled after it.  Used to
+// keep a batch of independent gather loads back to back instead of interleaved with the unpacking of the first ones.
+template <typename T, int VEC> __device__ __forceinline__ typename RawOf<sizeof(T) * VEC>::type ldg_raw(const T* p) {
+    using Raw = typename RawOf<sizeof(T) * VEC>::type;
+    return __ldg(reinterpret_cast<const Raw*>(p));
+}
+template <typename T, int VEC> __device__ __forceinline__ Pack<T, VEC> unpack_raw(const typename RawOf<sizeof(T) * VEC>::type& r) {
+    using Raw = typename RawOf<sizeof(T) * VEC>::type;
+    union { Raw rr; Pack<T, VEC> k; } u;
+    u.rr = r;
+    return u.k;
+}
+__device__ __forceinline__ void pin_loaded(uint4& r) { asm volatile("" : "+r"(r.x), "+r"(r.y), "+r"(r.z), "+r"(r.w)); }
+__device__ __forceinline__ void pin_loaded(uint2& r) { asm volatile("" : "+r"(r.x), "+r"(r.y)); }
+__device__ __forceinline__ void pin_loaded(unsigned int& r) { asm volatile("" : "+r"(r)); }
+__device__ __forceinline__ void pin_loaded(unsigned short& r) { asm volatile("" : "+h"(r)); }
+__device__ __forceinline__ void issue_barrier() { asm volatile("" ::: "memory"); }
+template <typename Raw> __device__ __forceinline__ Raw raw_zero() { Raw r; memset(&r, 0, sizeof(Raw)); return r; }
+
 template <typename T, int VEC> __device__ __forceinline__ void st_pack(T* p, const Pack<T, VEC>& k) {
     using Raw = typename RawOf<sizeof(T) * VEC>::type;
     union { Raw r; Pack<T, VEC> kk; } u;

@@ -295,30 +295,39 @@ decoder_layer_kernel(const LayerParams prm) {
             const float ly = ref_v + oy / (float)H;
             const float w_im = lx * (float)W - 0.5f;
             const float h_im = ly * (float)H - 0.5f;
-            if (h_im > -1.0f && w_im > -1.0f && h_im < (float)H && w_im < (float)W) {
-                const float hf = floorf(h_im), wf = floorf(w_im);
-                const int h0 = (int)hf, w0 = (int)wf;
-                const float lh = h_im - hf, lw = w_im - wf, hh = 1.0f - lh, hw = 1.0f - lw;
-                const bool t_ok = h0 >= 0, b_ok = h0 + 1 <= H - 1, l_ok = w0 >= 0, r_ok = w0 + 1 <= W - 1;
-                const float wt[4] = {t_ok && l_ok ? hh * hw * a : 0.0f, t_ok && r_ok ? hh * lw * a : 0.0f,
-                                     b_ok && l_ok ? lh * hw * a : 0.0f, b_ok && r_ok ? lh * lw * a : 0.0f};
-                const long long base = (long long)h0 * W + w0;
-                const long long offs[4] = {base, base + 1, base + W, base + W + 1};
+            // Unconditional loads from clamped corner addresses (weight 0 where the corner or the whole sample is out of
+            // bounds): the sixteen 16-byte row requests of a sample issue back to back instead of behind four branches.
+            const bool inside = h_im > -1.0f && w_im > -1.0f && h_im < (float)H && w_im < (float)W;
+            const float hs = inside ? h_im : 0.0f, ws = inside ? w_im : 0.0f;
+            const float hf = floorf(hs), wf = floorf(ws);
+            const int h0 = (int)hf, w0 = (int)wf;
+            const float lh = hs - hf, lw = ws - wf, hh = 1.0f - lh, hw = 1.0f - lw;
+            const bool t_ok = inside && h0 >= 0, b_ok = inside && h0 + 1 <= H - 1;
+            const bool l_ok = w0 >= 0, r_ok = w0 + 1 <= W - 1;
+            const float wt[4] = {t_ok && l_ok ? hh * hw * a : 0.0f, t_ok && r_ok ? hh * lw * a : 0.0f,
+                                 b_ok && l_ok ? lh * hw * a : 0.0f, b_ok && r_ok ? lh * lw * a : 0.0f};
+            const int h0c = min(max(h0, 0), H - 1), h1c = min(max(h0 + 1, 0), H - 1);
+            const int w0c = min(max(w0, 0), W - 1), w1c = min(max(w0 + 1, 0), W - 1);
+            const float4* rows[4] = {reinterpret_cast<const float4*>(lvl + ((long long)h0c * W + w0c) * C),
+                                     reinterpret_cast<const float4*>(lvl + ((long long)h0c * W + w1c) * C),
+                                     reinterpret_cast<const float4*>(lvl + ((long long)h1c * W + w0c) * C),
+                                     reinterpret_cast<const float4*>(lvl + ((long long)h1c * W + w1c) * C)};
+            float4 f[4][4];
 #pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                    if (wt[k] != 0.0f) {
-                        const float4* row = reinterpret_cast<const float4*>(lvl + offs[k] * C);
+            for (int k = 0; k < 4; ++k) {
 #pragma unroll
-                        for (int c4 = 0; c4 < 4; ++c4) {
-                            const float4 f = __ldg(row + c4);
-                            agg[4 * c4] = fmaf(wt[k], f.x, agg[4 * c4]);
-                            agg[4 * c4 + 1] = fmaf(wt[k], f.y, agg[4 * c4 + 1]);
-                            agg[4 * c4 + 2] = fmaf(wt[k], f.z, agg[4 * c4 + 2]);
-                            agg[4 * c4 + 3] = fmaf(wt[k], f.w, agg[4 * c4 + 3]);
-                        }
-                        inb += wt[k];
-                    }
+                for (int c4 = 0; c4 < 4; ++c4) f[k][c4] = __ldg(rows[k] + c4);
+            }
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+#pragma unroll
+                for (int c4 = 0; c4 < 4; ++c4) {
+                    agg[4 * c4] = fmaf(wt[k], f[k][c4].x, agg[4 * c4]);
+                    agg[4 * c4 + 1] = fmaf(wt[k], f[k][c4].y, agg[4 * c4 + 1]);
+                    agg[4 * c4 + 2] = fmaf(wt[k], f[k][c4].z, agg[4 * c4 + 2]);
+                    agg[4 * c4 + 3] = fmaf(wt[k], f[k][c4].w, agg[4 * c4 + 3]);
                 }
+                inb += wt[k];
             }
         }
     }
