@@ -80,9 +80,10 @@ template <int BLOCK_N, int STAGES, int EPI_RES_BUFS> struct SmemLayout {
     static constexpr int kABytes = BLOCK_M * BLOCK_K * 2;
     static constexpr int kBBytes = BLOCK_N * BLOCK_K * 2;
     static constexpr int kStageBytes = kABytes + kBBytes;
-    static constexpr int kEpiBytes = 4 * (EPI_RES_BUFS + EPI_OUT_BUFS) * EPI_BUF_BYTES;     // 80 KB
+    static constexpr int kEpiBytes = 4 * (EPI_RES_BUFS + EPI_OUT_BUFS) * EPI_BUF_BYTES;
+    static constexpr int kBiasBytes = 2 * BLOCK_N * 4;                                      // double-buffered tile bias
     static constexpr int kBarrierBytes = (2 * STAGES + 4 + 4 * EPI_RES_BUFS) * 8 + 16;
-    static constexpr int kTotal = STAGES * kStageBytes + kEpiBytes + kBarrierBytes + 1024;  // +1024: alignment slack
+    static constexpr int kTotal = STAGES * kStageBytes + kEpiBytes + kBiasBytes + kBarrierBytes;
 };
 
 __device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, const void* src, int c0, int c1) {
@@ -102,12 +103,13 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                  const __grid_constant__ CUtensorMap tmap_d, const __grid_constant__ CUtensorMap tmap_r,
                  const ConvParams prm) {
     using L = SmemLayout<BLOCK_N, STAGES, EPI_RES_BUFS>;
-    extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    extern __shared__ __align__(1024) uint8_t smem[];                    // 128-byte swizzle needs 1024-byte alignment
+    if ((smem_u32(smem) & 1023u) != 0) __trap();
     uint8_t* smem_a = smem;
     uint8_t* smem_b = smem + STAGES * L::kABytes;
-    uint8_t* smem_epi = smem + STAGES * L::kStageBytes;                  // per warp: 3 residual + 2 output sub-tiles
-    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem_epi + L::kEpiBytes);
+    uint8_t* smem_epi = smem + STAGES * L::kStageBytes;                  // per warp: residual + output sub-tiles
+    float* smem_bias = reinterpret_cast<float*>(smem_epi + L::kEpiBytes);   // [2][BLOCK_N]
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem_epi + L::kEpiBytes + L::kBiasBytes);
     uint64_t* empty_bar = full_bar + STAGES;
     uint64_t* tmem_full = empty_bar + STAGES;
     uint64_t* tmem_empty = tmem_full + 2;
@@ -238,6 +240,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         int acc = 0;
         uint32_t acc_phase = 0;
         int item = 0;
+        int tile_count = 0;
 #pragma unroll
         for (int i = 0; i < EPI_RES_BUFS - 1; ++i) prefetch_residual(i);
         const int sw = lane & 7;                      // swizzle phase of this thread's row
@@ -246,6 +249,12 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
             mbar_wait(&tmem_full[acc], acc_phase);
             tcgen05_fence_after();
             const int n0 = n_tile * BLOCK_N;
+            // this tile's bias -> shared memory (double-buffered; one named barrier per tile among the 4 epilogue warps)
+            float* bias_s = smem_bias + (tile_count & 1) * BLOCK_N;
+            for (int i = (quad * 32 + lane) * 4; i < BLOCK_N; i += 128 * 4)
+                *reinterpret_cast<float4*>(bias_s + i) = __ldg(reinterpret_cast<const float4*>(prm.bias + n0 + i));
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+            ++tile_count;
             if (prm.out_f32) {
                 // FPN lateral: inner = conv1x1 + bias (+ top-down), 16 fp32 channels per pixel, written directly
                 const long long m = (long long)m_tile * BLOCK_M + quad * 32 + lane;
@@ -265,7 +274,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                     float4* o = reinterpret_cast<float4*>(prm.out_f32 + m * 16);
 #pragma unroll
                     for (int j4 = 0; j4 < 4; ++j4) {
-                        const float4 bv = __ldg(reinterpret_cast<const float4*>(prm.bias) + j4);
+                        const float4 bv = *reinterpret_cast<const float4*>(bias_s + 4 * j4);
                         float4 r = make_float4(__uint_as_float(v[4 * j4]) + bv.x, __uint_as_float(v[4 * j4 + 1]) + bv.y,
                                                __uint_as_float(v[4 * j4 + 2]) + bv.z, __uint_as_float(v[4 * j4 + 3]) + bv.w);
                         if (cp) {
@@ -283,7 +292,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                     tmem_ld_32x32b_x32(taddr, v);
                     tmem_ld_32x32b_x32(taddr + 32, v + 32);
                     tmem_ld_wait();
-                    const float4* bias4 = reinterpret_cast<const float4*>(prm.bias + n0 + c * EPI_COLS);
+                    const float4* bias4 = reinterpret_cast<const float4*>(bias_s + c * EPI_COLS);
                     const uint8_t* rrow = res_buf + (item % EPI_RES_BUFS) * EPI_BUF_BYTES + lane * 128;
                     if (has_res) mbar_wait(&my_res_bar[item % EPI_RES_BUFS], (uint32_t)((item / EPI_RES_BUFS) & 1));
                     // the output buffer of item-2 must have been read by its TMA store before it is overwritten
@@ -293,7 +302,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
 #pragma unroll
                     for (int j = 0; j < EPI_COLS / 8; ++j) {       // 8 columns = one 16-byte chunk of the row
                         float f[8];
-                        const float4 b0 = __ldg(bias4 + 2 * j), b1 = __ldg(bias4 + 2 * j + 1);
+                        const float4 b0 = bias4[2 * j], b1 = bias4[2 * j + 1];
                         f[0] = __uint_as_float(v[8 * j]) + b0.x;     f[1] = __uint_as_float(v[8 * j + 1]) + b0.y;
                         f[2] = __uint_as_float(v[8 * j + 2]) + b0.z; f[3] = __uint_as_float(v[8 * j + 3]) + b0.w;
                         f[4] = __uint_as_float(v[8 * j + 4]) + b1.x; f[5] = __uint_as_float(v[8 * j + 5]) + b1.y;
@@ -512,7 +521,7 @@ extern "C" int dpft_conv2d_nhwc(const void* x, const void* w, const float* bias,
     if (st) return st;
     cudaStream_t s = (cudaStream_t)stream;
     const bool stream_bound = residual != nullptr && prm.kblocks <= 4;   // 1x1 expand convs: deep residual prefetch
-    if (bn == 256) return stream_bound ? launch<256, 2, 6>(ta, tb, td, tr, prm, s) : launch<256, 3, 3>(ta, tb, td, tr, prm, s);
+    if (bn == 256) return stream_bound ? launch<256, 2, 5>(ta, tb, td, tr, prm, s) : launch<256, 3, 3>(ta, tb, td, tr, prm, s);
     if (bn == 128) return stream_bound ? launch<128, 2, 7>(ta, tb, td, tr, prm, s) : launch<128, 4, 3>(ta, tb, td, tr, prm, s);
     return stream_bound ? launch<64, 3, 7>(ta, tb, td, tr, prm, s) : launch<64, 6, 3>(ta, tb, td, tr, prm, s);
 }

@@ -98,84 +98,76 @@ msda_fwd_kernel(const T* __restrict__ value, const int64_t* __restrict__ shapes,
 #pragma unroll
     for (int k = 0; k < VEC; ++k) acc[k] = (A)0;
 
-    // Two samples per trip: their eight corner-row requests are issued back to back before any of them is consumed, so
-    // each thread keeps 8 x 16 B in flight (the op is bound by memory-level parallelism, not by arithmetic).
+    // The op is bound by memory-level parallelism, and the best issue pattern differs by element size (measured on B200,
+    // BASELINE config 5, D = 32): 32/64-bit values gain from two samples per trip (eight 16-byte corner requests issued back
+    // to back: 0.76 -> 0.95 of the HBM roofline), while for 16-bit values the unpack arithmetic that the scheduler
+    // interleaves with the loads and the extra registers cost more than they win (0.61 -> 0.48), so they keep one sample per
+    // trip with the next sample's (location, weight) words prefetched.
     Pack<T, VEC> z;
 #pragma unroll
     for (int k = 0; k < VEC; ++k) z.v[k] = from_acc<T>((A)0);
-    // Software pipeline: the (location, weight) words of the NEXT trip are requested before this trip's corner rows,
-    // so they arrive while the rows are in flight and the next trip starts without a dependent-load bubble.
-    using RawXY = typename RawOf<sizeof(T) * 2>::type;
-    using RawA = typename RawOf<sizeof(T)>::type;
-    RawXY nxy1 = raw_zero<RawXY>(), nxy2 = raw_zero<RawXY>();
-    RawA na1 = raw_zero<RawA>(), na2 = raw_zero<RawA>();
-    if (sp < LP) {
-        nxy1 = ldg_raw<T, 2>(locg + 2 * sp);
-        na1 = ldg_raw<T, 1>(attg + sp);
-        if (sp + split < LP) {
-            nxy2 = ldg_raw<T, 2>(locg + 2 * (sp + split));
-            na2 = ldg_raw<T, 1>(attg + sp + split);
-        }
-    }
-    for (int i = sp; i < LP; i += 2 * split) {
-        const int i2 = i + split;
-        const bool two = i2 < LP;
-        const int j2 = two ? i2 : i;
-        const int l1 = i / P, l2 = j2 / P;
-        RawXY cxy1 = nxy1, cxy2 = nxy2;
-        RawA ca1 = na1, ca2 = na2;
-        {
-            const int n1 = i + 2 * split, n2 = n1 + split;
-            if (n1 < LP) {
-                nxy1 = ldg_raw<T, 2>(locg + 2 * n1);
-                na1 = ldg_raw<T, 1>(attg + n1);
+    if constexpr (sizeof(T) >= 4) {
+        for (int i = sp; i < LP; i += 2 * split) {
+            const int i2 = i + split;
+            const bool two = i2 < LP;
+            const int j2 = two ? i2 : i;
+            const int l1 = i / P, l2 = j2 / P;
+            const Pack<T, 2> xy1 = ldg_pack<T, 2>(locg + 2 * i);
+            const Pack<T, 2> xy2 = ldg_pack<T, 2>(locg + 2 * j2);
+            const A a1 = to_acc<T>(__ldg(attg + i));
+            const A a2 = two ? to_acc<T>(__ldg(attg + j2)) : (A)0;
+            const Footprint<A> f1 = footprint<A>(to_acc<T>(xy1.v[0]), to_acc<T>(xy1.v[1]), lv.h[l1], lv.w[l1]);
+            Footprint<A> f2 = footprint<A>(to_acc<T>(xy2.v[0]), to_acc<T>(xy2.v[1]), lv.h[l2], lv.w[l2]);
+            f2.k00 = f2.k00 && two; f2.k01 = f2.k01 && two; f2.k10 = f2.k10 && two; f2.k11 = f2.k11 && two;
+            const T* v1 = vb + lv.start[l1] * MD;
+            const T* v2 = vb + lv.start[l2] * MD;
+            const Pack<T, VEC> p00 = f1.k00 ? ldg_pack<T, VEC>(v1 + (long long)f1.o00 * MD) : z;
+            const Pack<T, VEC> p01 = f1.k01 ? ldg_pack<T, VEC>(v1 + (long long)f1.o01 * MD) : z;
+            const Pack<T, VEC> p10 = f1.k10 ? ldg_pack<T, VEC>(v1 + (long long)f1.o10 * MD) : z;
+            const Pack<T, VEC> p11 = f1.k11 ? ldg_pack<T, VEC>(v1 + (long long)f1.o11 * MD) : z;
+            const Pack<T, VEC> r00 = f2.k00 ? ldg_pack<T, VEC>(v2 + (long long)f2.o00 * MD) : z;
+            const Pack<T, VEC> r01 = f2.k01 ? ldg_pack<T, VEC>(v2 + (long long)f2.o01 * MD) : z;
+            const Pack<T, VEC> r10 = f2.k10 ? ldg_pack<T, VEC>(v2 + (long long)f2.o10 * MD) : z;
+            const Pack<T, VEC> r11 = f2.k11 ? ldg_pack<T, VEC>(v2 + (long long)f2.o11 * MD) : z;
+            {
+                const A w00 = f1.hh * f1.hw, w01 = f1.hh * f1.lw, w10 = f1.lh * f1.hw, w11 = f1.lh * f1.lw;
+#pragma unroll
+                for (int k = 0; k < VEC; ++k)
+                    acc[k] += a1 * (w00 * to_acc<T>(p00.v[k]) + w01 * to_acc<T>(p01.v[k]) +
+                                    w10 * to_acc<T>(p10.v[k]) + w11 * to_acc<T>(p11.v[k]));
             }
-            if (n2 < LP) {
-                nxy2 = ldg_raw<T, 2>(locg + 2 * n2);
-                na2 = ldg_raw<T, 1>(attg + n2);
+            {
+                const A w00 = f2.hh * f2.hw, w01 = f2.hh * f2.lw, w10 = f2.lh * f2.hw, w11 = f2.lh * f2.lw;
+#pragma unroll
+                for (int k = 0; k < VEC; ++k)
+                    acc[k] += a2 * (w00 * to_acc<T>(r00.v[k]) + w01 * to_acc<T>(r01.v[k]) +
+                                    w10 * to_acc<T>(r10.v[k]) + w11 * to_acc<T>(r11.v[k]));
             }
-            issue_barrier();
         }
-        pin_loaded(cxy1); pin_loaded(cxy2); pin_loaded(ca1); pin_loaded(ca2);
-        const Pack<T, 2> xy1 = unpack_raw<T, 2>(cxy1);
-        const Pack<T, 2> xy2 = two ? unpack_raw<T, 2>(cxy2) : xy1;
-        const A a1 = to_acc<T>(unpack_raw<T, 1>(ca1).v[0]);
-        const A a2 = two ? to_acc<T>(unpack_raw<T, 1>(ca2).v[0]) : (A)0;
-        const Footprint<A> f1 = footprint<A>(to_acc<T>(xy1.v[0]), to_acc<T>(xy1.v[1]), lv.h[l1], lv.w[l1]);
-        Footprint<A> f2 = footprint<A>(to_acc<T>(xy2.v[0]), to_acc<T>(xy2.v[1]), lv.h[l2], lv.w[l2]);
-        f2.k00 = f2.k00 && two; f2.k01 = f2.k01 && two; f2.k10 = f2.k10 && two; f2.k11 = f2.k11 && two;
-        const T* v1 = vb + lv.start[l1] * MD;
-        const T* v2 = vb + lv.start[l2] * MD;
-        using Raw = typename RawOf<sizeof(T) * VEC>::type;
-        Raw q[8];
-        q[0] = f1.k00 ? ldg_raw<T, VEC>(v1 + (long long)f1.o00 * MD) : raw_zero<Raw>();
-        q[1] = f1.k01 ? ldg_raw<T, VEC>(v1 + (long long)f1.o01 * MD) : raw_zero<Raw>();
-        q[2] = f1.k10 ? ldg_raw<T, VEC>(v1 + (long long)f1.o10 * MD) : raw_zero<Raw>();
-        q[3] = f1.k11 ? ldg_raw<T, VEC>(v1 + (long long)f1.o11 * MD) : raw_zero<Raw>();
-        q[4] = f2.k00 ? ldg_raw<T, VEC>(v2 + (long long)f2.o00 * MD) : raw_zero<Raw>();
-        q[5] = f2.k01 ? ldg_raw<T, VEC>(v2 + (long long)f2.o01 * MD) : raw_zero<Raw>();
-        q[6] = f2.k10 ? ldg_raw<T, VEC>(v2 + (long long)f2.o10 * MD) : raw_zero<Raw>();
-        q[7] = f2.k11 ? ldg_raw<T, VEC>(v2 + (long long)f2.o11 * MD) : raw_zero<Raw>();
-        issue_barrier();                       // all eight requests are in flight before any of them is unpacked
+    } else {
+        Pack<T, 2> xy_next = ldg_pack<T, 2>(locg + 2 * (sp < LP ? sp : 0));
+        T a_next = __ldg(attg + (sp < LP ? sp : 0));
+        for (int i = sp; i < LP; i += split) {
+            const int l = i / P;
+            const Pack<T, 2> xy = xy_next;
+            const A a = to_acc<T>(a_next);
+            if (i + split < LP) {
+                xy_next = ldg_pack<T, 2>(locg + 2 * (i + split));
+                a_next = __ldg(attg + i + split);
+            }
+            const int H = lv.h[l], W = lv.w[l];
+            const Footprint<A> f = footprint<A>(to_acc<T>(xy.v[0]), to_acc<T>(xy.v[1]), H, W);
+            const T* vl = vb + lv.start[l] * MD;
+            const Pack<T, VEC> v00 = f.k00 ? ldg_pack<T, VEC>(vl + (long long)f.o00 * MD) : z;
+            const Pack<T, VEC> v01 = f.k01 ? ldg_pack<T, VEC>(vl + (long long)f.o01 * MD) : z;
+            const Pack<T, VEC> v10 = f.k10 ? ldg_pack<T, VEC>(vl + (long long)f.o10 * MD) : z;
+            const Pack<T, VEC> v11 = f.k11 ? ldg_pack<T, VEC>(vl + (long long)f.o11 * MD) : z;
+            const A w00 = f.hh * f.hw, w01 = f.hh * f.lw, w10 = f.lh * f.hw, w11 = f.lh * f.lw;
 #pragma unroll
-        for (int t = 0; t < 8; ++t) pin_loaded(q[t]);
-        const Pack<T, VEC> p00 = unpack_raw<T, VEC>(q[0]), p01 = unpack_raw<T, VEC>(q[1]);
-        const Pack<T, VEC> p10 = unpack_raw<T, VEC>(q[2]), p11 = unpack_raw<T, VEC>(q[3]);
-        const Pack<T, VEC> r00 = unpack_raw<T, VEC>(q[4]), r01 = unpack_raw<T, VEC>(q[5]);
-        const Pack<T, VEC> r10 = unpack_raw<T, VEC>(q[6]), r11 = unpack_raw<T, VEC>(q[7]);
-        {
-            const A w00 = f1.hh * f1.hw, w01 = f1.hh * f1.lw, w10 = f1.lh * f1.hw, w11 = f1.lh * f1.lw;
-#pragma unroll
-            for (int k = 0; k < VEC; ++k)
-                acc[k] += a1 * (w00 * to_acc<T>(p00.v[k]) + w01 * to_acc<T>(p01.v[k]) +
-                                w10 * to_acc<T>(p10.v[k]) + w11 * to_acc<T>(p11.v[k]));
-        }
-        {
-            const A w00 = f2.hh * f2.hw, w01 = f2.hh * f2.lw, w10 = f2.lh * f2.hw, w11 = f2.lh * f2.lw;
-#pragma unroll
-            for (int k = 0; k < VEC; ++k)
-                acc[k] += a2 * (w00 * to_acc<T>(r00.v[k]) + w01 * to_acc<T>(r01.v[k]) +
-                                w10 * to_acc<T>(r10.v[k]) + w11 * to_acc<T>(r11.v[k]));
+            for (int k = 0; k < VEC; ++k) {
+                acc[k] += a * (w00 * to_acc<T>(v00.v[k]) + w01 * to_acc<T>(v01.v[k]) +
+                               w10 * to_acc<T>(v10.v[k]) + w11 * to_acc<T>(v11.v[k]));
+            }
         }
     }
     // head-weighted reduce across the SPLIT lanes of the group
@@ -288,17 +280,10 @@ msda_bwd_kernel(const T* __restrict__ value, const int64_t* __restrict__ shapes,
         Pack<T, VEC> z;
 #pragma unroll
         for (int k = 0; k < VEC; ++k) z.v[k] = from_acc<T>((A)0);
-        using Raw = typename RawOf<sizeof(T) * VEC>::type;
-        Raw q[4];
-        q[0] = f.k00 ? ldg_raw<T, VEC>(vl + (long long)f.o00 * MD) : raw_zero<Raw>();
-        q[1] = f.k01 ? ldg_raw<T, VEC>(vl + (long long)f.o01 * MD) : raw_zero<Raw>();
-        q[2] = f.k10 ? ldg_raw<T, VEC>(vl + (long long)f.o10 * MD) : raw_zero<Raw>();
-        q[3] = f.k11 ? ldg_raw<T, VEC>(vl + (long long)f.o11 * MD) : raw_zero<Raw>();
-        issue_barrier();
-#pragma unroll
-        for (int t = 0; t < 4; ++t) pin_loaded(q[t]);
-        const Pack<T, VEC> v00 = unpack_raw<T, VEC>(q[0]), v01 = unpack_raw<T, VEC>(q[1]);
-        const Pack<T, VEC> v10 = unpack_raw<T, VEC>(q[2]), v11 = unpack_raw<T, VEC>(q[3]);
+        const Pack<T, VEC> v00 = f.k00 ? ldg_pack<T, VEC>(vl + (long long)f.o00 * MD) : z;
+        const Pack<T, VEC> v01 = f.k01 ? ldg_pack<T, VEC>(vl + (long long)f.o01 * MD) : z;
+        const Pack<T, VEC> v10 = f.k10 ? ldg_pack<T, VEC>(vl + (long long)f.o10 * MD) : z;
+        const Pack<T, VEC> v11 = f.k11 ? ldg_pack<T, VEC>(vl + (long long)f.o11 * MD) : z;
         const A w00 = f.hh * f.hw, w01 = f.hh * f.lw, w10 = f.lh * f.hw, w11 = f.lh * f.lw;
 
         A ga = (A)0, gx = (A)0, gy = (A)0;
