@@ -213,8 +213,9 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     } else {
         // ======================================= epilogue =======================================
         // Each warp owns the TMEM lane quadrant warp%4 = 32 rows of the tile and walks it in [32 x 64] "items".
-        // Output items are staged in shared memory (128-byte swizzle) and written by TMA; residual items are
-        // prefetched by TMA two items ahead so the loads overlap the arithmetic.
+        // Output items are staged in shared memory (128-byte swizzle, conflict-free row writes) and written out with
+        // coalesced 16-byte stores (4 full rows per instruction); residual items are prefetched by TMA several items
+        // ahead so the loads overlap the arithmetic.
         const int quad = warp & 3;
         uint8_t* my_smem = smem_epi + quad * (EPI_RES_BUFS + EPI_OUT_BUFS) * EPI_BUF_BYTES;
         uint8_t* res_buf = my_smem;
@@ -295,9 +296,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                     const float4* bias4 = reinterpret_cast<const float4*>(bias_s + c * EPI_COLS);
                     const uint8_t* rrow = res_buf + (item % EPI_RES_BUFS) * EPI_BUF_BYTES + lane * 128;
                     if (has_res) mbar_wait(&my_res_bar[item % EPI_RES_BUFS], (uint32_t)((item / EPI_RES_BUFS) & 1));
-                    // the output buffer of item-2 must have been read by its TMA store before it is overwritten
-                    if (lane == 0) bulk_wait_read<EPI_OUT_BUFS - 1>();
-                    __syncwarp();
+                    __syncwarp();                     // the staging buffer was read back two items ago
                     uint8_t* orow = out_buf + (item % EPI_OUT_BUFS) * EPI_BUF_BYTES + lane * 128;
 #pragma unroll
                     for (int j = 0; j < EPI_COLS / 8; ++j) {       // 8 columns = one 16-byte chunk of the row
@@ -336,12 +335,19 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                         }
                         *reinterpret_cast<uint4*>(orow + phys) = ov;
                     }
-                    fence_proxy_async();              // make the generic-proxy smem writes visible to the TMA engine
-                    __syncwarp();                     // all rows written (and this item's residual rows consumed)
-                    if (lane == 0) {
-                        tma_store_2d(&tmap_d, out_buf + (item % EPI_OUT_BUFS) * EPI_BUF_BYTES, n0 + c * EPI_COLS,
-                                     m_tile * BLOCK_M + quad * 32);
-                        bulk_commit();
+                    __syncwarp();                     // all 32 rows staged (and this item's residual rows consumed)
+                    // write-out: each instruction stores 4 complete rows x 128 B (8 lanes per row) — fully coalesced
+                    {
+                        const uint8_t* obuf = out_buf + (item % EPI_OUT_BUFS) * EPI_BUF_BYTES;
+                        const long long m_base = (long long)m_tile * BLOCK_M + quad * 32;
+                        const int chunk = lane & 7;
+                        uint8_t* gout = reinterpret_cast<uint8_t*>(prm.out) + ((long long)(n0 + c * EPI_COLS) + chunk * 8) * 2;
+#pragma unroll
+                        for (int it = 0; it < 8; ++it) {
+                            const int r = it * 4 + (lane >> 3);
+                            const uint4 ov = *reinterpret_cast<const uint4*>(obuf + r * 128 + ((chunk ^ (r & 7)) << 4));
+                            if (m_base + r < prm.M) *reinterpret_cast<uint4*>(gout + (m_base + r) * prm.N * 2) = ov;
+                        }
                     }
                     prefetch_residual(item + EPI_RES_BUFS - 1);   // refills the buffer consumed by item-1
                 }
@@ -351,7 +357,6 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
             if (lane == 0) mbar_arrive(&tmem_empty[acc]);
             if (++acc == 2) { acc = 0; acc_phase ^= 1; }
         }
-        if (lane == 0) bulk_wait_read<0>();           // smem must stay valid until the last stores have read it
     }
 
     tcgen05_fence_before();

@@ -183,6 +183,106 @@ msda_fwd_kernel(const T* __restrict__ value, const int64_t* __restrict__ shapes,
     }
 }
 
+// Forward variant for 16-byte corner slices of 16-bit values: the four corner rows of each sample are fetched with
+// cp.async (LDGSTS, L2 -> shared memory, zero-fill for out-of-bounds corners) into a per-thread ring of RING slots, so
+// RING samples x 64 B per thread are in flight without holding them in registers, and the unpack / FMA work of sample n
+// overlaps the requests of samples n+1 .. n+RING-1.  No cross-thread communication: each thread only reads what it wrote.
+constexpr int kRing = 4;
+
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, bool valid) {
+    const int bytes = valid ? 16 : 0;               // src-size 0: the 16 destination bytes are zero-filled
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+template <typename T, int D, int VEC>
+__global__ void __launch_bounds__(kThreads)
+msda_fwd_ring_kernel(const T* __restrict__ value, const int64_t* __restrict__ shapes, const int64_t* __restrict__ lsi,
+                     const T* __restrict__ loc, const T* __restrict__ attn, T* __restrict__ out,
+                     int S, int M, int N, int L, int P, int split_log2, long long n_groups) {
+    static_assert(sizeof(T) * VEC == 16, "ring variant moves 16-byte corner slices");
+    using A = typename AccOf<T>::type;
+    constexpr int CH = D / VEC;
+    extern __shared__ __align__(16) uint8_t ring_smem[];     // [kRing][4 corners][kThreads] x 16 B
+    __shared__ LevelTable lv;
+    load_levels(lv, shapes, lsi, L);
+
+    const int lanes_log2 = ilog2_floor(CH) + split_log2;
+    const long long gtid = (long long)blockIdx.x * kThreads + threadIdx.x;
+    long long group = gtid >> lanes_log2;
+    const int sub = (int)(gtid & ((1 << lanes_log2) - 1));
+    const int chunk = sub & (CH - 1);
+    const int sp = sub >> ilog2_floor(CH);
+    const int split = 1 << split_log2;
+    const bool active = group < n_groups;
+    if (!active) group = n_groups - 1;
+
+    const int m = (int)(group % M);
+    const long long b = group / ((long long)M * N);
+    const int MD = M * D;
+    const T* vb = value + (b * S) * MD + m * D + chunk * VEC;
+    const int LP = L * P;
+    const T* locg = loc + group * LP * 2;
+    const T* attg = attn + group * LP;
+    const uint32_t slot0 = (uint32_t)__cvta_generic_to_shared(ring_smem) + threadIdx.x * 16;
+    const int count = sp < LP ? (LP - sp + split - 1) >> split_log2 : 0;
+
+    A acc[VEC];
+#pragma unroll
+    for (int k = 0; k < VEC; ++k) acc[k] = (A)0;
+    A wgt[kRing][4];                                  // attention * bilinear weights of the samples in flight
+
+    auto issue = [&](int n, int slot) {
+        if (n < count) {
+            const int i = sp + n * split;
+            const int l = i / P;
+            const Pack<T, 2> xy = ldg_pack<T, 2>(locg + 2 * i);
+            const A a = to_acc<T>(__ldg(attg + i));
+            const Footprint<A> f = footprint<A>(to_acc<T>(xy.v[0]), to_acc<T>(xy.v[1]), lv.h[l], lv.w[l]);
+            const T* vl = vb + lv.start[l] * MD;
+            const uint32_t dst = slot0 + slot * (4 * kThreads * 16);
+            cp_async16(dst, vl + (long long)(f.k00 ? f.o00 : 0) * MD, f.k00);
+            cp_async16(dst + kThreads * 16, vl + (long long)(f.k01 ? f.o01 : 0) * MD, f.k01);
+            cp_async16(dst + 2 * kThreads * 16, vl + (long long)(f.k10 ? f.o10 : 0) * MD, f.k10);
+            cp_async16(dst + 3 * kThreads * 16, vl + (long long)(f.k11 ? f.o11 : 0) * MD, f.k11);
+            wgt[slot][0] = a * (f.hh * f.hw); wgt[slot][1] = a * (f.hh * f.lw);
+            wgt[slot][2] = a * (f.lh * f.hw); wgt[slot][3] = a * (f.lh * f.lw);
+        }
+        cp_async_commit();                            // always commit so the group count stays uniform
+    };
+
+#pragma unroll
+    for (int s = 0; s < kRing - 1; ++s) issue(s, s);
+    for (int base = 0; base < count; base += kRing) {
+#pragma unroll
+        for (int s = 0; s < kRing; ++s) {
+            const int n = base + s;
+            issue(n + kRing - 1, (s + kRing - 1) % kRing);
+            cp_async_wait<kRing - 1>();
+            if (n < count) {
+                const uint8_t* src = ring_smem + threadIdx.x * 16 + s * (4 * kThreads * 16);
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    const Pack<T, VEC> v = *reinterpret_cast<const Pack<T, VEC>*>(src + c * kThreads * 16);
+#pragma unroll
+                    for (int k = 0; k < VEC; ++k) acc[k] = fma(wgt[s][c], to_acc<T>(v.v[k]), acc[k]);
+                }
+            }
+        }
+    }
+    for (int o = CH; o < (1 << lanes_log2); o <<= 1) {
+#pragma unroll
+        for (int k = 0; k < VEC; ++k) acc[k] += __shfl_xor_sync(0xffffffffu, acc[k], o);
+    }
+    if (active && sp == 0) {
+        Pack<T, VEC> r;
+#pragma unroll
+        for (int k = 0; k < VEC; ++k) r.v[k] = from_acc<T>(acc[k]);
+        st_pack<T, VEC>(out + group * D + chunk * VEC, r);
+    }
+}
+
 // Any D (not a power of two, or > 32 lanes' worth): one thread per output element.
 template <typename T>
 __global__ void __launch_bounds__(kThreads)
@@ -393,6 +493,21 @@ template <typename T, int D> int launch_fwd(const Args& a) {
     const int sl = pick_split_log2(n_groups, CH, a.L * a.P);
     const long long threads = n_groups * CH << sl;
     const unsigned grid = (unsigned)((threads + kThreads - 1) / kThreads);
+    if constexpr (sizeof(T) == 2 && sizeof(T) * VEC == 16) {
+        constexpr int smem = kRing * 4 * kThreads * 16;
+        static bool configured = false;
+        if (!configured) {
+            auto kern = msda_fwd_ring_kernel<T, D, VEC>;
+            int st = cuda_status(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem), "msda ring attr");
+            if (st) return st;
+            configured = true;
+        }
+        msda_fwd_ring_kernel<T, D, VEC><<<grid, kThreads, smem, a.stream>>>(
+            (const T*)a.value, a.shapes, a.lsi, (const T*)a.loc, (const T*)a.attn, (T*)a.out, a.S, a.M, a.N, a.L,
+            a.P, sl, n_groups);
+        DPFT_LAUNCH_CHECK("msda_fwd_ring_kernel");
+        return DPFT_OK;
+    }
     msda_fwd_kernel<T, D, VEC><<<grid, kThreads, 0, a.stream>>>(
         (const T*)a.value, a.shapes, a.lsi, (const T*)a.loc, (const T*)a.attn, (T*)a.out, a.S, a.M, a.N, a.L,
         a.P, sl, n_groups);
