@@ -30,7 +30,7 @@ namespace {
 constexpr int BLOCK_M = 128;
 constexpr int BLOCK_K = 64;          // bf16 elements = 128 bytes = one swizzle row
 constexpr int UMMA_K = 16;
-constexpr int kNumThreads = 192;
+constexpr int kNumThreads = 320;       // warp 0 TMA, warp 1 MMA, warps 2-9 epilogue (two per TMEM lane quadrant / scheduler)
 constexpr int kEpilogueWarp0 = 2;
 
 enum ConvMode : int { kTiled2D = 0, kIm2col = 1 };
@@ -131,7 +131,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         }
         for (int i = 0; i < 2; ++i) {
             mbar_init(&tmem_full[i], 1);
-            mbar_init(&tmem_empty[i], 4);             // one arrive per epilogue warp
+            mbar_init(&tmem_empty[i], 8);             // one arrive per epilogue warp
         }
         for (int i = 0; i < 4 * EPI_RES_BUFS; ++i) mbar_init(&res_bar[i], 1);
         fence_barrier_init();
@@ -212,11 +212,13 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         }
     } else {
         // ======================================= epilogue =======================================
-        // Each warp owns the TMEM lane quadrant warp%4 = 32 rows of the tile and walks it in [32 x 64] "items".
-        // Output items are staged in shared memory (128-byte swizzle, conflict-free row writes) and written out with
-        // coalesced 16-byte stores (4 full rows per instruction); residual items are prefetched by TMA several items
-        // ahead so the loads overlap the arithmetic.
+        // Eight warps: warps w and w+4 share TMEM lane quadrant w%4 (= 32 rows of the tile) and the same scheduler, and
+        // walk it in [32 rows x 64 cols] "items"; within an item warp group A (warps 2-5) handles columns 0-31 and group
+        // B (warps 6-9) columns 32-63, so two warps per scheduler hide each other's dependent-issue latency.  Output items
+        // are staged in shared memory (128-byte swizzle) and written by TMA; residual items are prefetched by TMA several
+        // items ahead.  The pair synchronises with a 64-thread named barrier around the staging buffer.
         const int quad = warp & 3;
+        const int grp = (warp - 2) >> 2;              // 0 = A (issues the TMA traffic), 1 = B
         uint8_t* my_smem = smem_epi + quad * (EPI_RES_BUFS + EPI_OUT_BUFS) * EPI_BUF_BYTES;
         uint8_t* res_buf = my_smem;
         uint8_t* out_buf = my_smem + EPI_RES_BUFS * EPI_BUF_BYTES;
@@ -225,13 +227,15 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         const bool has_res = prm.residual != nullptr;
         const int my_tiles = blockIdx.x < num_tiles ? (num_tiles - 1 - blockIdx.x) / gridDim.x + 1 : 0;
         const int total_items = my_tiles * kChunks;
+        const bool issuer = grp == 0 && lane == 0;
+        auto pair_sync = [&]() { asm volatile("bar.sync %0, 64;" ::"r"(2 + quad) : "memory"); };
 
         auto prefetch_residual = [&](int item) {
             if (!has_res || item >= total_items) return;
             const int tile = blockIdx.x + (item / kChunks) * gridDim.x;
             const int m_tile = tile / prm.n_tiles, n_tile = tile % prm.n_tiles;
             const int b = item % EPI_RES_BUFS;
-            if (lane == 0) {
+            if (issuer) {
                 mbar_expect_tx(&my_res_bar[b], EPI_BUF_BYTES);
                 tma_load_2d(&tmap_r, &my_res_bar[b], res_buf + b * EPI_BUF_BYTES, n_tile * BLOCK_N + (item % kChunks) * EPI_COLS,
                             m_tile * BLOCK_M + quad * 32);
@@ -250,62 +254,67 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
             mbar_wait(&tmem_full[acc], acc_phase);
             tcgen05_fence_after();
             const int n0 = n_tile * BLOCK_N;
-            // this tile's bias -> shared memory (double-buffered; one named barrier per tile among the 4 epilogue warps)
+            // this tile's bias -> shared memory (double-buffered; one named barrier per tile among the 8 epilogue warps)
             float* bias_s = smem_bias + (tile_count & 1) * BLOCK_N;
-            for (int i = (quad * 32 + lane) * 4; i < BLOCK_N; i += 128 * 4)
+            for (int i = (threadIdx.x - 64) * 4; i < BLOCK_N; i += 256 * 4)
                 *reinterpret_cast<float4*>(bias_s + i) = __ldg(reinterpret_cast<const float4*>(prm.bias + n0 + i));
-            asm volatile("bar.sync 1, 128;" ::: "memory");
+            asm volatile("bar.sync 1, 256;" ::: "memory");
             ++tile_count;
             if (prm.out_f32) {
-                // FPN lateral: inner = conv1x1 + bias (+ top-down), 16 fp32 channels per pixel, written directly
+                // FPN lateral: inner = conv1x1 + bias (+ top-down), 16 fp32 channels per pixel, written directly (group A)
                 const long long m = (long long)m_tile * BLOCK_M + quad * 32 + lane;
-                uint32_t v[32];
-                tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * BLOCK_N), v);
-                tmem_ld_wait();
-                if (m < prm.M) {
-                    const float4* cp = nullptr;
-                    if (prm.coarse) {
-                        const int pq = prm.P * prm.Q;
-                        const int bi = (int)(m / pq);
-                        const int rem = (int)(m - (long long)bi * pq);
-                        const int p = rem / prm.Q, q = rem - p * prm.Q;
-                        const int hc = nearest_src(p, prm.Hc, prm.P), wc = nearest_src(q, prm.Wc, prm.Q);
-                        cp = reinterpret_cast<const float4*>(prm.coarse + (((long long)bi * prm.Hc + hc) * prm.Wc + wc) * 16);
-                    }
-                    float4* o = reinterpret_cast<float4*>(prm.out_f32 + m * 16);
-#pragma unroll
-                    for (int j4 = 0; j4 < 4; ++j4) {
-                        const float4 bv = *reinterpret_cast<const float4*>(bias_s + 4 * j4);
-                        float4 r = make_float4(__uint_as_float(v[4 * j4]) + bv.x, __uint_as_float(v[4 * j4 + 1]) + bv.y,
-                                               __uint_as_float(v[4 * j4 + 2]) + bv.z, __uint_as_float(v[4 * j4 + 3]) + bv.w);
-                        if (cp) {
-                            const float4 c = __ldg(cp + j4);
-                            r.x += c.x; r.y += c.y; r.z += c.z; r.w += c.w;
+                if (grp == 0) {
+                    uint32_t v[16];
+                    tmem_ld_32x32b_x16(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * BLOCK_N), v);
+                    tmem_ld_wait();
+                    if (m < prm.M) {
+                        const float4* cp = nullptr;
+                        if (prm.coarse) {
+                            const int pq = prm.P * prm.Q;
+                            const int bi = (int)(m / pq);
+                            const int rem = (int)(m - (long long)bi * pq);
+                            const int p = rem / prm.Q, q = rem - p * prm.Q;
+                            const int hc = nearest_src(p, prm.Hc, prm.P), wc = nearest_src(q, prm.Wc, prm.Q);
+                            cp = reinterpret_cast<const float4*>(prm.coarse + (((long long)bi * prm.Hc + hc) * prm.Wc + wc) * 16);
                         }
-                        o[j4] = r;
+                        float4* o = reinterpret_cast<float4*>(prm.out_f32 + m * 16);
+#pragma unroll
+                        for (int j4 = 0; j4 < 4; ++j4) {
+                            const float4 bv = *reinterpret_cast<const float4*>(bias_s + 4 * j4);
+                            float4 r = make_float4(__uint_as_float(v[4 * j4]) + bv.x, __uint_as_float(v[4 * j4 + 1]) + bv.y,
+                                                   __uint_as_float(v[4 * j4 + 2]) + bv.z, __uint_as_float(v[4 * j4 + 3]) + bv.w);
+                            if (cp) {
+                                const float4 c = __ldg(cp + j4);
+                                r.x += c.x; r.y += c.y; r.z += c.z; r.w += c.w;
+                            }
+                            o[j4] = r;
+                        }
                     }
                 }
             } else {
 #pragma unroll 1
                 for (int c = 0; c < kChunks; ++c, ++item) {
-                    uint32_t v[EPI_COLS];
-                    const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * BLOCK_N + c * EPI_COLS);
+                    uint32_t v[32];
+                    const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) +
+                                           (uint32_t)(acc * BLOCK_N + c * EPI_COLS + grp * 32);
                     tmem_ld_32x32b_x32(taddr, v);
-                    tmem_ld_32x32b_x32(taddr + 32, v + 32);
                     tmem_ld_wait();
-                    const float4* bias4 = reinterpret_cast<const float4*>(bias_s + c * EPI_COLS);
+                    const float4* bias4 = reinterpret_cast<const float4*>(bias_s + c * EPI_COLS + grp * 32);
                     const uint8_t* rrow = res_buf + (item % EPI_RES_BUFS) * EPI_BUF_BYTES + lane * 128;
                     if (has_res) mbar_wait(&my_res_bar[item % EPI_RES_BUFS], (uint32_t)((item / EPI_RES_BUFS) & 1));
-                    __syncwarp();                     // the staging buffer was read back two items ago
+                    // the staging buffer of item-2 must have been read by its TMA store before it is overwritten
+                    if (issuer) bulk_wait_read<EPI_OUT_BUFS - 1>();
+                    pair_sync();
                     uint8_t* orow = out_buf + (item % EPI_OUT_BUFS) * EPI_BUF_BYTES + lane * 128;
 #pragma unroll
-                    for (int j = 0; j < EPI_COLS / 8; ++j) {       // 8 columns = one 16-byte chunk of the row
+                    for (int jj = 0; jj < 4; ++jj) {               // 8 columns = one 16-byte chunk of the row
+                        const int j = grp * 4 + jj;                 // chunk index within the 128-byte row
                         float f[8];
-                        const float4 b0 = bias4[2 * j], b1 = bias4[2 * j + 1];
-                        f[0] = __uint_as_float(v[8 * j]) + b0.x;     f[1] = __uint_as_float(v[8 * j + 1]) + b0.y;
-                        f[2] = __uint_as_float(v[8 * j + 2]) + b0.z; f[3] = __uint_as_float(v[8 * j + 3]) + b0.w;
-                        f[4] = __uint_as_float(v[8 * j + 4]) + b1.x; f[5] = __uint_as_float(v[8 * j + 5]) + b1.y;
-                        f[6] = __uint_as_float(v[8 * j + 6]) + b1.z; f[7] = __uint_as_float(v[8 * j + 7]) + b1.w;
+                        const float4 b0 = bias4[2 * jj], b1 = bias4[2 * jj + 1];
+                        f[0] = __uint_as_float(v[8 * jj]) + b0.x;     f[1] = __uint_as_float(v[8 * jj + 1]) + b0.y;
+                        f[2] = __uint_as_float(v[8 * jj + 2]) + b0.z; f[3] = __uint_as_float(v[8 * jj + 3]) + b0.w;
+                        f[4] = __uint_as_float(v[8 * jj + 4]) + b1.x; f[5] = __uint_as_float(v[8 * jj + 5]) + b1.y;
+                        f[6] = __uint_as_float(v[8 * jj + 6]) + b1.z; f[7] = __uint_as_float(v[8 * jj + 7]) + b1.w;
                         const int phys = (j ^ sw) << 4;             // 128-byte swizzle: chunk index xor (row % 8)
                         if (has_res) {
                             const uint4 rv = *reinterpret_cast<const uint4*>(rrow + phys);
@@ -335,19 +344,12 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                         }
                         *reinterpret_cast<uint4*>(orow + phys) = ov;
                     }
-                    __syncwarp();                     // all 32 rows staged (and this item's residual rows consumed)
-                    // write-out: each instruction stores 4 complete rows x 128 B (8 lanes per row) — fully coalesced
-                    {
-                        const uint8_t* obuf = out_buf + (item % EPI_OUT_BUFS) * EPI_BUF_BYTES;
-                        const long long m_base = (long long)m_tile * BLOCK_M + quad * 32;
-                        const int chunk = lane & 7;
-                        uint8_t* gout = reinterpret_cast<uint8_t*>(prm.out) + ((long long)(n0 + c * EPI_COLS) + chunk * 8) * 2;
-#pragma unroll
-                        for (int it = 0; it < 8; ++it) {
-                            const int r = it * 4 + (lane >> 3);
-                            const uint4 ov = *reinterpret_cast<const uint4*>(obuf + r * 128 + ((chunk ^ (r & 7)) << 4));
-                            if (m_base + r < prm.M) *reinterpret_cast<uint4*>(gout + (m_base + r) * prm.N * 2) = ov;
-                        }
+                    fence_proxy_async();              // make the generic-proxy smem writes visible to the TMA engine
+                    pair_sync();                      // both halves staged, this item's residual rows consumed
+                    if (issuer) {
+                        tma_store_2d(&tmap_d, out_buf + (item % EPI_OUT_BUFS) * EPI_BUF_BYTES, n0 + c * EPI_COLS,
+                                     m_tile * BLOCK_M + quad * 32);
+                        bulk_commit();
                     }
                     prefetch_residual(item + EPI_RES_BUFS - 1);   // refills the buffer consumed by item-1
                 }
@@ -357,6 +359,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
             if (lane == 0) mbar_arrive(&tmem_empty[acc]);
             if (++acc == 2) { acc = 0; acc_phase ^= 1; }
         }
+        if (issuer) bulk_wait_read<0>();              // smem must stay valid until the last stores have read it
     }
 
     tcgen05_fence_before();
