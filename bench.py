@@ -160,6 +160,49 @@ def run_reference(args):
     print(json.dumps(line), flush=True)
 
 
+def conv_roofline(model, resident, dev, tf_peak, peak_src):
+    """The dominant kernel of the step: the tcgen05 implicit-GEMM convolution (every backbone conv launch of one forward).
+    achieved = sum of algorithmic FLOPs / sum of CUDA-event durations of those launches (eager, serial streams)."""
+    from dpft_b200 import conv
+    saved = (model.use_cuda_graph, model.parallel_views)
+    model.use_cuda_graph, model.parallel_views = False, False
+    try:
+        with torch.no_grad():
+            model(resident)
+            conv.PROFILE = []
+            model(resident)
+            torch.cuda.synchronize()
+            prof, conv.PROFILE = conv.PROFILE, None
+    finally:
+        conv.PROFILE = None
+        model.use_cuda_graph, model.parallel_views = saved
+    flops = sum(p[0] for p in prof)
+    nbytes = sum(p[1] for p in prof)
+    secs = sum(p[2].elapsed_time(p[3]) for p in prof) * 1e-3
+    achieved = flops / secs / 1e12
+    return {"kernel": "conv_gemm_kernel (all %d backbone conv launches of one step)" % len(prof), "bound": "tensor",
+            "achieved": achieved, "peak": tf_peak, "unit": "TFLOP/s", "frac": achieved / tf_peak, "traffic": None,
+            "peak_source": peak_src + ", bf16_tflops_sustained (kernel timed inside a long step)",
+            "algorithmic_flops_per_step": flops, "algorithmic_bytes_per_step": nbytes, "ms_in_kernel_per_step": secs * 1e3,
+            "gbps": nbytes / secs / 1e9, "launches": len(prof)}
+
+
+def msda_stress(dev, hbm_peak):
+    """BASELINE config 5 (bs 16, 900 queries, 4 levels, D = 32): the bandwidth-bound regime of the deformable-attention op."""
+    import subprocess
+    out = {}
+    for case in ("cfg5_bf16_D32", "cfg5_fp32_D32"):
+        r = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "msda_sweep.py"), "--only", case, "--reps", "10"],
+                           capture_output=True, text=True, timeout=300)
+        try:
+            j = json.loads(r.stdout.strip().splitlines()[-1])
+            out[case] = {"fwd_frac": j["fwd_frac"], "fwd_GBps": j["fwd_GBps"], "bwd_frac": j["bwd_frac"],
+                         "bwd_GBps": j["bwd_GBps"], "fwd_alg_MB": j["fwd_alg_MB"], "peak_GBps": hbm_peak}
+        except Exception as e:  # noqa: BLE001
+            out[case] = {"error": str(e), "stderr": r.stderr[-300:]}
+    return out
+
+
 def msda_roofline(model, feats_flat, dev, hbm_peak, peak_src, reps=20):
     """Times the deformable-attention forward kernel on tensors of the step's own shape (camera view: the largest
     pyramid), L2 flushed between launches; algorithmic bytes per SURVEY.md §8d."""
@@ -346,14 +389,17 @@ def main():
     frames = B * world * args.steps
     line = None
     if rank == 0:
-        hbm_peak, _, peak_src = peaks()
-        # the deformable-attention kernel on the camera pyramid of this very workload
+        hbm_peak, tf_peak, peak_src = peaks()
+        roof = conv_roofline(model, resident, dev, tf_peak, peak_src) if args.dtype != "f32" else None
+        # the deformable-attention op on the camera pyramid of this very workload (shipped D = 2: latency-bound)
         with torch.no_grad():
-            feats = model.extract_features(resident)
-            from dpft_b200.models.fuser import FeaturePyramid
-            pyr = FeaturePyramid.from_levels(feats[model.inputs[0]])
-            roof = msda_roofline(model, (pyr.flat, pyr.shapes_t, pyr.lsi_t), dev, hbm_peak, peak_src)
-            del feats, pyr
+            pyr = model._engine.pyramids(resident)[0]
+            roof_msda = msda_roofline(model, (pyr.flat, pyr.shapes_t, pyr.lsi_t), dev, hbm_peak, peak_src)
+            del pyr
+        if roof is None:
+            roof = roof_msda
+        torch.cuda.empty_cache()
+        roof_msda["stress_config5"] = msda_stress(dev, hbm_peak) if world == 1 and not args.small else None
         line = {"metric": METRIC, "value": frames / t_res, "unit": UNIT, "n_gpus": world, "steps": args.steps,
                 "warmup": max(args.warmup, 3), "ms_per_step": 1e3 * t_res / args.steps, "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": args.dtype, "data": "synthetic",
@@ -361,7 +407,7 @@ def main():
                            "arithmetic": "backbone convs: %s operands, f32 accumulate (tcgen05); FPN/decoder f32" % args.dtype, "l2": "flushed between timed steps (256 MiB write)",
                            "sizes": {k: list(v) for k, v in sizes.items()}, "parallelism": f"replicas x{world}",
                            "valid": not args.small},
-                "roofline": roof, "clocks": clocks,
+                "roofline": roof, "roofline_msda": roof_msda, "clocks": clocks,
                 "e2e": {"value": frames / t_e2e, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes,
                         "d2h_bytes_per_step": d2h_bytes, "ms_per_step": 1e3 * t_e2e / args.steps},
                 "gpu_launches": launches}

@@ -13,6 +13,9 @@ from torch import nn
 
 from . import native
 
+# bench.py sets this to a list to collect (flops, bytes, start_event, end_event) of every conv launch of one step
+PROFILE = None
+
 
 def fold_conv_bn(conv: nn.Conv2d, bn: Optional[nn.Module]) -> Tuple[torch.Tensor, torch.Tensor]:
     """Returns (weight (Cout, R, S, Cin) fp32, bias (Cout,) fp32) of conv followed by eval-mode BatchNorm."""
@@ -47,7 +50,7 @@ class FoldedConv:
 
 def conv2d_nhwc(x: torch.Tensor, weight: torch.Tensor, bias: torch.Tensor, stride: int, pad: int, relu: bool,
                      residual: Optional[torch.Tensor] = None, out: Optional[torch.Tensor] = None,
-                     block_n: int = 0) -> torch.Tensor:
+                     block_n: int = 0, cluster_mode: int = 0) -> torch.Tensor:
     """x (B,H,W,Cin) bf16|f16 contiguous, weight (Cout,R,S,Cin) same dtype, bias (Cout,) fp32 -> (B,P,Q,Cout)."""
     native.require_cuda(x, weight, bias)
     if x.dtype not in (torch.bfloat16, torch.float16) or weight.dtype != x.dtype or bias.dtype != torch.float32:
@@ -65,10 +68,19 @@ def conv2d_nhwc(x: torch.Tensor, weight: torch.Tensor, bias: torch.Tensor, strid
                                  or residual.dtype != x.dtype):
         raise RuntimeError("conv2d_nhwc: residual must be a contiguous tensor of the output shape and dtype")
     lib = native.load_library()
+    prof = PROFILE
+    if prof is not None:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
     with torch.cuda.device(x.device):
         st = lib.dpft_conv2d_nhwc(native.ptr(x), native.ptr(weight), native.ptr(bias), native.ptr(residual),
-                                  native.ptr(out), B, H, W, Cin, Cout, R, S, stride, pad, int(relu), block_n,
+                                  native.ptr(out), B, H, W, Cin, Cout, R, S, stride, pad, int(relu), block_n, cluster_mode,
                                   native.dtype_code(x), native.stream_ptr(x.device))
     native.check(st, "dpft_conv2d_nhwc")
     native.count_launch()
+    if prof is not None:
+        e1.record()
+        M = B * P * Q
+        prof.append((2.0 * M * Cout * R * S * Cin,
+                     2.0 * (x.numel() + weight.numel() + M * Cout * (2 if residual is not None else 1)), e0, e1))
     return out

@@ -76,9 +76,9 @@ constexpr int EPI_OUT_BUFS = 2;
 // EPI_RES_BUFS = residual sub-tiles per warp (EPI_RES_BUFS - 1 prefetched + one in use).  Layers with a short K loop
 // and a residual (the 1x1 "expand" convs) are bound by the residual/output streams, not by the operand pipeline, so
 // they trade operand stages for a deeper residual prefetch.
-template <int BLOCK_N, int STAGES, int EPI_RES_BUFS> struct SmemLayout {
+template <int BLOCK_N, int STAGES, int EPI_RES_BUFS, int CG = 1> struct SmemLayout {
     static constexpr int kABytes = BLOCK_M * BLOCK_K * 2;
-    static constexpr int kBBytes = BLOCK_N * BLOCK_K * 2;
+    static constexpr int kBBytes = (BLOCK_N / CG) * BLOCK_K * 2;          // a CTA pair holds half of the B tile each
     static constexpr int kStageBytes = kABytes + kBBytes;
     static constexpr int kEpiBytes = 4 * (EPI_RES_BUFS + EPI_OUT_BUFS) * EPI_BUF_BYTES;
     static constexpr int kBiasBytes = 2 * BLOCK_N * 4;                                      // double-buffered tile bias
@@ -96,13 +96,73 @@ template <int N> __device__ __forceinline__ void bulk_wait_read() {
     asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
 }
 
+
+// ---- 2-CTA (cta_group::2) helpers: the CTA pair of a cluster cooperates on a 256-row tile; CTA 0 issues the MMAs ----
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// shared::cluster address of the same shared-memory variable in CTA `rank` of the cluster
+__device__ __forceinline__ uint32_t map_to_cta(const void* p, uint32_t rank) {
+    uint32_t a;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(a) : "r"(smem_u32(p)), "r"(rank));
+    return a;
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+// TMA loads of a CTA pair: the data lands in the issuing CTA's shared memory, the bytes are counted on `bar_cluster_addr`
+// (the leader CTA's barrier).
+__device__ __forceinline__ void tma_load_2d_2sm(const CUtensorMap* map, uint32_t bar_cluster_addr, void* dst, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::
+            "r"(smem_u32(dst)), "l"(map), "r"(bar_cluster_addr), "r"(c0), "r"(c1)
+        : "memory");
+}
+__device__ __forceinline__ void tma_load_im2col_4d_2sm(const CUtensorMap* map, uint32_t bar_cluster_addr, void* dst, int c, int w,
+                                                       int h, int n, uint16_t off_w, uint16_t off_h) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.im2col.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], "
+        "[%2], {%7, %8};" ::"r"(smem_u32(dst)),
+        "l"(map), "r"(bar_cluster_addr), "r"(c), "r"(w), "r"(h), "r"(n), "h"(off_w), "h"(off_h)
+        : "memory");
+}
+__device__ __forceinline__ void umma_2sm(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n"
+        "}\n" ::"r"(tmem_d),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// commit of a CTA-pair MMA: arrives on the barrier at the same offset in both CTAs
+__device__ __forceinline__ void umma_commit_2sm(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(smem_u32(bar)),
+                 "h"((uint16_t)3)
+                 : "memory");
+}
+__device__ __forceinline__ void tmem_alloc_2sm(uint32_t* slot_in_smem, uint32_t cols) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(slot_in_smem)), "r"(cols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc_2sm(uint32_t base, uint32_t cols) {
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(base), "r"(cols) : "memory");
+}
+
 // ---- the kernel -------------------------------------------------------------------------------------------------
-template <int BLOCK_N, int STAGES, int EPI_RES_BUFS>
+template <int BLOCK_N, int STAGES, int EPI_RES_BUFS, int CG>
 __global__ void __launch_bounds__(kNumThreads, 1)
 conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                  const __grid_constant__ CUtensorMap tmap_d, const __grid_constant__ CUtensorMap tmap_r,
                  const ConvParams prm) {
-    using L = SmemLayout<BLOCK_N, STAGES, EPI_RES_BUFS>;
+    using L = SmemLayout<BLOCK_N, STAGES, EPI_RES_BUFS, CG>;
     extern __shared__ __align__(1024) uint8_t smem[];                    // 128-byte swizzle needs 1024-byte alignment
     if ((smem_u32(smem) & 1023u) != 0) __trap();
     uint8_t* smem_a = smem;
@@ -119,6 +179,8 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
     constexpr uint32_t kTmemCols = 2 * BLOCK_N;       // 128, 256 or 512: a power of two >= 32
+    const uint32_t rank = CG == 2 ? cluster_ctarank() : 0;       // position in the CTA pair
+    const int cta_id = blockIdx.x / CG, num_ctas = gridDim.x / CG;   // the pair walks the tile list together
 
     if (warp == 0 && elect_one()) {
         prefetch_tmap(&tmap_a);
@@ -131,27 +193,32 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         }
         for (int i = 0; i < 2; ++i) {
             mbar_init(&tmem_full[i], 1);
-            mbar_init(&tmem_empty[i], 8);             // one arrive per epilogue warp
+            mbar_init(&tmem_empty[i], 8 * CG);        // one arrive per epilogue warp (of both CTAs of a pair)
         }
         for (int i = 0; i < 4 * EPI_RES_BUFS; ++i) mbar_init(&res_bar[i], 1);
         fence_barrier_init();
     } else if (warp == 1) {
-        tmem_alloc(tmem_slot, kTmemCols);
+        if (CG == 2) tmem_alloc_2sm(tmem_slot, kTmemCols);
+        else tmem_alloc(tmem_slot, kTmemCols);
     }
     tcgen05_fence_before();
-    __syncthreads();
+    if (CG == 2) cluster_sync_all();                  // the peer's barriers must be initialised before anything signals them
+    else __syncthreads();
     tcgen05_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
-    const int num_tiles = prm.m_tiles * prm.n_tiles;
+    // CG == 2: a tile is 256 rows (this CTA owns rows rank*128 .. +128 of it) and the pair shares the B tile
+    const int big_m_tiles = (prm.m_tiles + CG - 1) / CG;
+    const int num_tiles = big_m_tiles * prm.n_tiles;
 
     if (warp == 0) {
         // ===================================== TMA producer =====================================
         if (elect_one()) {
             int stage = 0;
             uint32_t phase = 0;
-            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-                const int m_tile = tile / prm.n_tiles, n_tile = tile % prm.n_tiles;
+            const uint32_t full_leader = CG == 2 ? map_to_cta(full_bar, 0) : 0;     // the pair's loads count on CTA 0's barrier
+            for (int tile = cta_id; tile < num_tiles; tile += num_ctas) {
+                const int m_tile = (tile / prm.n_tiles) * CG + (int)rank, n_tile = tile % prm.n_tiles;
                 int cw = 0, ch = 0, cn = 0;           // first pixel of the tile in im2col tensor-map coordinates
                 if (prm.mode == kIm2col) {
                     const int m0 = m_tile * BLOCK_M;
@@ -164,30 +231,41 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                 }
                 for (int kb = 0; kb < prm.kblocks; ++kb) {
                     mbar_wait(&empty_bar[stage], phase ^ 1);
-                    mbar_expect_tx(&full_bar[stage], L::kStageBytes);
+                    if (rank == 0) mbar_expect_tx(&full_bar[stage], CG * L::kStageBytes);
                     void* a_dst = smem_a + stage * L::kABytes;
                     void* b_dst = smem_b + stage * L::kBBytes;
                     const int tap = kb / prm.cblocks;
                     const int c0 = (kb - tap * prm.cblocks) * BLOCK_K;
-                    if (prm.mode == kTiled2D) {
-                        tma_load_2d(&tmap_a, &full_bar[stage], a_dst, c0, m_tile * BLOCK_M);
+                    if (CG == 2) {
+                        const uint32_t bar = full_leader + stage * 8;
+                        if (prm.mode == kTiled2D) {
+                            tma_load_2d_2sm(&tmap_a, bar, a_dst, c0, m_tile * BLOCK_M);
+                        } else {
+                            const int r = tap / prm.taps_s, s = tap - r * prm.taps_s;
+                            tma_load_im2col_4d_2sm(&tmap_a, bar, a_dst, c0, cw, ch, cn, (uint16_t)s, (uint16_t)r);
+                        }
+                        tma_load_2d_2sm(&tmap_b, bar, b_dst, kb * BLOCK_K, n_tile * BLOCK_N + (int)rank * (BLOCK_N / 2));
                     } else {
-                        const int r = tap / prm.taps_s, s = tap - r * prm.taps_s;
-                        tma_load_im2col_4d(&tmap_a, &full_bar[stage], a_dst, c0, cw, ch, cn, (uint16_t)s, (uint16_t)r);
+                        if (prm.mode == kTiled2D) {
+                            tma_load_2d(&tmap_a, &full_bar[stage], a_dst, c0, m_tile * BLOCK_M);
+                        } else {
+                            const int r = tap / prm.taps_s, s = tap - r * prm.taps_s;
+                            tma_load_im2col_4d(&tmap_a, &full_bar[stage], a_dst, c0, cw, ch, cn, (uint16_t)s, (uint16_t)r);
+                        }
+                        tma_load_2d(&tmap_b, &full_bar[stage], b_dst, kb * BLOCK_K, n_tile * BLOCK_N);
                     }
-                    tma_load_2d(&tmap_b, &full_bar[stage], b_dst, kb * BLOCK_K, n_tile * BLOCK_N);
                     if (++stage == STAGES) { stage = 0; phase ^= 1; }
                 }
             }
         }
-    } else if (warp == 1) {
-        // ====================================== MMA issuer ======================================
-        const uint32_t idesc = umma_idesc_16bit(BLOCK_N, prm.is_f16 != 0);
+    } else if (warp == 1 && rank == 0) {
+        // ====================================== MMA issuer (leader CTA of a pair) ======================================
+        const uint32_t idesc = tc::umma_idesc_16bit(BLOCK_M * CG, BLOCK_N, prm.is_f16 != 0);
         int stage = 0;
         uint32_t phase = 0;
         int acc = 0;
         uint32_t acc_phase = 0;
-        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        for (int tile = cta_id; tile < num_tiles; tile += num_ctas) {
             mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
             tcgen05_fence_after();
             const uint32_t tmem_d = tmem_base + acc * BLOCK_N;
@@ -200,17 +278,23 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
 #pragma unroll
                     for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
                         // +32 bytes per K=16 step inside the 128-byte swizzle row: start-address field += 2
-                        umma_bf16(tmem_d, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) ? 1u : 0u);
+                        if (CG == 2) umma_2sm(tmem_d, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) ? 1u : 0u);
+                        else umma_bf16(tmem_d, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) ? 1u : 0u);
                     }
-                    umma_commit(&empty_bar[stage]);                  // frees the smem stage when the MMAs retire
-                    if (kb == prm.kblocks - 1) umma_commit(&tmem_full[acc]);
+                    if (CG == 2) {
+                        umma_commit_2sm(&empty_bar[stage]);          // frees the stage in both CTAs
+                        if (kb == prm.kblocks - 1) umma_commit_2sm(&tmem_full[acc]);
+                    } else {
+                        umma_commit(&empty_bar[stage]);              // frees the smem stage when the MMAs retire
+                        if (kb == prm.kblocks - 1) umma_commit(&tmem_full[acc]);
+                    }
                 }
                 __syncwarp();
                 if (++stage == STAGES) { stage = 0; phase ^= 1; }
             }
             if (++acc == 2) { acc = 0; acc_phase ^= 1; }
         }
-    } else {
+    } else if (warp >= 2) {
         // ======================================= epilogue =======================================
         // Eight warps: warps w and w+4 share TMEM lane quadrant w%4 (= 32 rows of the tile) and the same scheduler, and
         // walk it in [32 rows x 64 cols] "items"; within an item warp group A (warps 2-5) handles columns 0-31 and group
@@ -225,15 +309,16 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         uint64_t* my_res_bar = res_bar + quad * EPI_RES_BUFS;
         constexpr int kChunks = BLOCK_N / EPI_COLS;
         const bool has_res = prm.residual != nullptr;
-        const int my_tiles = blockIdx.x < num_tiles ? (num_tiles - 1 - blockIdx.x) / gridDim.x + 1 : 0;
+        const int my_tiles = cta_id < num_tiles ? (num_tiles - 1 - cta_id) / num_ctas + 1 : 0;
+        const uint32_t empty_leader = CG == 2 ? map_to_cta(tmem_empty, 0) : 0;
         const int total_items = my_tiles * kChunks;
         const bool issuer = grp == 0 && lane == 0;
         auto pair_sync = [&]() { asm volatile("bar.sync %0, 64;" ::"r"(2 + quad) : "memory"); };
 
         auto prefetch_residual = [&](int item) {
             if (!has_res || item >= total_items) return;
-            const int tile = blockIdx.x + (item / kChunks) * gridDim.x;
-            const int m_tile = tile / prm.n_tiles, n_tile = tile % prm.n_tiles;
+            const int tile = cta_id + (item / kChunks) * num_ctas;
+            const int m_tile = (tile / prm.n_tiles) * CG + (int)rank, n_tile = tile % prm.n_tiles;
             const int b = item % EPI_RES_BUFS;
             if (issuer) {
                 mbar_expect_tx(&my_res_bar[b], EPI_BUF_BYTES);
@@ -249,8 +334,8 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
 #pragma unroll
         for (int i = 0; i < EPI_RES_BUFS - 1; ++i) prefetch_residual(i);
         const int sw = lane & 7;                      // swizzle phase of this thread's row
-        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-            const int m_tile = tile / prm.n_tiles, n_tile = tile % prm.n_tiles;
+        for (int tile = cta_id; tile < num_tiles; tile += num_ctas) {
+            const int m_tile = (tile / prm.n_tiles) * CG + (int)rank, n_tile = tile % prm.n_tiles;
             mbar_wait(&tmem_full[acc], acc_phase);
             tcgen05_fence_after();
             const int n0 = n_tile * BLOCK_N;
@@ -356,17 +441,22 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
             }
             tcgen05_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+            if (lane == 0) {
+                if (CG == 2) mbar_arrive_cluster(empty_leader + acc * 8);   // the leader's MMA warp waits for both CTAs
+                else mbar_arrive(&tmem_empty[acc]);
+            }
             if (++acc == 2) { acc = 0; acc_phase ^= 1; }
         }
         if (issuer) bulk_wait_read<0>();              // smem must stay valid until the last stores have read it
     }
 
     tcgen05_fence_before();
-    __syncthreads();
+    if (CG == 2) cluster_sync_all();                  // neither CTA may leave while the other can still signal it
+    else __syncthreads();
     if (warp == 1) {
         tcgen05_fence_after();
-        tmem_dealloc(tmem_base, kTmemCols);
+        if (CG == 2) tmem_dealloc_2sm(tmem_base, kTmemCols);
+        else tmem_dealloc(tmem_base, kTmemCols);
     }
 }
 
@@ -416,22 +506,40 @@ int encode_2d(CUtensorMap* map, const void* base, uint64_t inner, uint64_t outer
     return 0;
 }
 
-template <int BLOCK_N, int STAGES, int RES_BUFS>
+template <int BLOCK_N, int STAGES, int RES_BUFS, int CG = 1>
 int launch(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& td, const CUtensorMap& tr, const ConvParams& prm,
            cudaStream_t stream) {
-    using L = SmemLayout<BLOCK_N, STAGES, RES_BUFS>;
+    using L = SmemLayout<BLOCK_N, STAGES, RES_BUFS, CG>;
     static_assert(L::kTotal <= 232448, "shared memory budget of one CTA exceeded");
+    auto kern = conv_gemm_kernel<BLOCK_N, STAGES, RES_BUFS, CG>;
     static bool configured = false;
     if (!configured) {
-        auto kern = conv_gemm_kernel<BLOCK_N, STAGES, RES_BUFS>;
         int st = cuda_status(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                                   L::kTotal), "cudaFuncSetAttribute(conv_gemm_kernel)");
         if (st) return st;
         configured = true;
     }
-    const int tiles = prm.m_tiles * prm.n_tiles;
-    const int grid = tiles < g_sm_count ? tiles : g_sm_count;
-    conv_gemm_kernel<BLOCK_N, STAGES, RES_BUFS><<<grid, kNumThreads, L::kTotal, stream>>>(ta, tb, td, tr, prm);
+    const int tiles = ((prm.m_tiles + CG - 1) / CG) * prm.n_tiles;
+    const int max_ctas = g_sm_count / CG;
+    const int grid = CG * (tiles < max_ctas ? tiles : max_ctas);
+    if (CG == 1) {
+        kern<<<grid, kNumThreads, L::kTotal, stream>>>(ta, tb, td, tr, prm);
+    } else {
+        cudaLaunchConfig_t cfg{};
+        cfg.gridDim = dim3(grid);
+        cfg.blockDim = dim3(kNumThreads);
+        cfg.dynamicSmemBytes = L::kTotal;
+        cfg.stream = stream;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = CG;
+        attr[0].val.clusterDim.y = 1;
+        attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+        int st = cuda_status(cudaLaunchKernelEx(&cfg, kern, ta, tb, td, tr, prm), "cudaLaunchKernelEx(conv_gemm_kernel, cluster 2)");
+        if (st) return st;
+    }
     DPFT_LAUNCH_CHECK("conv_gemm_kernel");
     return DPFT_OK;
 }
@@ -472,12 +580,12 @@ extern "C" int dpft_fpn_lateral_forward(const void* x, const void* w, const floa
     if (st) return st;
     st = encode_2d(&tb, w, (uint64_t)Cin, 64, (uint64_t)Cin * 2, BLOCK_K, 64, is_f16);
     if (st) return st;
-    return launch<64, 6, 3>(ta, tb, ta, ta, prm, (cudaStream_t)stream);   // d / r maps unused in the fp32 lateral form
+    return launch<64, 6, 3, 1>(ta, tb, ta, ta, prm, (cudaStream_t)stream);   // d / r maps unused in the fp32 lateral form
 }
 
 extern "C" int dpft_conv2d_nhwc(const void* x, const void* w, const float* bias, const void* residual, void* y,
                                 int B, int H, int W, int Cin, int Cout, int R, int S, int stride, int pad, int relu,
-                                int block_n, int dtype, void* stream) {
+                                int block_n, int cluster_mode, int dtype, void* stream) {
     DPFT_REQUIRE(x && w && bias && y, "conv2d: null pointer");
     DPFT_REQUIRE(dtype == DPFT_BF16 || dtype == DPFT_F16, "conv2d: dtype must be DPFT_BF16 or DPFT_F16");
     const bool is_f16 = dtype == DPFT_F16;
@@ -519,7 +627,11 @@ extern "C" int dpft_conv2d_nhwc(const void* x, const void* w, const float* bias,
         if (g_driver_version <= 13010 && (uint64_t)B * H * W * Cin * 2 < 131072)
             reinterpret_cast<uint64_t*>(&ta)[1] &= ~(1ull << 21);
     }
-    st = encode_2d(&tb, w, (uint64_t)R * S * Cin, (uint64_t)Cout, (uint64_t)R * S * Cin * 2, BLOCK_K, bn, is_f16);
+    // CTA pairs (cta_group::2) for the operand-bound layers: long K loop and enough 256-row tiles; each CTA then loads only
+    // half of the B tile.  cluster_mode: 0 = choose, 1 = single CTA, 2 = force pairs (tests).
+    const bool pairs = bn >= 128 && (cluster_mode == 2 || (cluster_mode == 0 && prm.kblocks >= 8 &&
+                       (long long)((prm.m_tiles + 1) / 2) * prm.n_tiles >= g_sm_count / 4));
+    st = encode_2d(&tb, w, (uint64_t)R * S * Cin, (uint64_t)Cout, (uint64_t)R * S * Cin * 2, BLOCK_K, pairs ? bn / 2 : bn, is_f16);
     if (st) return st;
     // output / residual as [M, Cout] matrices, written / read in [32 rows x 64 cols] boxes (128-byte swizzle)
     CUtensorMap td, tr;
@@ -528,6 +640,11 @@ extern "C" int dpft_conv2d_nhwc(const void* x, const void* w, const float* bias,
     st = encode_2d(&tr, residual ? residual : y, (uint64_t)Cout, (uint64_t)prm.M, (uint64_t)Cout * 2, EPI_COLS, 32, is_f16);
     if (st) return st;
     cudaStream_t s = (cudaStream_t)stream;
+    if (pairs) {
+        cudaStream_t s2 = (cudaStream_t)stream;
+        if (bn == 256) return launch<256, 4, 3, 2>(ta, tb, td, tr, prm, s2);
+        return launch<128, 6, 3, 2>(ta, tb, td, tr, prm, s2);
+    }
     const bool stream_bound = residual != nullptr && prm.kblocks <= 4;   // 1x1 expand convs: deep residual prefetch
     if (bn == 256) return stream_bound ? launch<256, 2, 5>(ta, tb, td, tr, prm, s) : launch<256, 3, 3>(ta, tb, td, tr, prm, s);
     if (bn == 128) return stream_bound ? launch<128, 2, 7>(ta, tb, td, tr, prm, s) : launch<128, 4, 3>(ta, tb, td, tr, prm, s);

@@ -90,10 +90,11 @@ DPFT_API int dpft_msda_backward(const void* value, const int64_t* shapes, const 
  *   residual (B, P, Q, Cout)      bf16 or NULL
  *   y        (B, P, Q, Cout)      bf16, P = (H+2*pad-R)/stride+1, Q likewise
  * block_n: 0 = choose, or 64 / 128 / 256 (output-channel tile; tests sweep it).
+ * cluster_mode: 0 = choose, 1 = one CTA per tile, 2 = CTA pairs (tcgen05 cta_group::2, 256-row tiles, B tile split across the pair).
  */
 DPFT_API int dpft_conv2d_nhwc(const void* x, const void* w, const float* bias, const void* residual, void* y,
                               int B, int H, int W, int Cin, int Cout, int R, int S, int stride, int pad, int relu,
-                              int block_n, int dtype, void* stream);
+                              int block_n, int cluster_mode, int dtype, void* stream);
 
 /*
  * ResNet stem: [1x1 adjustment conv (radar, 6 -> 3, resnet.py:47-51) folded into] conv1 7x7 stride 2 pad 3 + BatchNorm

@@ -48,13 +48,14 @@ def test_conv_matches_torch_fp32(shape, block_n, relu, with_res):
     torch.backends.cudnn.allow_tf32 = False
     torch.backends.cuda.matmul.allow_tf32 = False
     want = _reference(x, w, bias, stride, pad, relu, res)
-    got = conv.conv2d_nhwc(x, w, bias, stride, pad, relu, res, block_n=block_n)
-    torch.cuda.synchronize()
-    assert got.shape == (B, P, Q, Cout) and got.dtype == torch.bfloat16
-    err = (got.float() - want).abs().max().item()
     scale = want.abs().max().item()
-    assert err <= 1e-2 * scale, (err, scale)                       # north_star bf16 bar
-    assert err <= 2.0 ** -7 * scale, (err, scale)                  # only the bf16 output rounding should remain
+    for cluster_mode in (1, 2):      # one CTA per tile; CTA pairs (tcgen05 cta_group::2) where the tile allows it
+        got = conv.conv2d_nhwc(x, w, bias, stride, pad, relu, res, block_n=block_n, cluster_mode=cluster_mode)
+        torch.cuda.synchronize()
+        assert got.shape == (B, P, Q, Cout) and got.dtype == torch.bfloat16
+        err = (got.float() - want).abs().max().item()
+        assert err <= 1e-2 * scale, (cluster_mode, err, scale)         # north_star bf16 bar
+        assert err <= 2.0 ** -7 * scale, (cluster_mode, err, scale)    # only the bf16 output rounding should remain
 
 
 def test_folded_bottleneck_matches_torch_block():

@@ -18,13 +18,18 @@ CASES = [
     ("c3_tiny", 1, 2, 4, 512, 512, 3, 1, 1, 0),
     ("big_pw", 8, 45, 80, 1024, 256, 1, 1, 0, 0),
     ("big_c3", 8, 45, 80, 256, 256, 3, 1, 1, 0),
+    ("pair_pw_small", 2, 16, 24, 256, 256, 1, 1, 0, 256, 2),
+    ("pair_pw_tail", 1, 9, 21, 512, 128, 1, 1, 0, 128, 2),
+    ("pair_c3", 2, 16, 24, 128, 256, 3, 1, 1, 256, 2),
+    ("pair_big_pw", 8, 45, 80, 1024, 256, 1, 1, 0, 256, 2),
+    ("pair_big_c3", 8, 45, 80, 256, 256, 3, 1, 1, 256, 2),
 ]
 
 CHILD = r"""
 import json, sys, torch, torch.nn.functional as F
 sys.path.insert(0, '.')
 from dpft_b200 import conv
-name, B, H, W, Cin, Cout, R, stride, pad, bn = json.loads(sys.argv[1])
+cfg = json.loads(sys.argv[1]); name, B, H, W, Cin, Cout, R, stride, pad, bn = cfg[:10]; cm = cfg[10] if len(cfg) > 10 else 1
 dev = 'cuda:0'
 torch.backends.cudnn.allow_tf32 = False
 g = torch.Generator(device=dev).manual_seed(1)
@@ -32,7 +37,7 @@ x = torch.randn(B, H, W, Cin, generator=g, device=dev).bfloat16()
 w = (torch.randn(Cout, R, R, Cin, generator=g, device=dev) / (R * R * Cin) ** 0.5).bfloat16()
 bias = torch.randn(Cout, generator=g, device=dev)
 want = F.conv2d(x.float().permute(0, 3, 1, 2), w.float().permute(0, 3, 1, 2), bias, stride=stride, padding=pad).permute(0, 2, 3, 1)
-got = conv.conv2d_nhwc(x, w, bias, stride, pad, False, None, block_n=bn)
+got = conv.conv2d_nhwc(x, w, bias, stride, pad, False, None, block_n=bn, cluster_mode=cm)
 torch.cuda.synchronize()
 d = (got.float() - want).abs()
 res = {"case": name, "max_err": d.max().item(), "scale": want.abs().max().item(), "mean_err": d.mean().item(),
@@ -44,11 +49,11 @@ if res["frac_bad"] > 0:
     res["got0"] = got.flatten(0, 2)[0, :6].float().tolist(); res["want0"] = want.flatten(0, 2)[0, :6].tolist()
 # timing
 import time
-for _ in range(3): conv.conv2d_nhwc(x, w, bias, stride, pad, True, None, block_n=bn)
+for _ in range(3): conv.conv2d_nhwc(x, w, bias, stride, pad, True, None, block_n=bn, cluster_mode=cm)
 torch.cuda.synchronize()
 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 e0.record()
-for _ in range(10): conv.conv2d_nhwc(x, w, bias, stride, pad, True, None, block_n=bn)
+for _ in range(10): conv.conv2d_nhwc(x, w, bias, stride, pad, True, None, block_n=bn, cluster_mode=cm)
 e1.record(); e1.synchronize()
 ms = e0.elapsed_time(e1) / 10
 P = (H + 2 * pad - R) // stride + 1; Q = (W + 2 * pad - R) // stride + 1
