@@ -81,7 +81,7 @@ template <int BLOCK_N, int STAGES, int EPI_RES_BUFS, int CG = 1> struct SmemLayo
     static constexpr int kBBytes = (BLOCK_N / CG) * BLOCK_K * 2;          // a CTA pair holds half of the B tile each
     static constexpr int kStageBytes = kABytes + kBBytes;
     static constexpr int kEpiBytes = 4 * (EPI_RES_BUFS + EPI_OUT_BUFS) * EPI_BUF_BYTES;
-    static constexpr int kBiasBytes = 2 * BLOCK_N * 4;                                      // double-buffered tile bias
+    static constexpr int kBiasBytes = 4 * BLOCK_N * 4;                                      // tile bias, one copy per warp pair
     static constexpr int kBarrierBytes = (2 * STAGES + 4 + 4 * EPI_RES_BUFS) * 8 + 16;
     static constexpr int kTotal = STAGES * kStageBytes + kEpiBytes + kBiasBytes + kBarrierBytes;
 };
@@ -168,7 +168,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     uint8_t* smem_a = smem;
     uint8_t* smem_b = smem + STAGES * L::kABytes;
     uint8_t* smem_epi = smem + STAGES * L::kStageBytes;                  // per warp: residual + output sub-tiles
-    float* smem_bias = reinterpret_cast<float*>(smem_epi + L::kEpiBytes);   // [2][BLOCK_N]
+    float* smem_bias = reinterpret_cast<float*>(smem_epi + L::kEpiBytes);   // [4 pairs][BLOCK_N]
     uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem_epi + L::kEpiBytes + L::kBiasBytes);
     uint64_t* empty_bar = full_bar + STAGES;
     uint64_t* tmem_full = empty_bar + STAGES;
@@ -312,7 +312,8 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         const int my_tiles = cta_id < num_tiles ? (num_tiles - 1 - cta_id) / num_ctas + 1 : 0;
         const uint32_t empty_leader = CG == 2 ? map_to_cta(tmem_empty, 0) : 0;
         const int total_items = my_tiles * kChunks;
-        const bool issuer = grp == 0 && lane == 0;
+        const bool issuer = grp == 0 && lane == 0;          // issues the TMA stores of the pair
+        const bool loader = grp == 1 && lane == 0;          // issues the residual TMA loads of the pair
         auto pair_sync = [&]() { asm volatile("bar.sync %0, 64;" ::"r"(2 + quad) : "memory"); };
 
         auto prefetch_residual = [&](int item) {
@@ -320,7 +321,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
             const int tile = cta_id + (item / kChunks) * num_ctas;
             const int m_tile = (tile / prm.n_tiles) * CG + (int)rank, n_tile = tile % prm.n_tiles;
             const int b = item % EPI_RES_BUFS;
-            if (issuer) {
+            if (loader) {
                 mbar_expect_tx(&my_res_bar[b], EPI_BUF_BYTES);
                 tma_load_2d(&tmap_r, &my_res_bar[b], res_buf + b * EPI_BUF_BYTES, n_tile * BLOCK_N + (item % kChunks) * EPI_COLS,
                             m_tile * BLOCK_M + quad * 32);
@@ -330,7 +331,6 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         int acc = 0;
         uint32_t acc_phase = 0;
         int item = 0;
-        int tile_count = 0;
 #pragma unroll
         for (int i = 0; i < EPI_RES_BUFS - 1; ++i) prefetch_residual(i);
         const int sw = lane & 7;                      // swizzle phase of this thread's row
@@ -339,12 +339,11 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
             mbar_wait(&tmem_full[acc], acc_phase);
             tcgen05_fence_after();
             const int n0 = n_tile * BLOCK_N;
-            // this tile's bias -> shared memory (double-buffered; one named barrier per tile among the 8 epilogue warps)
-            float* bias_s = smem_bias + (tile_count & 1) * BLOCK_N;
-            for (int i = (threadIdx.x - 64) * 4; i < BLOCK_N; i += 256 * 4)
+            // this tile's bias -> the pair's shared-memory copy (the previous tile's readers are past their last pair_sync)
+            float* bias_s = smem_bias + quad * BLOCK_N;
+            for (int i = (grp * 32 + lane) * 4; i < BLOCK_N; i += 64 * 4)
                 *reinterpret_cast<float4*>(bias_s + i) = __ldg(reinterpret_cast<const float4*>(prm.bias + n0 + i));
-            asm volatile("bar.sync 1, 256;" ::: "memory");
-            ++tile_count;
+            pair_sync();
             if (prm.out_f32) {
                 // FPN lateral: inner = conv1x1 + bias (+ top-down), 16 fp32 channels per pixel, written directly (group A)
                 const long long m = (long long)m_tile * BLOCK_M + quad * 32 + lane;
@@ -415,17 +414,16 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
 #pragma unroll
                             for (int t = 0; t < 8; ++t) f[t] = fmaxf(f[t], 0.0f);
                         }
-                        uint4 ov;
+                        uint4 ov;                   // cvt.rn.satfinite packs two floats and clamps to the finite range
+                        uint32_t* ow = reinterpret_cast<uint32_t*>(&ov);
                         if (prm.is_f16) {
-                            __half2* oh = reinterpret_cast<__half2*>(&ov);
 #pragma unroll
-                            for (int t = 0; t < 4; ++t)   // saturate instead of overflowing to inf
-                                oh[t] = __floats2half2_rn(fminf(fmaxf(f[2 * t], -65504.0f), 65504.0f),
-                                                          fminf(fmaxf(f[2 * t + 1], -65504.0f), 65504.0f));
+                            for (int t = 0; t < 4; ++t)
+                                asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(ow[t]) : "f"(f[2 * t + 1]), "f"(f[2 * t]));
                         } else {
-                            __nv_bfloat162* ob = reinterpret_cast<__nv_bfloat162*>(&ov);
 #pragma unroll
-                            for (int t = 0; t < 4; ++t) ob[t] = __floats2bfloat162_rn(f[2 * t], f[2 * t + 1]);
+                            for (int t = 0; t < 4; ++t)
+                                asm("cvt.rn.satfinite.bf16x2.f32 %0, %1, %2;" : "=r"(ow[t]) : "f"(f[2 * t + 1]), "f"(f[2 * t]));
                         }
                         *reinterpret_cast<uint4*>(orow + phys) = ov;
                     }
@@ -646,7 +644,7 @@ extern "C" int dpft_conv2d_nhwc(const void* x, const void* w, const float* bias,
         return launch<128, 6, 3, 2>(ta, tb, td, tr, prm, s2);
     }
     const bool stream_bound = residual != nullptr && prm.kblocks <= 4;   // 1x1 expand convs: deep residual prefetch
-    if (bn == 256) return stream_bound ? launch<256, 2, 5>(ta, tb, td, tr, prm, s) : launch<256, 3, 3>(ta, tb, td, tr, prm, s);
+    if (bn == 256) return stream_bound ? launch<256, 2, 5>(ta, tb, td, tr, prm, s) : launch<256, 3, 2>(ta, tb, td, tr, prm, s);
     if (bn == 128) return stream_bound ? launch<128, 2, 7>(ta, tb, td, tr, prm, s) : launch<128, 4, 3>(ta, tb, td, tr, prm, s);
     return stream_bound ? launch<64, 3, 7>(ta, tb, td, tr, prm, s) : launch<64, 6, 3>(ta, tb, td, tr, prm, s);
 }

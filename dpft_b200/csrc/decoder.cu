@@ -38,7 +38,7 @@ constexpr int kMaxViews = 4;
 constexpr int ROW = C + 1;     // padded smem row of a per-query 16-vector
 
 struct ViewDesc {
-    const float* pyramid;      // (B, S, 16) fp32, positional embedding already added
+    const void* pyramid;       // (B, S, 16) fp32 or f16, positional embedding already added
     const float* weights;      // packed layer image (see pack_layer in dpft_b200/decoder.py)
     const float* transform;    // (B, 4, 4)
     const float* projection;   // (B, 4, 4) (3x4 inputs are padded with the row [0 0 0 1])
@@ -125,7 +125,73 @@ __device__ __forceinline__ float dot16(const float* wrow, const float* x) {
     return acc;
 }
 
-template <int L, int P>
+// 16-channel pyramid row of one corner, as fp32 (4 x 16 B) or f16 (2 x 16 B)
+template <typename PT> struct RowRegs;
+template <> struct RowRegs<float> {
+    float4 q[4];
+    __device__ __forceinline__ void load(const void* base, long long pixel) {
+        const float4* r = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(base) + pixel * C);
+#pragma unroll
+        for (int c4 = 0; c4 < 4; ++c4) q[c4] = __ldg(r + c4);
+    }
+    __device__ __forceinline__ void accumulate(float w, float* agg) const {
+#pragma unroll
+        for (int c4 = 0; c4 < 4; ++c4) {
+            agg[4 * c4] = fmaf(w, q[c4].x, agg[4 * c4]);
+            agg[4 * c4 + 1] = fmaf(w, q[c4].y, agg[4 * c4 + 1]);
+            agg[4 * c4 + 2] = fmaf(w, q[c4].z, agg[4 * c4 + 2]);
+            agg[4 * c4 + 3] = fmaf(w, q[c4].w, agg[4 * c4 + 3]);
+        }
+    }
+};
+template <> struct RowRegs<__half> {
+    uint4 q[2];
+    __device__ __forceinline__ void load(const void* base, long long pixel) {
+        const uint4* r = reinterpret_cast<const uint4*>(reinterpret_cast<const __half*>(base) + pixel * C);
+        q[0] = __ldg(r);
+        q[1] = __ldg(r + 1);
+    }
+    __device__ __forceinline__ void accumulate(float w, float* agg) const {
+        const __half2* h = reinterpret_cast<const __half2*>(q);
+#pragma unroll
+        for (int t = 0; t < 8; ++t) {
+            const float2 f = __half22float2(h[t]);
+            agg[2 * t] = fmaf(w, f.x, agg[2 * t]);
+            agg[2 * t + 1] = fmaf(w, f.y, agg[2 * t + 1]);
+        }
+    }
+};
+
+// bilinear footprint of one sample on an (H, W) level: clamped corner pixels + weights (already times the attention weight)
+struct Corners {
+    long long px[4];
+    float wt[4];
+};
+__device__ __forceinline__ Corners corners_of(float lx, float ly, float a, int H, int W) {
+    Corners c;
+    const float w_im = lx * (float)W - 0.5f;
+    const float h_im = ly * (float)H - 0.5f;
+    // Unconditional loads from clamped corner addresses (weight 0 where the corner or the whole sample is out of bounds):
+    // the row requests of a sample issue back to back instead of behind four branches.
+    const bool inside = h_im > -1.0f && w_im > -1.0f && h_im < (float)H && w_im < (float)W;
+    const float hs = inside ? h_im : 0.0f, ws = inside ? w_im : 0.0f;
+    const float hf = floorf(hs), wf = floorf(ws);
+    const int h0 = (int)hf, w0 = (int)wf;
+    const float lh = hs - hf, lw = ws - wf, hh = 1.0f - lh, hw = 1.0f - lw;
+    const bool t_ok = inside && h0 >= 0, b_ok = inside && h0 + 1 <= H - 1;
+    const bool l_ok = w0 >= 0, r_ok = w0 + 1 <= W - 1;
+    c.wt[0] = t_ok && l_ok ? hh * hw * a : 0.0f;
+    c.wt[1] = t_ok && r_ok ? hh * lw * a : 0.0f;
+    c.wt[2] = b_ok && l_ok ? lh * hw * a : 0.0f;
+    c.wt[3] = b_ok && r_ok ? lh * lw * a : 0.0f;
+    const int h0c = min(max(h0, 0), H - 1), h1c = min(max(h0 + 1, 0), H - 1);
+    const int w0c = min(max(w0, 0), W - 1), w1c = min(max(w0 + 1, 0), W - 1);
+    c.px[0] = (long long)h0c * W + w0c; c.px[1] = (long long)h0c * W + w1c;
+    c.px[2] = (long long)h1c * W + w0c; c.px[3] = (long long)h1c * W + w1c;
+    return c;
+}
+
+template <int L, int P, typename PT>
 __global__ void __launch_bounds__(kThreads)
 decoder_layer_kernel(const LayerParams prm) {
     using IMG = LayerImage<L, P>;
@@ -279,55 +345,38 @@ decoder_layer_kernel(const LayerParams prm) {
 #pragma unroll
     for (int c = 0; c < C; ++c) agg[c] = 0.0f;
     float inb = 0.0f;                                     // attention-weighted in-bounds weight mass (bias term)
-    const float* pyr = vd.pyramid + (long long)b * vd.S * C;
+    const PT* pyr = reinterpret_cast<const PT*>(vd.pyramid) + (long long)b * vd.S * C;
+    // f16 rows are half as wide: two samples (sixteen 16-byte requests) are kept in flight per trip, as with fp32 rows
+    constexpr int SPT = sizeof(PT) == 2 ? 2 : 1;          // samples per trip
+    static_assert(P % SPT == 0, "points per level must be even for the f16 pyramid path");
 #pragma unroll
     for (int l = 0; l < L; ++l) {
         const int H = vd.h[l], W = vd.w[l];
-        const float* lvl = pyr + vd.start[l] * C;
+        const PT* lvl = pyr + vd.start[l] * C;
 #pragma unroll
-        for (int p = 0; p < P; ++p) {
-            const int i = l * P + p;
-            const float* orow = s_w + IMG::off_w + j * IMG::off_stride + (2 * i) * C;
-            const float ox = dot16(orow, vec) + s_w[IMG::off_b + (j * LP + i) * 2];
-            const float oy = dot16(orow + C, vec) + s_w[IMG::off_b + (j * LP + i) * 2 + 1];
-            const float a = logit[i] * linv;
-            const float lx = ref_u + ox / (float)W;
-            const float ly = ref_v + oy / (float)H;
-            const float w_im = lx * (float)W - 0.5f;
-            const float h_im = ly * (float)H - 0.5f;
-            // Unconditional loads from clamped corner addresses (weight 0 where the corner or the whole sample is out of
-            // bounds): the sixteen 16-byte row requests of a sample issue back to back instead of behind four branches.
-            const bool inside = h_im > -1.0f && w_im > -1.0f && h_im < (float)H && w_im < (float)W;
-            const float hs = inside ? h_im : 0.0f, ws = inside ? w_im : 0.0f;
-            const float hf = floorf(hs), wf = floorf(ws);
-            const int h0 = (int)hf, w0 = (int)wf;
-            const float lh = hs - hf, lw = ws - wf, hh = 1.0f - lh, hw = 1.0f - lw;
-            const bool t_ok = inside && h0 >= 0, b_ok = inside && h0 + 1 <= H - 1;
-            const bool l_ok = w0 >= 0, r_ok = w0 + 1 <= W - 1;
-            const float wt[4] = {t_ok && l_ok ? hh * hw * a : 0.0f, t_ok && r_ok ? hh * lw * a : 0.0f,
-                                 b_ok && l_ok ? lh * hw * a : 0.0f, b_ok && r_ok ? lh * lw * a : 0.0f};
-            const int h0c = min(max(h0, 0), H - 1), h1c = min(max(h0 + 1, 0), H - 1);
-            const int w0c = min(max(w0, 0), W - 1), w1c = min(max(w0 + 1, 0), W - 1);
-            const float4* rows[4] = {reinterpret_cast<const float4*>(lvl + ((long long)h0c * W + w0c) * C),
-                                     reinterpret_cast<const float4*>(lvl + ((long long)h0c * W + w1c) * C),
-                                     reinterpret_cast<const float4*>(lvl + ((long long)h1c * W + w0c) * C),
-                                     reinterpret_cast<const float4*>(lvl + ((long long)h1c * W + w1c) * C)};
-            float4 f[4][4];
+        for (int p = 0; p < P; p += SPT) {
+            Corners cs[SPT];
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {
+            for (int u = 0; u < SPT; ++u) {
+                const int i = l * P + p + u;
+                const float* orow = s_w + IMG::off_w + j * IMG::off_stride + (2 * i) * C;
+                const float ox = dot16(orow, vec) + s_w[IMG::off_b + (j * LP + i) * 2];
+                const float oy = dot16(orow + C, vec) + s_w[IMG::off_b + (j * LP + i) * 2 + 1];
+                cs[u] = corners_of(ref_u + ox / (float)W, ref_v + oy / (float)H, logit[i] * linv, H, W);
+            }
+            RowRegs<PT> rows[SPT][4];
 #pragma unroll
-                for (int c4 = 0; c4 < 4; ++c4) f[k][c4] = __ldg(rows[k] + c4);
+            for (int u = 0; u < SPT; ++u) {
+#pragma unroll
+                for (int k = 0; k < 4; ++k) rows[u][k].load(lvl, cs[u].px[k]);
             }
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {
+            for (int u = 0; u < SPT; ++u) {
 #pragma unroll
-                for (int c4 = 0; c4 < 4; ++c4) {
-                    agg[4 * c4] = fmaf(wt[k], f[k][c4].x, agg[4 * c4]);
-                    agg[4 * c4 + 1] = fmaf(wt[k], f[k][c4].y, agg[4 * c4 + 1]);
-                    agg[4 * c4 + 2] = fmaf(wt[k], f[k][c4].z, agg[4 * c4 + 2]);
-                    agg[4 * c4 + 3] = fmaf(wt[k], f[k][c4].w, agg[4 * c4 + 3]);
+                for (int k = 0; k < 4; ++k) {
+                    rows[u][k].accumulate(cs[u].wt[k], agg);
+                    inb += cs[u].wt[k];
                 }
-                inb += wt[k];
             }
         }
     }
@@ -469,7 +518,7 @@ decoder_head_kernel(const HeadParams prm) {
     }
 }
 
-template <int L, int P>
+template <int L, int P, typename PT>
 int launch_layer(const LayerParams& prm, cudaStream_t stream) {
     const size_t smem = sizeof(float) * (((prm.weight_floats + 3) & ~3) + (size_t)prm.N * C * 2 + TQ * ROW + TQ * (prm.d_ffn + 1));
     DPFT_REQUIRE(smem <= 227 * 1024, "decoder: %zu bytes of shared memory needed (N=%d too large)", smem, prm.N);
@@ -479,14 +528,14 @@ int launch_layer(const LayerParams& prm, cudaStream_t stream) {
                  prm.weight_floats, expected);
     static size_t configured = 0;                      // raise the limit only when needed (never inside a graph replay)
     if (smem > configured) {
-        auto kern_attr = decoder_layer_kernel<L, P>;
+        auto kern_attr = decoder_layer_kernel<L, P, PT>;
         int st = cuda_status(cudaFuncSetAttribute(kern_attr, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem),
                              "cudaFuncSetAttribute(decoder_layer_kernel)");
         if (st) return st;
         configured = smem;
     }
     const int tiles = (prm.N + TQ - 1) / TQ;
-    auto kern = decoder_layer_kernel<L, P>;
+    auto kern = decoder_layer_kernel<L, P, PT>;
     kern<<<prm.B * prm.V * tiles, kThreads, smem, stream>>>(prm);
     DPFT_LAUNCH_CHECK("decoder_layer_kernel");
     return DPFT_OK;
@@ -500,7 +549,8 @@ using namespace dpft;
 extern "C" int dpft_decoder_layer_forward(const dpft_decoder_view* views, int V, const float* query, long long query_batch_stride,
                                           const float* pos, const float* center, long long center_batch_stride, float* out,
                                           int B, int N, int L, int P, int d_ffn, int activation, int weight_floats,
-                                          void* stream) {
+                                          int pyramid_dtype, void* stream) {
+    DPFT_REQUIRE(pyramid_dtype == DPFT_F32 || pyramid_dtype == DPFT_F16, "decoder_layer: pyramid dtype must be DPFT_F32 or DPFT_F16");
     DPFT_REQUIRE(views && query && pos && center && out, "decoder_layer: null pointer");
     DPFT_REQUIRE(V >= 1 && V <= kMaxViews, "decoder_layer: V=%d views (1..%d supported)", V, kMaxViews);
     DPFT_REQUIRE(B >= 1 && N >= 1 && d_ffn >= 1 && d_ffn % 4 == 0, "decoder_layer: bad sizes B=%d N=%d d_ffn=%d", B, N, d_ffn);
@@ -520,12 +570,13 @@ extern "C" int dpft_decoder_layer_forward(const dpft_decoder_view* views, int V,
     prm.B = B; prm.V = V; prm.N = N; prm.d_ffn = d_ffn; prm.act = activation; prm.weight_floats = weight_floats;
     cudaStream_t s = (cudaStream_t)stream;
     if (P == 4) {
+        const bool h = pyramid_dtype == DPFT_F16;
         switch (L) {
-            case 1: return launch_layer<1, 4>(prm, s);
-            case 2: return launch_layer<2, 4>(prm, s);
-            case 3: return launch_layer<3, 4>(prm, s);
-            case 4: return launch_layer<4, 4>(prm, s);
-            case 5: return launch_layer<5, 4>(prm, s);
+            case 1: return h ? launch_layer<1, 4, __half>(prm, s) : launch_layer<1, 4, float>(prm, s);
+            case 2: return h ? launch_layer<2, 4, __half>(prm, s) : launch_layer<2, 4, float>(prm, s);
+            case 3: return h ? launch_layer<3, 4, __half>(prm, s) : launch_layer<3, 4, float>(prm, s);
+            case 4: return h ? launch_layer<4, 4, __half>(prm, s) : launch_layer<4, 4, float>(prm, s);
+            case 5: return h ? launch_layer<5, 4, __half>(prm, s) : launch_layer<5, 4, float>(prm, s);
             default: break;
         }
     }

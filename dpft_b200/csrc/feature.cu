@@ -149,10 +149,28 @@ struct FpnOutParams {
     const float* bias;         // [16]
     const float* pos_y;        // (H, 16)
     const float* pos_x;        // (W, 16)
-    float* pyramid;            // (B, S, 16)
+    void* pyramid;             // (B, S, 16) fp32 or f16
+    int pyramid_f16;
     long long S, start;
     int H, W, Hc, Wc;
 };
+
+// one pyramid row (16 channels of one pixel): 64 B as fp32 or 32 B as f16 (saturating)
+__device__ __forceinline__ void store_pyramid_row(void* pyramid, long long pixel, const float* v, bool f16) {
+    if (f16) {
+        uint4 pk[2];
+        uint32_t* w = reinterpret_cast<uint32_t*>(pk);
+#pragma unroll
+        for (int t = 0; t < 8; ++t) asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(w[t]) : "f"(v[2 * t + 1]), "f"(v[2 * t]));
+        uint4* o = reinterpret_cast<uint4*>(reinterpret_cast<__half*>(pyramid) + pixel * FC);
+        o[0] = pk[0];
+        o[1] = pk[1];
+    } else {
+        float4* o = reinterpret_cast<float4*>(reinterpret_cast<float*>(pyramid) + pixel * FC);
+#pragma unroll
+        for (int c4 = 0; c4 < 4; ++c4) o[c4] = make_float4(v[4 * c4], v[4 * c4 + 1], v[4 * c4 + 2], v[4 * c4 + 3]);
+    }
+}
 
 __device__ __forceinline__ int nearest_src(int dst, int in_size, int out_size) {
     // torch 'nearest': src = min(floor(dst * (float(in) / out)), in - 1)
@@ -254,14 +272,17 @@ fpn_output_kernel(const FpnOutParams prm) {
     if (p < H && q < W) {
         const float4* px = reinterpret_cast<const float4*>(prm.pos_x + (long long)q * FC);
         const float4* py = reinterpret_cast<const float4*>(prm.pos_y + (long long)p * FC);
-        float4* o = reinterpret_cast<float4*>(prm.pyramid + ((long long)b * prm.S + prm.start + (long long)p * W + q) * FC);
+        float outv[FC];
 #pragma unroll
         for (int c4 = 0; c4 < 4; ++c4) {
             const float4 a = __ldg(px + c4), c = __ldg(py + c4);
             // reference order: feat += pos_x; feat += pos_y (sinusoidal.py:107-108)
-            o[c4] = make_float4((acc[4 * c4] + a.x) + c.x, (acc[4 * c4 + 1] + a.y) + c.y,
-                                (acc[4 * c4 + 2] + a.z) + c.z, (acc[4 * c4 + 3] + a.w) + c.w);
+            outv[4 * c4] = (acc[4 * c4] + a.x) + c.x;
+            outv[4 * c4 + 1] = (acc[4 * c4 + 1] + a.y) + c.y;
+            outv[4 * c4 + 2] = (acc[4 * c4 + 2] + a.z) + c.z;
+            outv[4 * c4 + 3] = (acc[4 * c4 + 3] + a.w) + c.w;
         }
+        store_pyramid_row(prm.pyramid, (long long)b * prm.S + prm.start + (long long)p * W + q, outv, prm.pyramid_f16 != 0);
     }
 }
 
@@ -400,15 +421,16 @@ fpn_output_tc_kernel(const FpnOutParams prm) {
         const int p = p0 + r;
         if (p < H && q < W) {
             const float4* py = reinterpret_cast<const float4*>(prm.pos_y + (long long)p * FC);
-            float4* o = reinterpret_cast<float4*>(prm.pyramid + ((long long)b * prm.S + prm.start + (long long)p * W + q) * FC);
+            float outv[FC];
 #pragma unroll
             for (int c4 = 0; c4 < 4; ++c4) {
                 const float4 c = __ldg(py + c4);
-                o[c4] = make_float4(((__uint_as_float(v[4 * c4]) + bias4[c4].x) + px4[c4].x) + c.x,
-                                    ((__uint_as_float(v[4 * c4 + 1]) + bias4[c4].y) + px4[c4].y) + c.y,
-                                    ((__uint_as_float(v[4 * c4 + 2]) + bias4[c4].z) + px4[c4].z) + c.z,
-                                    ((__uint_as_float(v[4 * c4 + 3]) + bias4[c4].w) + px4[c4].w) + c.w);
+                outv[4 * c4] = ((__uint_as_float(v[4 * c4]) + bias4[c4].x) + px4[c4].x) + c.x;
+                outv[4 * c4 + 1] = ((__uint_as_float(v[4 * c4 + 1]) + bias4[c4].y) + px4[c4].y) + c.y;
+                outv[4 * c4 + 2] = ((__uint_as_float(v[4 * c4 + 2]) + bias4[c4].z) + px4[c4].z) + c.z;
+                outv[4 * c4 + 3] = ((__uint_as_float(v[4 * c4 + 3]) + bias4[c4].w) + px4[c4].w) + c.w;
             }
+            store_pyramid_row(prm.pyramid, (long long)b * prm.S + prm.start + (long long)p * W + q, outv, prm.pyramid_f16 != 0);
         }
     }
     tc::tcgen05_fence_before();
@@ -627,12 +649,15 @@ extern "C" int dpft_maxpool3x3s2_nhwc(const void* x, void* y, int B, int H, int 
 
 extern "C" int dpft_fpn_output_forward(const float* inner, const float* raw, int raw_channels, const float* lat_w,
                                        const float* lat_b, const float* coarse, int Hc, int Wc, const float* w,
-                                       const float* bias, const float* pos_y, const float* pos_x, float* pyramid,
-                                       long long S, long long start, int B, int H, int W, int impl, void* stream) {
+                                       const float* bias, const float* pos_y, const float* pos_x, void* pyramid,
+                                       int pyramid_dtype, long long S, long long start, int B, int H, int W, int impl,
+                                       void* stream) {
+    DPFT_REQUIRE(pyramid_dtype == DPFT_F32 || pyramid_dtype == DPFT_F16, "fpn_output: pyramid dtype must be DPFT_F32 or DPFT_F16");
     DPFT_REQUIRE(w && bias && pos_y && pos_x && pyramid, "fpn_output: null pointer");
     DPFT_REQUIRE((inner != nullptr) != (raw != nullptr), "fpn_output: exactly one of inner / raw must be given");
     DPFT_REQUIRE(B > 0 && H > 0 && W > 0, "fpn_output: bad size");
-    FpnOutParams prm{inner, raw, lat_w, lat_b, coarse, w, bias, pos_y, pos_x, pyramid, S, start, H, W, Hc, Wc};
+    FpnOutParams prm{inner, raw, lat_w, lat_b, coarse, w, bias, pos_y, pos_x, pyramid, pyramid_dtype == DPFT_F16 ? 1 : 0,
+                     S, start, H, W, Hc, Wc};
     cudaStream_t s = (cudaStream_t)stream;
     DPFT_REQUIRE(impl >= 0 && impl <= 2, "fpn_output: impl must be 0 (auto), 1 (CUDA cores) or 2 (tensor cores)");
     if (!inner) {

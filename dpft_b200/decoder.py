@@ -94,7 +94,8 @@ def head_eligible(head) -> Optional[str]:
 
 
 def layer_forward(views: Sequence[DecoderView], query: torch.Tensor, pos: torch.Tensor, center: torch.Tensor,
-                  out: torch.Tensor, B: int, N: int, L: int, P: int, d_ffn: int, act: int, weight_floats: int) -> None:
+                  out: torch.Tensor, B: int, N: int, L: int, P: int, d_ffn: int, act: int, weight_floats: int,
+                  pyramid_dtype: torch.dtype = torch.float32) -> None:
     lib = native.load_library()
     V = len(views)
     arr = (DecoderView * V)(*views)
@@ -102,7 +103,7 @@ def layer_forward(views: Sequence[DecoderView], query: torch.Tensor, pos: torch.
     cs = 0 if center.dim() == 2 else N * 3
     st = lib.dpft_decoder_layer_forward(ctypes.cast(arr, ctypes.c_void_p), V, native.ptr(query), qs, native.ptr(pos),
                                         native.ptr(center), cs, native.ptr(out), B, N, L, P, d_ffn, act, weight_floats,
-                                        native.stream_ptr(out.device))
+                                        native._DTYPE_CODE[pyramid_dtype], native.stream_ptr(out.device))
     native.check(st, "dpft_decoder_layer_forward")
     native.count_launch()
 

@@ -45,13 +45,14 @@ class FusedEngine:
                                  for v in range(self.V)])
             self.head_w.append(dec.pack_head(mp.reduction_layer, fuser.heads[it], fuser.reduction).to(self.device))
         self.feature_dtype = getattr(model, "feature_dtype", torch.float16)
+        self.pyramid_dtype = getattr(model, "pyramid_dtype", torch.float16)
         # native 16-bit feature path per view where the configuration allows it (model.native_features switches it)
         self.views: List[Optional[NativeView]] = []
         for name in model.inputs:
             why = NativeView.ineligible_reason(model.backbones[name], model.necks[name], model.embeddings[name],
                                                model.skiplinks[name])
             self.views.append(NativeView(model.backbones[name], model.necks[name], model.embeddings[name],
-                                         model.skiplinks[name], self.device, self.feature_dtype)
+                                         model.skiplinks[name], self.device, self.feature_dtype, self.pyramid_dtype)
                               if why is None else None)
         self.query = fuser.query.detach().float().contiguous()
         self.pos = fuser.query_embedding.weight.detach().float().contiguous()
@@ -103,7 +104,8 @@ class FusedEngine:
 
     def accepts(self, batch: Dict[str, torch.Tensor]) -> bool:
         if (self._version(self.model) != self._param_version
-                or getattr(self.model, "feature_dtype", torch.float16) != self.feature_dtype):   # repack
+                or getattr(self.model, "feature_dtype", torch.float16) != self.feature_dtype
+                or getattr(self.model, "pyramid_dtype", torch.float16) != self.pyramid_dtype):   # repack
             self.__init__(self.model)
         x = batch[self.model.inputs[0]]
         return x.dtype == torch.float32 and (x.is_cuda or x.device.type == "cpu")
@@ -155,7 +157,11 @@ class FusedEngine:
         N, V = self.N, self.V
         keep = []                                  # keeps the small per-call device tensors alive
         base_views = []
-        for name, pyr in zip(model.inputs, pyramids):
+        flats = [pyr.flat if pyr.flat.is_contiguous() else pyr.flat.contiguous() for pyr in pyramids]
+        if any(f.dtype not in (torch.float32, torch.float16) for f in flats) or len({f.dtype for f in flats}) != 1:
+            flats = [f.float() for f in flats]     # mixed native / torch views: one storage type per launch
+        pyr_dtype = flats[0].dtype
+        for name, pyr, flat in zip(model.inputs, pyramids, flats):
             t = batch[f"label_to_{name}_t"].float().contiguous()
             p = batch[f"label_to_{name}_p"].float()
             if p.shape[1] == 3:                    # radar projections are 3x4 (dataset.py:271-293)
@@ -163,7 +169,6 @@ class FusedEngine:
             p = p.contiguous()
             shape_hw = batch[f"{name}_shape"][:, :2].float().contiguous()
             flag = t.any().to(torch.int32).reshape(1)
-            flat = pyr.flat if pyr.flat.is_contiguous() else pyr.flat.contiguous()
             keep += [t, p, shape_hw, flag, flat]
             view = dec.DecoderView()
             view.pyramid, view.transform, view.projection = flat.data_ptr(), t.data_ptr(), p.data_ptr()
@@ -183,7 +188,7 @@ class FusedEngine:
                 for v, view in enumerate(base_views):
                     view.weights = self.layer_w[it][v].data_ptr()
                 dec.layer_forward(base_views, query, self.pos, center, views_out, B, N, self.levels[0], self.P,
-                                  self.d_ffn, self.act, self.layer_w[it][0].numel())
+                                  self.d_ffn, self.act, self.layer_w[it][0].numel(), pyr_dtype)
                 last = it == self.I - 1
                 query_out = torch.empty((B, N, 16), dtype=torch.float32, device=dev)
                 center_out = torch.empty((B, N, 3), dtype=torch.float32, device=dev)

@@ -69,8 +69,8 @@ def fpn_output_forward(pyramid: torch.Tensor, start: int, H: int, W: int, w: tor
     raw_c = raw.shape[-1] if raw is not None else 0
     st = _lib().dpft_fpn_output_forward(native.ptr(inner), native.ptr(raw), raw_c, native.ptr(lat_w), native.ptr(lat_b),
                                         native.ptr(coarse), hc, wc, native.ptr(w), native.ptr(bias), native.ptr(pos_y),
-                                        native.ptr(pos_x), native.ptr(pyramid), S, start, B, H, W, impl,
-                                        native.stream_ptr(pyramid.device))
+                                        native.ptr(pos_x), native.ptr(pyramid), native.dtype_code(pyramid), S, start, B, H, W,
+                                        impl, native.stream_ptr(pyramid.device))
     native.check(st, "dpft_fpn_output_forward")
     native.count_launch()
 
@@ -98,9 +98,10 @@ class NativeView:
         return None
 
     def __init__(self, backbone: Backbone, neck: FPN, embedding: MultiLevelSinusoidalEmbedding, skiplink: bool, device,
-                 dtype: torch.dtype = torch.bfloat16):
+                 dtype: torch.dtype = torch.bfloat16, pyramid_dtype: torch.dtype = torch.float32):
         self.device = device
         self.dtype = dtype                                                 # activation / weight type of the backbone
+        self.pyramid_dtype = pyramid_dtype                                 # storage type of the (B, S, 16) pyramid
         self.skiplink = skiplink
         self.cin = backbone.in_channels
         body = backbone.body
@@ -169,7 +170,7 @@ class NativeView:
         sizes = [h * w for h, w in shapes]
         starts = [sum(sizes[:i]) for i in range(len(sizes))]
         S = sum(sizes)
-        pyr = torch.empty((B, S, FC), dtype=torch.float32, device=x.device)
+        pyr = torch.empty((B, S, FC), dtype=self.pyramid_dtype, device=x.device)
         first = 1 if self.skiplink else 0
         coarse = None
         # top-down: coarsest level first

@@ -58,6 +58,7 @@ class DPRT(nn.Module):
         self.native_features = True    # fused pipeline: 16-bit tcgen05 backbone/FPN (True) or torch fp32 features (False)
         self.feature_dtype = torch.float16    # activation type of the native backbone: torch.float16 (10-bit mantissa,
                                               # outputs saturate at +-65504) or torch.bfloat16
+        self.pyramid_dtype = torch.float16    # storage of the native (B, S, 16) feature pyramid: float16 or float32
         self.use_cuda_graph = True     # fused pipeline: replay a captured graph once an input shape repeats
         self.parallel_views = True     # fused pipeline: run the per-view feature extractors on forked streams
         self._engine = None

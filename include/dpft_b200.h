@@ -122,7 +122,8 @@ DPFT_API int dpft_fpn_lateral_forward(const void* x, const void* w, const float*
 /*
  * FPN output stage of one level fused with the sinusoidal positional embedding, written into the view's pyramid:
  *   pyramid[b, start + p*W + q, :] = conv3x3(inner)[b, p, q, :] + bias + pos_x[q, :] + pos_y[p, :]
- * (fpn.py:77 layer_blocks; embeddings/sinusoidal.py:107-108; the (B, S, 16) layout of mpfusion.py:179).
+ * (fpn.py:77 layer_blocks; embeddings/sinusoidal.py:107-108; the (B, S, 16) layout of mpfusion.py:179); the pyramid is
+ * stored as DPFT_F32 or DPFT_F16 (pyramid_dtype; f16 halves the bytes the decoder gathers).
  * Either `inner` (B, H, W, 16) f32 is given (levels fed by dpft_fpn_lateral_forward), or `raw` (B, H, W, raw_channels)
  * f32 with the lateral weights lat_w [16][raw_channels], lat_b [16] and the coarser inner map `coarse` (may be NULL):
  * then inner = lat_w raw + lat_b + nearest-upsampled coarse is formed on the fly (skip-link level, dprt.py:222-225).
@@ -131,8 +132,9 @@ DPFT_API int dpft_fpn_lateral_forward(const void* x, const void* w, const float*
  */
 DPFT_API int dpft_fpn_output_forward(const float* inner, const float* raw, int raw_channels, const float* lat_w,
                                      const float* lat_b, const float* coarse, int Hc, int Wc, const float* w,
-                                     const float* bias, const float* pos_y, const float* pos_x, float* pyramid,
-                                     long long S, long long start, int B, int H, int W, int impl, void* stream);
+                                     const float* bias, const float* pos_y, const float* pos_x, void* pyramid,
+                                     int pyramid_dtype, long long S, long long start, int B, int H, int W, int impl,
+                                     void* stream);
 
 /*
  * Fused query decoder (inference), d_model = 16, 8 heads.
@@ -154,7 +156,7 @@ DPFT_API int dpft_fpn_output_forward(const float* inner, const float* raw, int r
  *   activation    0 = ReLU, 1 = Mish, 2 = GELU
  */
 typedef struct dpft_decoder_view {
-    const float* pyramid;
+    const void* pyramid;        /* (B, S, 16), DPFT_F32 or DPFT_F16 (see pyramid_dtype) */
     const float* weights;
     const float* transform;     /* (B, 4, 4) */
     const float* projection;    /* (B, 4, 4); 3x4 matrices padded with the row [0 0 0 1] */
@@ -169,7 +171,7 @@ typedef struct dpft_decoder_view {
 DPFT_API int dpft_decoder_layer_forward(const dpft_decoder_view* views, int V, const float* query,
                                         long long query_batch_stride, const float* pos, const float* center,
                                         long long center_batch_stride, float* out, int B, int N, int L, int P,
-                                        int d_ffn, int activation, int weight_floats, void* stream);
+                                        int d_ffn, int activation, int weight_floats, int pyramid_dtype, void* stream);
 
 /*
  * View reduction + detection head for one iteration: MPFusion.reduce (mpfusion.py:416-470; 0 = 'linear' with the

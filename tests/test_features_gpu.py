@@ -73,8 +73,11 @@ def test_backbone_and_pyramid(name, view, size):
         assert g.shape == w.shape, k
         assert _rel(g, w) < 5e-3, (k, _rel(g, w))          # f16 activations through up to 33 blocks
     flat, shapes = nv.pyramid(x)
-    assert shapes == want_pyr.shapes and flat.shape == want_pyr.flat.shape
+    assert shapes == want_pyr.shapes and flat.shape == want_pyr.flat.shape and flat.dtype == torch.float32
     assert _rel(flat, want_pyr.flat) < 5e-3, _rel(flat, want_pyr.flat)
+    nv16 = NativeView(m.backbones[view], m.necks[view], m.embeddings[view], True, DEV, torch.float16, torch.float16)
+    flat16, _ = nv16.pyramid(x)                         # f16 storage of the pyramid: one more 2^-11 rounding
+    assert flat16.dtype == torch.float16 and _rel(flat16, flat) < 1e-3, _rel(flat16, flat)
 
 
 def test_fpn_stages_in_isolation():
