@@ -214,7 +214,7 @@ def msda_roofline(model, feats_flat, dev, hbm_peak, peak_src, reps=20):
     D = C // M
     N = model.fuser.n_queries
     g = torch.Generator(device=dev).manual_seed(0)
-    value = flat.view(B, S, M, D).contiguous()
+    value = flat.float().view(B, S, M, D).contiguous()     # the op itself is timed in fp32 (the reference's dtype)
     loc = torch.rand(B, N, M, L, P, 2, generator=g, device=dev)
     attn = torch.softmax(torch.randn(B, N, M, L * P, generator=g, device=dev), -1).view(B, N, M, L, P)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
