@@ -31,7 +31,6 @@ constexpr int BLOCK_M = 128;
 constexpr int BLOCK_K = 64;          // bf16 elements = 128 bytes = one swizzle row
 constexpr int UMMA_K = 16;
 constexpr int kNumThreads = 320;       // warp 0 TMA, warp 1 MMA, warps 2-9 epilogue (two per TMEM lane quadrant / scheduler)
-constexpr int kEpilogueWarp0 = 2;
 
 enum ConvMode : int { kTiled2D = 0, kIm2col = 1 };
 

@@ -146,6 +146,7 @@ struct FpnOutParams {
     const float* lat_b;        // [16]
     const float* coarse;       // (B, Hc, Wc, 16) fp32 inner map of the next coarser level (top-down), or null
     const float* w;            // [9][16 out][16 in] 3x3 weights
+    const uint4* w_packed;     // f16 UMMA image of w (tensor-core kernel), 4608 B
     const float* bias;         // [16]
     const float* pos_y;        // (H, 16)
     const float* pos_x;        // (W, 16)
@@ -303,8 +304,18 @@ constexpr int TC_ROWB = 2 * TC_PLANE;
 constexpr int TC_A_BYTES = (TC_TH + 2) * TC_ROWB;    // 43,520
 constexpr int TC_B_BYTES = 9 * 512;                  // 9 taps x [2 K-halves][2 N-groups][8 rows][16 B]
 
+constexpr int TC_THREADS = 256;
+
+// w[tap][o][c] fp32 -> f16 UMMA image [tap][khalf][ngroup][8 rows][8 elems], once per model
+__global__ void fpn_pack_weights_kernel(const float* __restrict__ w, __half* __restrict__ packed) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= 9 * 16 * 16) return;
+    const int c = i & 15, o = (i >> 4) & 15, tap = i >> 8;
+    packed[tap * 256 + (c >> 3) * 128 + (o >> 3) * 64 + (o & 7) * 8 + (c & 7)] = __float2half_rn(w[i]);
+}
+
 template <int CIN>   // CIN == 0: inner map comes from global memory
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(TC_THREADS)
 fpn_output_tc_kernel(const FpnOutParams prm) {
     extern __shared__ __align__(128) uint8_t tsm[];
     uint8_t* s_a = tsm;
@@ -323,19 +334,14 @@ fpn_output_tc_kernel(const FpnOutParams prm) {
         for (int r = 0; r < TC_TH; ++r) tc::mbar_init(&bars[r], 1);
         tc::fence_barrier_init();
     }
-    // 3x3 weights -> f16, [tap][khalf][ngroup][8 rows][8 elems]   (w is [tap][o][c] fp32)
-    for (int i = tid; i < 9 * 16 * 16; i += 128) {
-        const int c = i & 15, o = (i >> 4) & 15, tap = i >> 8;
-        const int off = tap * 512 + (c >> 3) * 256 + (o >> 3) * 128 + (o & 7) * 16 + (c & 7) * 2;
-        *reinterpret_cast<__half*>(s_b + off) = __float2half_rn(__ldg(prm.w + i));
-    }
+    for (int i = tid; i < TC_B_BYTES / 16; i += TC_THREADS) reinterpret_cast<uint4*>(s_b)[i] = __ldg(prm.w_packed + i);
     if (CIN > 0) {
-        for (int i = tid; i < FC * CIN; i += 128) s_lat[i] = __ldg(prm.lat_w + i);
+        for (int i = tid; i < FC * CIN; i += TC_THREADS) s_lat[i] = __ldg(prm.lat_w + i);
         if (tid < FC) s_lat[FC * CIN + tid] = __ldg(prm.lat_b + tid);
         __syncthreads();
     }
     // inner halo tile (zero outside the image), f16
-    for (int i = tid; i < (TC_TH + 2) * TC_PW; i += 128) {
+    for (int i = tid; i < (TC_TH + 2) * TC_PW; i += TC_THREADS) {
         const int rr = i / TC_PW, px = i - rr * TC_PW;
         const int hh = p0 - 1 + rr, ww = q0 - 1 + px;
         float v[FC];
@@ -409,10 +415,10 @@ fpn_output_tc_kernel(const FpnOutParams prm) {
     float4 px4[4], bias4[4];
 #pragma unroll
     for (int c4 = 0; c4 < 4; ++c4) {
-        px4[c4] = q < W ? __ldg(reinterpret_cast<const float4*>(prm.pos_x + (long long)q * FC) + c4) : make_float4(0, 0, 0, 0);
+        px4[c4] = (q < W && warp < 4) ? __ldg(reinterpret_cast<const float4*>(prm.pos_x + (long long)q * FC) + c4) : make_float4(0, 0, 0, 0);
         bias4[c4] = __ldg(reinterpret_cast<const float4*>(prm.bias) + c4);
     }
-    for (int r = 0; r < TC_TH; ++r) {
+    for (int r = 0; r < TC_TH && warp < 4; ++r) {
         tc::mbar_wait(&bars[r], 0);
         tc::tcgen05_fence_after();
         uint32_t v[16];
@@ -458,9 +464,23 @@ constexpr int ST_ROWB = 2 * ST_PLANE;
 constexpr int ST_A_BYTES = ST_ROWS * ST_ROWB;        // 56,576
 constexpr int ST_B_BYTES = 7 * 4 * 2048;             // (r, tap pair) x [2 K-halves][8 N-groups][8 rows][16 B] = 57,344
 
+constexpr int ST_THREADS = 256;                      // all build the operands; warps 0-3 own the 128 TMEM lanes
+
+// w[r][s][c][o] fp32 -> f16 UMMA image [(r*4 + s/2)][s&1][o/8][o%8][c (8, zero padded)] (zero 8th tap), once per model
+template <int CIN>
+__global__ void stem_pack_weights_kernel(const float* __restrict__ w, __half* __restrict__ packed) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;      // one packed element
+    if (i >= ST_B_BYTES / 2) return;
+    const int c = i & 7, orow = (i >> 3) & 7, og = (i >> 6) & 7, kh = (i >> 9) & 1, rj = i >> 10;
+    const int r = rj >> 2, s2 = (rj & 3) * 2 + kh, o = og * 8 + orow;
+    float v = 0.0f;
+    if (s2 < 7 && c < CIN) v = w[((r * 7 + s2) * CIN + c) * 64 + o];
+    packed[i] = __float2half_rn(v);
+}
+
 template <int CIN, typename OT>
-__global__ void __launch_bounds__(128)
-stem_tc_kernel(const float* __restrict__ x, const float* __restrict__ w /* [7][7][CIN][64] */, const float* __restrict__ bias,
+__global__ void __launch_bounds__(ST_THREADS)
+stem_tc_kernel(const float* __restrict__ x, const uint4* __restrict__ w_packed, const float* __restrict__ bias,
                OT* __restrict__ y, int H, int W, int P, int Q) {
     extern __shared__ __align__(128) uint8_t tsm[];
     uint8_t* s_a = tsm;
@@ -477,20 +497,11 @@ stem_tc_kernel(const float* __restrict__ x, const float* __restrict__ w /* [7][7
         for (int r = 0; r < ST_TH; ++r) tc::mbar_init(&bars[r], 1);
         tc::fence_barrier_init();
     }
-    // weights: zero fill, then scatter w[r][s][c][o] into [(r*4 + s/2)][s&1][o/8][o%8][c]
-    for (int i = tid; i < ST_B_BYTES / 16; i += 128) reinterpret_cast<uint4*>(s_b)[i] = make_uint4(0, 0, 0, 0);
-    __syncthreads();
-    for (int i = tid; i < 49 * CIN * 64; i += 128) {
-        const int o = i & 63;
-        const int c = (i >> 6) % CIN;
-        const int tap = (i >> 6) / CIN;
-        const int r = tap / 7, s2 = tap - r * 7;
-        const int off = (r * 4 + (s2 >> 1)) * 2048 + (s2 & 1) * 1024 + (o >> 3) * 128 + (o & 7) * 16 + c * 2;
-        *reinterpret_cast<__half*>(s_b + off) = __float2half_rn(__ldg(w + i));
-    }
+    // weights: the pre-packed f16 UMMA image
+    for (int i = tid; i < ST_B_BYTES / 16; i += ST_THREADS) reinterpret_cast<uint4*>(s_b)[i] = __ldg(w_packed + i);
     // input tile: rows 2*p0-3 .. 2*p0-3+ST_ROWS-1, columns 2*q0-3 .. (+2*ST_PLANE_ENTRIES-1), even/odd planes
     const int h_base = 2 * p0 - 3, w_base = 2 * q0 - 3;
-    for (int i = tid; i < ST_ROWS * 2 * ST_PLANE_ENTRIES; i += 128) {
+    for (int i = tid; i < ST_ROWS * 2 * ST_PLANE_ENTRIES; i += ST_THREADS) {
         const int rr = i / (2 * ST_PLANE_ENTRIES);
         const int xl = i - rr * (2 * ST_PLANE_ENTRIES);          // local column
         const int hh = h_base + rr, ww = w_base + xl;
@@ -528,7 +539,7 @@ stem_tc_kernel(const float* __restrict__ x, const float* __restrict__ w /* [7][7
     }
     __syncwarp();
     const int q = q0 + tid;
-    for (int pr = 0; pr < ST_TH; ++pr) {
+    for (int pr = 0; pr < ST_TH && warp < 4; ++pr) {
         tc::mbar_wait(&bars[pr], 0);
         tc::tcgen05_fence_after();
         const int p = p0 + pr;
@@ -568,7 +579,7 @@ stem_tc_kernel(const float* __restrict__ x, const float* __restrict__ w /* [7][7
 }
 
 template <int CIN, typename OT>
-static int launch_stem_tc(const float* x, const float* w, const float* bias, void* y, int B, int H, int W, int P, int Q,
+static int launch_stem_tc(const float* x, const void* w_packed, const float* bias, void* y, int B, int H, int W, int P, int Q,
                           cudaStream_t s) {
     auto kern = stem_tc_kernel<CIN, OT>;
     const size_t smem = ST_A_BYTES + ST_B_BYTES + ST_TH * 8 + 16;
@@ -579,7 +590,7 @@ static int launch_stem_tc(const float* x, const float* w, const float* bias, voi
         configured = true;
     }
     const dim3 grid((Q + ST_TW - 1) / ST_TW, (P + ST_TH - 1) / ST_TH, B);
-    kern<<<grid, 128, smem, s>>>(x, w, bias, (OT*)y, H, W, P, Q);
+    kern<<<grid, ST_THREADS, smem, s>>>(x, (const uint4*)w_packed, bias, (OT*)y, H, W, P, Q);
     return 0;
 }
 
@@ -602,8 +613,19 @@ static int launch_stem(const float* x, const float* w, const float* bias, void* 
     return 0;
 }
 
-extern "C" int dpft_stem_conv7x7_forward(const float* x, const float* w, const float* bias, void* y, int B, int H, int W,
-                                         int Cin, int dtype, int impl, void* stream) {
+extern "C" int dpft_stem_pack_weights(const float* w, void* packed, int Cin, void* stream) {
+    DPFT_REQUIRE(w && packed, "stem_pack_weights: null pointer");
+    DPFT_REQUIRE(Cin == 3 || Cin == 6, "stem_pack_weights: Cin=%d (3 or 6 supported)", Cin);
+    const int n = ST_B_BYTES / 2;
+    if (Cin == 3) stem_pack_weights_kernel<3><<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(w, (__half*)packed);
+    else stem_pack_weights_kernel<6><<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(w, (__half*)packed);
+    DPFT_LAUNCH_CHECK("stem_pack_weights_kernel");
+    return DPFT_OK;
+}
+
+extern "C" int dpft_stem_conv7x7_forward(const float* x, const float* w, const void* w_packed, const float* bias, void* y,
+                                         int B, int H, int W, int Cin, int dtype, int impl, void* stream) {
+    DPFT_REQUIRE(impl != 2 || w_packed, "stem: the tensor-core kernel needs the packed weights (dpft_stem_pack_weights)");
     DPFT_REQUIRE(impl >= 0 && impl <= 2, "stem: impl must be 0 (auto), 1 (CUDA cores) or 2 (tensor cores)");
     DPFT_REQUIRE(x && w && bias && y, "stem: null pointer");
     DPFT_REQUIRE(dtype == DPFT_BF16 || dtype == DPFT_F16, "stem: output dtype must be DPFT_BF16 or DPFT_F16");
@@ -614,11 +636,11 @@ extern "C" int dpft_stem_conv7x7_forward(const float* x, const float* w, const f
     const size_t smem = sizeof(float) * (49 * Cin * STEM_COUT + STEM_PH * STEM_PW * Cin);
     cudaStream_t s = (cudaStream_t)stream;
     int st;
-    if (impl == 2 || (impl == 0 && Q >= 64)) {
-        if (Cin == 3) st = dtype == DPFT_F16 ? launch_stem_tc<3, __half>(x, w, bias, y, B, H, W, P, Q, s)
-                                             : launch_stem_tc<3, __nv_bfloat16>(x, w, bias, y, B, H, W, P, Q, s);
-        else st = dtype == DPFT_F16 ? launch_stem_tc<6, __half>(x, w, bias, y, B, H, W, P, Q, s)
-                                    : launch_stem_tc<6, __nv_bfloat16>(x, w, bias, y, B, H, W, P, Q, s);
+    if (impl == 2 || (impl == 0 && Q >= 64 && w_packed)) {
+        if (Cin == 3) st = dtype == DPFT_F16 ? launch_stem_tc<3, __half>(x, w_packed, bias, y, B, H, W, P, Q, s)
+                                             : launch_stem_tc<3, __nv_bfloat16>(x, w_packed, bias, y, B, H, W, P, Q, s);
+        else st = dtype == DPFT_F16 ? launch_stem_tc<6, __half>(x, w_packed, bias, y, B, H, W, P, Q, s)
+                                    : launch_stem_tc<6, __nv_bfloat16>(x, w_packed, bias, y, B, H, W, P, Q, s);
         if (st) return st;
         DPFT_LAUNCH_CHECK("stem_tc_kernel");
         return DPFT_OK;
@@ -647,16 +669,23 @@ extern "C" int dpft_maxpool3x3s2_nhwc(const void* x, void* y, int B, int H, int 
     return DPFT_OK;
 }
 
+extern "C" int dpft_fpn_pack_weights(const float* w, void* packed, void* stream) {
+    DPFT_REQUIRE(w && packed, "fpn_pack_weights: null pointer");
+    fpn_pack_weights_kernel<<<9, 256, 0, (cudaStream_t)stream>>>(w, (__half*)packed);
+    DPFT_LAUNCH_CHECK("fpn_pack_weights_kernel");
+    return DPFT_OK;
+}
+
 extern "C" int dpft_fpn_output_forward(const float* inner, const float* raw, int raw_channels, const float* lat_w,
                                        const float* lat_b, const float* coarse, int Hc, int Wc, const float* w,
-                                       const float* bias, const float* pos_y, const float* pos_x, void* pyramid,
+                                       const void* w_packed, const float* bias, const float* pos_y, const float* pos_x, void* pyramid,
                                        int pyramid_dtype, long long S, long long start, int B, int H, int W, int impl,
                                        void* stream) {
     DPFT_REQUIRE(pyramid_dtype == DPFT_F32 || pyramid_dtype == DPFT_F16, "fpn_output: pyramid dtype must be DPFT_F32 or DPFT_F16");
     DPFT_REQUIRE(w && bias && pos_y && pos_x && pyramid, "fpn_output: null pointer");
     DPFT_REQUIRE((inner != nullptr) != (raw != nullptr), "fpn_output: exactly one of inner / raw must be given");
     DPFT_REQUIRE(B > 0 && H > 0 && W > 0, "fpn_output: bad size");
-    FpnOutParams prm{inner, raw, lat_w, lat_b, coarse, w, bias, pos_y, pos_x, pyramid, pyramid_dtype == DPFT_F16 ? 1 : 0,
+    FpnOutParams prm{inner, raw, lat_w, lat_b, coarse, w, (const uint4*)w_packed, bias, pos_y, pos_x, pyramid, pyramid_dtype == DPFT_F16 ? 1 : 0,
                      S, start, H, W, Hc, Wc};
     cudaStream_t s = (cudaStream_t)stream;
     DPFT_REQUIRE(impl >= 0 && impl <= 2, "fpn_output: impl must be 0 (auto), 1 (CUDA cores) or 2 (tensor cores)");
@@ -665,7 +694,8 @@ extern "C" int dpft_fpn_output_forward(const float* inner, const float* raw, int
         DPFT_REQUIRE(coarse == nullptr || (Hc > 0 && Wc > 0), "fpn_output: bad coarse size");
         DPFT_REQUIRE(raw_channels == 3 || raw_channels == 6, "fpn_output: raw_channels=%d (3 or 6 supported)", raw_channels);
     }
-    if (impl == 2 || (impl == 0 && W >= 96)) {          // wide levels: 128-pixel row strips on the tensor cores
+    DPFT_REQUIRE(impl != 2 || w_packed, "fpn_output: the tensor-core kernel needs the packed weights (dpft_fpn_pack_weights)");
+    if (impl == 2 || (impl == 0 && W >= 96 && w_packed)) {          // wide levels: 128-pixel row strips on the tensor cores
         const dim3 tgrid((W + TC_TW - 1) / TC_TW, (H + TC_TH - 1) / TC_TH, B);
         const size_t smem = TC_A_BYTES + TC_B_BYTES + TC_TH * 8 + 16 + sizeof(float) * (FC * 6 + FC);
         static bool configured = false;
@@ -676,9 +706,9 @@ extern "C" int dpft_fpn_output_forward(const float* inner, const float* raw, int
             if (st) return st;
             configured = true;
         }
-        if (inner) fpn_output_tc_kernel<0><<<tgrid, 128, smem, s>>>(prm);
-        else if (raw_channels == 3) fpn_output_tc_kernel<3><<<tgrid, 128, smem, s>>>(prm);
-        else fpn_output_tc_kernel<6><<<tgrid, 128, smem, s>>>(prm);
+        if (inner) fpn_output_tc_kernel<0><<<tgrid, TC_THREADS, smem, s>>>(prm);
+        else if (raw_channels == 3) fpn_output_tc_kernel<3><<<tgrid, TC_THREADS, smem, s>>>(prm);
+        else fpn_output_tc_kernel<6><<<tgrid, TC_THREADS, smem, s>>>(prm);
         DPFT_LAUNCH_CHECK("fpn_output_tc_kernel");
         return DPFT_OK;
     }

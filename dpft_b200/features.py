@@ -28,11 +28,29 @@ def _lib():
     return native.load_library()
 
 
+def stem_pack_weights(w: torch.Tensor) -> torch.Tensor:
+    """[7][7][Cin][64] fp32 -> the f16 operand image of the tcgen05 stem kernel (57344 bytes)."""
+    packed = torch.empty(57344, dtype=torch.uint8, device=w.device)
+    st = _lib().dpft_stem_pack_weights(native.ptr(w), native.ptr(packed), w.shape[2], native.stream_ptr(w.device))
+    native.check(st, "dpft_stem_pack_weights")
+    return packed
+
+
+def fpn_pack_weights(w: torch.Tensor) -> torch.Tensor:
+    """[3][3][16][16] fp32 -> the f16 operand image of the tcgen05 FPN output kernel (4608 bytes)."""
+    packed = torch.empty(4608, dtype=torch.uint8, device=w.device)
+    st = _lib().dpft_fpn_pack_weights(native.ptr(w), native.ptr(packed), native.stream_ptr(w.device))
+    native.check(st, "dpft_fpn_pack_weights")
+    return packed
+
+
 def stem_forward(x: torch.Tensor, w: torch.Tensor, bias: torch.Tensor, dtype: torch.dtype = torch.bfloat16,
-                 impl: int = 0) -> torch.Tensor:
+                 impl: int = 0, w_packed: Optional[torch.Tensor] = None) -> torch.Tensor:
     B, H, W, Cin = x.shape
     y = torch.empty((B, (H - 1) // 2 + 1, (W - 1) // 2 + 1, 64), dtype=dtype, device=x.device)
-    st = _lib().dpft_stem_conv7x7_forward(native.ptr(x), native.ptr(w), native.ptr(bias), native.ptr(y), B, H, W, Cin,
+    if w_packed is None and impl == 2:
+        w_packed = stem_pack_weights(w)
+    st = _lib().dpft_stem_conv7x7_forward(native.ptr(x), native.ptr(w), native.ptr(w_packed), native.ptr(bias), native.ptr(y), B, H, W, Cin,
                                           native.dtype_code(y), impl, native.stream_ptr(x.device))
     native.check(st, "dpft_stem_conv7x7_forward")
     native.count_launch()
@@ -63,12 +81,15 @@ def lateral_forward(x: torch.Tensor, w: torch.Tensor, bias: torch.Tensor, coarse
 def fpn_output_forward(pyramid: torch.Tensor, start: int, H: int, W: int, w: torch.Tensor, bias: torch.Tensor,
                        pos_y: torch.Tensor, pos_x: torch.Tensor, inner: Optional[torch.Tensor] = None,
                        raw: Optional[torch.Tensor] = None, lat_w: Optional[torch.Tensor] = None,
-                       lat_b: Optional[torch.Tensor] = None, coarse: Optional[torch.Tensor] = None, impl: int = 0) -> None:
+                       lat_b: Optional[torch.Tensor] = None, coarse: Optional[torch.Tensor] = None, impl: int = 0,
+                       w_packed: Optional[torch.Tensor] = None) -> None:
     B, S, _ = pyramid.shape
+    if w_packed is None and impl == 2:
+        w_packed = fpn_pack_weights(w)
     hc, wc = (coarse.shape[1], coarse.shape[2]) if coarse is not None else (0, 0)
     raw_c = raw.shape[-1] if raw is not None else 0
     st = _lib().dpft_fpn_output_forward(native.ptr(inner), native.ptr(raw), raw_c, native.ptr(lat_w), native.ptr(lat_b),
-                                        native.ptr(coarse), hc, wc, native.ptr(w), native.ptr(bias), native.ptr(pos_y),
+                                        native.ptr(coarse), hc, wc, native.ptr(w), native.ptr(w_packed), native.ptr(bias), native.ptr(pos_y),
                                         native.ptr(pos_x), native.ptr(pyramid), native.dtype_code(pyramid), S, start, B, H, W,
                                         impl, native.stream_ptr(pyramid.device))
     native.check(st, "dpft_fpn_output_forward")
@@ -112,6 +133,7 @@ class NativeView:
             w = torch.einsum("orsc,cd->orsd", w, adj)
         self.stem_w = w.permute(1, 2, 3, 0).contiguous().to(device)        # [7][7][Cin][64]
         self.stem_b = b.to(device)
+        self.stem_w_packed = stem_pack_weights(self.stem_w)
         self.stages: List[List[Tuple[FoldedConv, FoldedConv, FoldedConv, Optional[FoldedConv]]]] = []
         for s in range(body.n_stages):
             blocks = []
@@ -124,12 +146,13 @@ class NativeView:
         # FPN
         fpn = neck.fpn
         self.n_levels = len(neck.in_channels_list)
-        self.out_w, self.out_b, self.lat_w, self.lat_b = [], [], [], []
+        self.out_w, self.out_b, self.lat_w, self.lat_b, self.out_w_packed = [], [], [], [], []
         for i in range(self.n_levels):
             lat = fpn.inner_blocks[i][0]
             out = fpn.layer_blocks[i][0]
             self.out_w.append(out.weight.detach().float().permute(2, 3, 0, 1).contiguous().to(device))   # [3][3][o][c]
             self.out_b.append(out.bias.detach().float().contiguous().to(device))
+            self.out_w_packed.append(fpn_pack_weights(self.out_w[-1]))
             if skiplink and i == 0:
                 self.lat_w.append(lat.weight.detach().float()[:, :, 0, 0].contiguous().to(device))        # [16][Cin]
                 self.lat_b.append(lat.bias.detach().float().contiguous().to(device))
@@ -153,7 +176,7 @@ class NativeView:
 
     def backbone(self, x: torch.Tensor) -> List[torch.Tensor]:
         """x (B,H,W,Cin) fp32 -> [layer1, ...] NHWC bf16."""
-        y = maxpool_forward(stem_forward(x, self.stem_w, self.stem_b, self.dtype))
+        y = maxpool_forward(stem_forward(x, self.stem_w, self.stem_b, self.dtype, w_packed=self.stem_w_packed))
         feats = []
         for blocks in self.stages:
             for c1, c2, c3, ds in blocks:
@@ -179,11 +202,12 @@ class NativeView:
             inner = lateral_forward(f, self.lat_w[li], self.lat_b[li], coarse)
             H, W = shapes[li]
             py, px = self._tables(li, H, W)
-            fpn_output_forward(pyr, starts[li], H, W, self.out_w[li], self.out_b[li], py, px, inner=inner)
+            fpn_output_forward(pyr, starts[li], H, W, self.out_w[li], self.out_b[li], py, px, inner=inner,
+                               w_packed=self.out_w_packed[li])
             coarse = inner
         if self.skiplink:
             H, W = shapes[0]
             py, px = self._tables(0, H, W)
             fpn_output_forward(pyr, 0, H, W, self.out_w[0], self.out_b[0], py, px, raw=x, lat_w=self.lat_w[0],
-                               lat_b=self.lat_b[0], coarse=coarse)
+                               lat_b=self.lat_b[0], coarse=coarse, w_packed=self.out_w_packed[0])
         return pyr, shapes

@@ -101,10 +101,14 @@ DPFT_API int dpft_conv2d_nhwc(const void* x, const void* w, const float* bias, c
  * (folded) + ReLU, reference src/dprt/models/backbones/resnet.py:98-101 (torchvision conv1/bn1/relu).
  *   x (B, H, W, Cin) f32 NHWC, Cin = 3 or 6, raw 0..255 values;  w [7][7][Cin][64] f32;  bias [64] f32
  *   y (B, P, Q, 64) dtype (DPFT_F16 | DPFT_BF16), P = (H-1)/2+1, Q = (W-1)/2+1
- * impl: 0 = choose (tcgen05 implicit GEMM with f16 operands for Q >= 64, else the fp32 CUDA-core kernel), 1 / 2 = force.
+ * w_packed: output of dpft_stem_pack_weights or NULL.
+ * impl: 0 = choose (tcgen05 implicit GEMM with f16 operands for Q >= 64 when w_packed is given, else the fp32 CUDA-core
+ * kernel), 1 / 2 = force.
  */
-DPFT_API int dpft_stem_conv7x7_forward(const float* x, const float* w, const float* bias, void* y, int B, int H, int W,
-                                       int Cin, int dtype, int impl, void* stream);
+DPFT_API int dpft_stem_conv7x7_forward(const float* x, const float* w, const void* w_packed, const float* bias, void* y,
+                                       int B, int H, int W, int Cin, int dtype, int impl, void* stream);
+/* w [7][7][Cin][64] f32 -> the 57344-byte f16 operand image the tcgen05 stem kernel stages (done once per model). */
+DPFT_API int dpft_stem_pack_weights(const float* w, void* packed, int Cin, void* stream);
 
 /* torchvision ResNet maxpool (kernel 3, stride 2, padding 1), NHWC bf16, C % 8 == 0.  y (B, (H-1)/2+1, (W-1)/2+1, C). */
 DPFT_API int dpft_maxpool3x3s2_nhwc(const void* x, void* y, int B, int H, int W, int C, int dtype, void* stream);
@@ -128,13 +132,18 @@ DPFT_API int dpft_fpn_lateral_forward(const void* x, const void* w, const float*
  * f32 with the lateral weights lat_w [16][raw_channels], lat_b [16] and the coarser inner map `coarse` (may be NULL):
  * then inner = lat_w raw + lat_b + nearest-upsampled coarse is formed on the fly (skip-link level, dprt.py:222-225).
  *   w [3][3][16 out][16 in] f32;  bias [16];  pos_y (H, 16), pos_x (W, 16) f32
- * impl: 0 = choose (tcgen05 row-strip kernel with an f16 inner tile for W >= 96, else the fp32 CUDA-core kernel), 1 / 2 = force.
+ * w_packed: output of dpft_fpn_pack_weights or NULL.
+ * impl: 0 = choose (tcgen05 row-strip kernel with an f16 inner tile for W >= 96 when w_packed is given, else the fp32
+ * CUDA-core kernel), 1 / 2 = force.
  */
 DPFT_API int dpft_fpn_output_forward(const float* inner, const float* raw, int raw_channels, const float* lat_w,
                                      const float* lat_b, const float* coarse, int Hc, int Wc, const float* w,
-                                     const float* bias, const float* pos_y, const float* pos_x, void* pyramid,
+                                     const void* w_packed, const float* bias, const float* pos_y, const float* pos_x, void* pyramid,
                                      int pyramid_dtype, long long S, long long start, int B, int H, int W, int impl,
                                      void* stream);
+
+/* w [3][3][16][16] f32 -> the 4608-byte f16 operand image of the tcgen05 FPN output kernel (done once per model). */
+DPFT_API int dpft_fpn_pack_weights(const float* w, void* packed, void* stream);
 
 /*
  * Fused query decoder (inference), d_model = 16, 8 heads.

@@ -19,10 +19,15 @@ LAYERS = {
     "s4_conv1": (23, 40, 2048, 512, 1, 1, 0, False), "s4_conv2": (23, 40, 512, 512, 3, 1, 1, False),
     "s4_conv3": (23, 40, 512, 2048, 1, 1, 0, True),
     "s3_down": (90, 160, 512, 1024, 1, 2, 0, False), "s3_conv2_s2": (90, 160, 256, 256, 3, 2, 1, False),
+    # radar ResNet-50 at 256x256 (bs 8): small-M layers
+    "r1_conv2": (64, 64, 64, 64, 3, 1, 1, False), "r2_conv3": (32, 32, 128, 512, 1, 1, 0, True),
+    "r3_conv1": (16, 16, 1024, 256, 1, 1, 0, False), "r3_conv2": (16, 16, 256, 256, 3, 1, 1, False),
+    "r3_conv3": (16, 16, 256, 1024, 1, 1, 0, True), "r4_conv2": (8, 8, 512, 512, 3, 1, 1, False),
 }
 B = 8
 dev = "cuda:0"
-only = sys.argv[1:] or None
+SWEEP = "--sweep" in sys.argv
+only = [a for a in sys.argv[1:] if not a.startswith("--")] or None
 flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
 for name, (H, W, Cin, Cout, R, stride, pad, res) in LAYERS.items():
     if only and name not in only:
@@ -34,6 +39,28 @@ for name, (H, W, Cin, Cout, R, stride, pad, res) in LAYERS.items():
     P, Q = (H + 2 * pad - R) // stride + 1, (W + 2 * pad - R) // stride + 1
     r = torch.randn(B, P, Q, Cout, generator=g, device=dev).half() if res else None
     out = torch.empty(B, P, Q, Cout, device=dev, dtype=torch.float16)
+    if SWEEP:   # every (output-channel tile, CTA-pair) choice, L2 flushed
+        res_row = {"layer": name}
+        for bn in (64, 128, 256):
+            if Cout % bn:
+                continue
+            for cm in (1, 2):
+                if cm == 2 and bn < 128:
+                    continue
+                ts = []
+                for _ in range(2):
+                    conv.conv2d_nhwc(x, w, bias, stride, pad, True, r, out, block_n=bn, cluster_mode=cm)
+                for _ in range(5):
+                    flush.zero_()
+                    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    e0.record()
+                    conv.conv2d_nhwc(x, w, bias, stride, pad, True, r, out, block_n=bn, cluster_mode=cm)
+                    e1.record()
+                    e1.synchronize()
+                    ts.append(e0.elapsed_time(e1) * 1e3)
+                res_row[f"bn{bn}_cg{cm}"] = round(min(ts), 1)
+        print(json.dumps(res_row), flush=True)
+        continue
     for _ in range(3):
         conv.conv2d_nhwc(x, w, bias, stride, pad, True, r, out)
     ts_cold, ts_warm = [], []

@@ -41,8 +41,8 @@ with torch.no_grad():
     res = {}
     for name, nv in zip(model.inputs, eng.views):
         x = batch[name].contiguous()
-        stem = features.stem_forward(x, nv.stem_w, nv.stem_b, nv.dtype)
-        res[f"{name}.stem"] = timeit(lambda: features.stem_forward(x, nv.stem_w, nv.stem_b, nv.dtype))
+        stem = features.stem_forward(x, nv.stem_w, nv.stem_b, nv.dtype, w_packed=nv.stem_w_packed)
+        res[f"{name}.stem"] = timeit(lambda: features.stem_forward(x, nv.stem_w, nv.stem_b, nv.dtype, w_packed=nv.stem_w_packed))
         pooled = features.maxpool_forward(stem)
         res[f"{name}.maxpool"] = timeit(lambda: features.maxpool_forward(stem))
         y = pooled
