@@ -341,52 +341,65 @@ fpn_output_tc_kernel(const FpnOutParams prm) {
         __syncthreads();
     }
     // inner halo tile (zero outside the image), f16
-    for (int i = tid; i < (TC_TH + 2) * TC_PW; i += TC_THREADS) {
-        const int rr = i / TC_PW, px = i - rr * TC_PW;
-        const int hh = p0 - 1 + rr, ww = q0 - 1 + px;
-        float v[FC];
+    // (batches of TC_BATCH entries per thread: every global load of a batch is issued before any is consumed)
+    constexpr int TC_ENTRIES = (TC_TH + 2) * TC_PW;
+    constexpr int TC_BATCH = 3;
+    for (int base = tid; base < TC_ENTRIES; base += TC_BATCH * TC_THREADS) {
+        float xin[TC_BATCH][CIN > 0 ? CIN : 1];
+        float4 cf[TC_BATCH][4];
+        bool okv[TC_BATCH];
 #pragma unroll
-        for (int c = 0; c < FC; ++c) v[c] = 0.0f;
-        if (px < TC_TW + 2 && hh >= 0 && hh < H && ww >= 0 && ww < W) {
+        for (int u = 0; u < TC_BATCH; ++u) {
+            const int i = base + u * TC_THREADS;
+            const int rr = i / TC_PW, px = i - rr * TC_PW;
+            const int hh = p0 - 1 + rr, ww = q0 - 1 + px;
+            const bool ok = i < TC_ENTRIES && px < TC_TW + 2 && hh >= 0 && hh < H && ww >= 0 && ww < W;
+            okv[u] = ok;
+            const int hs = ok ? hh : 0, ws = ok ? ww : 0;
             if (CIN > 0) {
-                float xin[CIN > 0 ? CIN : 1];
-                const float* xp = prm.raw + (((long long)b * H + hh) * W + ww) * CIN;
+                const float* xp = prm.raw + (((long long)b * H + hs) * W + ws) * CIN;
 #pragma unroll
-                for (int c = 0; c < CIN; ++c) xin[c] = __ldg(xp + c);
+                for (int c = 0; c < CIN; ++c) xin[u][c] = ok ? __ldg(xp + c) : 0.0f;
+                if (prm.coarse) {
+                    const int hc = nearest_src(hs, prm.Hc, H), wc = nearest_src(ws, prm.Wc, W);
+                    const float4* cp = reinterpret_cast<const float4*>(prm.coarse + (((long long)b * prm.Hc + hc) * prm.Wc + wc) * FC);
+#pragma unroll
+                    for (int c4 = 0; c4 < 4; ++c4) cf[u][c4] = ok ? __ldg(cp + c4) : make_float4(0.f, 0.f, 0.f, 0.f);
+                } else {
+#pragma unroll
+                    for (int c4 = 0; c4 < 4; ++c4) cf[u][c4] = make_float4(0.f, 0.f, 0.f, 0.f);
+                }
+            } else {
+                const float4* ip = reinterpret_cast<const float4*>(prm.inner + (((long long)b * H + hs) * W + ws) * FC);
+#pragma unroll
+                for (int c4 = 0; c4 < 4; ++c4) cf[u][c4] = ok ? __ldg(ip + c4) : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < TC_BATCH; ++u) {
+            const int i = base + u * TC_THREADS;
+            if (i >= TC_ENTRIES) continue;
+            const int rr = i / TC_PW, px = i - rr * TC_PW;
+            float v[FC];
+#pragma unroll
+            for (int c4 = 0; c4 < 4; ++c4) {
+                v[4 * c4] = cf[u][c4].x; v[4 * c4 + 1] = cf[u][c4].y; v[4 * c4 + 2] = cf[u][c4].z; v[4 * c4 + 3] = cf[u][c4].w;
+            }
+            if (CIN > 0 && okv[u]) {
 #pragma unroll
                 for (int o = 0; o < FC; ++o) {
                     float a = s_lat[FC * CIN + o];
 #pragma unroll
-                    for (int c = 0; c < CIN; ++c) a = fmaf(s_lat[o * CIN + c], xin[c], a);
-                    v[o] = a;
-                }
-                if (prm.coarse) {
-                    const int hc = nearest_src(hh, prm.Hc, H), wc = nearest_src(ww, prm.Wc, W);
-                    const float4* cp = reinterpret_cast<const float4*>(prm.coarse + (((long long)b * prm.Hc + hc) * prm.Wc + wc) * FC);
-#pragma unroll
-                    for (int c4 = 0; c4 < 4; ++c4) {
-                        const float4 f = __ldg(cp + c4);
-                        v[4 * c4] += f.x; v[4 * c4 + 1] += f.y; v[4 * c4 + 2] += f.z; v[4 * c4 + 3] += f.w;
-                    }
-                }
-            } else {
-                const float4* ip = reinterpret_cast<const float4*>(prm.inner + (((long long)b * H + hh) * W + ww) * FC);
-#pragma unroll
-                for (int c4 = 0; c4 < 4; ++c4) {
-                    const float4 f = __ldg(ip + c4);
-                    v[4 * c4] = f.x; v[4 * c4 + 1] = f.y; v[4 * c4 + 2] = f.z; v[4 * c4 + 3] = f.w;
+                    for (int c = 0; c < CIN; ++c) a = fmaf(s_lat[o * CIN + c], xin[u][c], a);
+                    v[o] += a;
                 }
             }
-        }
+            uint4 pk[2];
+            uint32_t* pw = reinterpret_cast<uint32_t*>(pk);
 #pragma unroll
-        for (int half = 0; half < 2; ++half) {
-            uint4 pk;
-            __half2* ph = reinterpret_cast<__half2*>(&pk);
-#pragma unroll
-            for (int t = 0; t < 4; ++t)
-                ph[t] = __floats2half2_rn(fminf(fmaxf(v[half * 8 + 2 * t], -65504.f), 65504.f),
-                                          fminf(fmaxf(v[half * 8 + 2 * t + 1], -65504.f), 65504.f));
-            *reinterpret_cast<uint4*>(s_a + rr * TC_ROWB + half * TC_PLANE + px * 16) = pk;
+            for (int t = 0; t < 8; ++t) asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(pw[t]) : "f"(v[2 * t + 1]), "f"(v[2 * t]));
+            *reinterpret_cast<uint4*>(s_a + rr * TC_ROWB + px * 16) = pk[0];
+            *reinterpret_cast<uint4*>(s_a + rr * TC_ROWB + TC_PLANE + px * 16) = pk[1];
         }
     }
     tc::fence_proxy_async();                 // generic-proxy smem writes -> visible to the tensor core (async proxy)
@@ -501,19 +514,34 @@ stem_tc_kernel(const float* __restrict__ x, const uint4* __restrict__ w_packed, 
     for (int i = tid; i < ST_B_BYTES / 16; i += ST_THREADS) reinterpret_cast<uint4*>(s_b)[i] = __ldg(w_packed + i);
     // input tile: rows 2*p0-3 .. 2*p0-3+ST_ROWS-1, columns 2*q0-3 .. (+2*ST_PLANE_ENTRIES-1), even/odd planes
     const int h_base = 2 * p0 - 3, w_base = 2 * q0 - 3;
-    for (int i = tid; i < ST_ROWS * 2 * ST_PLANE_ENTRIES; i += ST_THREADS) {
-        const int rr = i / (2 * ST_PLANE_ENTRIES);
-        const int xl = i - rr * (2 * ST_PLANE_ENTRIES);          // local column
-        const int hh = h_base + rr, ww = w_base + xl;
-        uint4 pk = make_uint4(0, 0, 0, 0);
-        if (hh >= 0 && hh < H && ww >= 0 && ww < W) {
-            const float* xp = x + (((long long)b * H + hh) * W + ww) * CIN;
-            __align__(16) __half hv[8];
+    // (batches of ST_BATCH entries per thread: all global loads of a batch are issued before any is converted)
+    constexpr int ST_ENTRIES = ST_ROWS * 2 * ST_PLANE_ENTRIES;
+    constexpr int ST_BATCH = 7;
+    for (int base = tid; base < ST_ENTRIES; base += ST_BATCH * ST_THREADS) {
+        float v[ST_BATCH][CIN];
 #pragma unroll
-            for (int c = 0; c < 8; ++c) hv[c] = __float2half_rn(c < CIN ? __ldg(xp + (c < CIN ? c : 0)) : 0.0f);
-            pk = *reinterpret_cast<uint4*>(hv);
+        for (int u = 0; u < ST_BATCH; ++u) {
+            const int i = base + u * ST_THREADS;
+            const int rr = i / (2 * ST_PLANE_ENTRIES);
+            const int xl = i - rr * (2 * ST_PLANE_ENTRIES);      // local column
+            const int hh = h_base + rr, ww = w_base + xl;
+            const bool ok = i < ST_ENTRIES && hh >= 0 && hh < H && ww >= 0 && ww < W;
+            const float* xp = x + (((long long)b * H + (ok ? hh : 0)) * W + (ok ? ww : 0)) * CIN;
+#pragma unroll
+            for (int c = 0; c < CIN; ++c) v[u][c] = ok ? __ldg(xp + c) : 0.0f;
         }
-        *reinterpret_cast<uint4*>(s_a + rr * ST_ROWB + (xl & 1) * ST_PLANE + (xl >> 1) * 16) = pk;
+#pragma unroll
+        for (int u = 0; u < ST_BATCH; ++u) {
+            const int i = base + u * ST_THREADS;
+            if (i < ST_ENTRIES) {
+                const int rr = i / (2 * ST_PLANE_ENTRIES);
+                const int xl = i - rr * (2 * ST_PLANE_ENTRIES);
+                __align__(16) __half hv[8];
+#pragma unroll
+                for (int c = 0; c < 8; ++c) hv[c] = __float2half_rn(c < CIN ? v[u][c < CIN ? c : 0] : 0.0f);
+                *reinterpret_cast<uint4*>(s_a + rr * ST_ROWB + (xl & 1) * ST_PLANE + (xl >> 1) * 16) = *reinterpret_cast<uint4*>(hv);
+            }
+        }
     }
     tc::fence_proxy_async();
     tc::tcgen05_fence_before();
