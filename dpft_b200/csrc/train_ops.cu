@@ -1,0 +1,538 @@
+// Training-mode companions of the tcgen05 convolutions (sm_100a): BatchNorm with batch statistics (forward and backward),
+// ReLU / residual add folded into the normalisation passes, max-pool backward, zero insertion for strided data gradients
+// and the per-step weight re-layout.  All NHWC, 16-bit activations (bf16 or f16), fp32 statistics; every kernel is a
+// streaming pass bound by HBM bandwidth: 16-byte accesses, one thread owns 8 channels of a pixel and keeps its
+// per-channel constants in registers across a grid-stride loop.
+//
+// Reference semantics: torchvision Bottleneck blocks in train() (src/dprt/models/backbones/resnet.py:54-55,101;
+// norm_layer BatchNorm2d, config/kradar.json:86) under autograd (src/dprt/training/trainer.py:125-133).
+#include "common.cuh"
+
+namespace dpft {
+namespace {
+
+constexpr int TB = 256;
+
+template <bool F16> struct H2;
+template <> struct H2<true> {
+    static __device__ __forceinline__ float2 unpack(uint32_t w) { return __half22float2(*reinterpret_cast<const __half2*>(&w)); }
+    static __device__ __forceinline__ uint32_t pack(float a, float b) {
+        uint32_t o;
+        asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(o) : "f"(b), "f"(a));
+        return o;
+    }
+};
+template <> struct H2<false> {
+    static __device__ __forceinline__ float2 unpack(uint32_t w) { return __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w)); }
+    static __device__ __forceinline__ uint32_t pack(float a, float b) {
+        uint32_t o;
+        asm("cvt.rn.satfinite.bf16x2.f32 %0, %1, %2;" : "=r"(o) : "f"(b), "f"(a));
+        return o;
+    }
+};
+
+template <bool F16> __device__ __forceinline__ void unpack8(const uint4& r, float* f) {
+    const uint32_t* w = reinterpret_cast<const uint32_t*>(&r);
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+        const float2 v = H2<F16>::unpack(w[t]);
+        f[2 * t] = v.x;
+        f[2 * t + 1] = v.y;
+    }
+}
+template <bool F16> __device__ __forceinline__ uint4 pack8(const float* f) {
+    uint4 r;
+    uint32_t* w = reinterpret_cast<uint32_t*>(&r);
+#pragma unroll
+    for (int t = 0; t < 4; ++t) w[t] = H2<F16>::pack(f[2 * t], f[2 * t + 1]);
+    return r;
+}
+
+__device__ __forceinline__ uint4 ld_stream(const void* p) {
+    uint4 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
+    return r;
+}
+
+// Block-level reduction of per-thread partial sums that belong to channel group (threadIdx.x % groups): NV values per thread.
+// Result is added to global memory by the first `groups` threads.
+template <int NV>
+__device__ __forceinline__ void block_reduce_to_global(const float (&v)[NV], int groups, float* const* dst, int c0) {
+    __shared__ float red[TB][NV + 1];
+#pragma unroll
+    for (int k = 0; k < NV; ++k) red[threadIdx.x][k] = v[k];
+    __syncthreads();
+    if ((int)threadIdx.x < groups) {
+        float acc[NV];
+#pragma unroll
+        for (int k = 0; k < NV; ++k) acc[k] = 0.0f;
+        for (int t = threadIdx.x; t < TB; t += groups) {
+#pragma unroll
+            for (int k = 0; k < NV; ++k) acc[k] += red[t][k];
+        }
+#pragma unroll
+        for (int k = 0; k < NV; ++k) atomicAdd(dst[k / 8] + c0 + (k % 8), acc[k]);
+    }
+}
+
+// ---- BatchNorm forward ---------------------------------------------------------------------------------------------
+// pass 1: per-channel sum and sum of squares of y (M, C)
+template <bool F16>
+__global__ void __launch_bounds__(TB) bn_stats_kernel(const uint4* __restrict__ y, float* __restrict__ sum, float* __restrict__ sumsq,
+                                                      long long nvec, int groups) {
+    float acc[16];
+#pragma unroll
+    for (int k = 0; k < 16; ++k) acc[k] = 0.0f;
+    const long long stride = (long long)gridDim.x * TB;
+    long long i = (long long)blockIdx.x * TB + threadIdx.x;
+    for (; i + 3 * stride < nvec; i += 4 * stride) {          // four independent 16-byte loads in flight per thread
+        uint4 r[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) r[u] = ld_stream(y + i + u * stride);
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            float f[8];
+            unpack8<F16>(r[u], f);
+#pragma unroll
+            for (int k = 0; k < 8; ++k) { acc[k] += f[k]; acc[8 + k] = fmaf(f[k], f[k], acc[8 + k]); }
+        }
+    }
+    for (; i < nvec; i += stride) {
+        float f[8];
+        unpack8<F16>(ld_stream(y + i), f);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) { acc[k] += f[k]; acc[8 + k] = fmaf(f[k], f[k], acc[8 + k]); }
+    }
+    float* dst[2] = {sum, sumsq};
+    block_reduce_to_global<16>(acc, groups, dst, (threadIdx.x % groups) * 8);
+}
+
+// pass 2 (C threads): batch mean / inverse std, the affine form used by the apply pass, and the running statistics
+// (momentum update with the unbiased variance, torch.nn.BatchNorm2d semantics).
+__global__ void bn_finalize_kernel(const float* __restrict__ sum, const float* __restrict__ sumsq, const float* __restrict__ gamma,
+                                   const float* __restrict__ beta, float* running_mean, float* running_var, float momentum, float eps,
+                                   float count, int C, float* __restrict__ scale, float* __restrict__ shift, float* __restrict__ mean_out,
+                                   float* __restrict__ invstd_out) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= C) return;
+    const float mean = sum[c] / count;
+    const float var = fmaxf(sumsq[c] / count - mean * mean, 0.0f);
+    const float invstd = rsqrtf(var + eps);
+    const float g = gamma ? gamma[c] : 1.0f, b = beta ? beta[c] : 0.0f;
+    scale[c] = g * invstd;
+    shift[c] = b - mean * g * invstd;
+    mean_out[c] = mean;
+    invstd_out[c] = invstd;
+    if (running_mean) running_mean[c] = (1.0f - momentum) * running_mean[c] + momentum * mean;
+    if (running_var) running_var[c] = (1.0f - momentum) * running_var[c] + momentum * var * (count > 1.0f ? count / (count - 1.0f) : 1.0f);
+}
+
+// pass 3: z = act(y * scale + shift (+ residual))
+template <bool F16>
+__global__ void __launch_bounds__(TB) bn_apply_kernel(const uint4* __restrict__ y, const float* __restrict__ scale,
+                                                      const float* __restrict__ shift, const uint4* __restrict__ residual,
+                                                      uint4* __restrict__ z, long long nvec, int groups, int relu) {
+    const int c0 = (threadIdx.x % groups) * 8;
+    float sc[8], sh[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) { sc[k] = scale[c0 + k]; sh[k] = shift[c0 + k]; }
+    const long long stride = (long long)gridDim.x * TB;
+    for (long long i = (long long)blockIdx.x * TB + threadIdx.x; i < nvec; i += 2 * stride) {
+        const bool two = i + stride < nvec;
+        uint4 ry[2], rr[2];
+        ry[0] = ld_stream(y + i);
+        if (two) ry[1] = ld_stream(y + i + stride);
+        if (residual) {
+            rr[0] = ld_stream(residual + i);
+            if (two) rr[1] = ld_stream(residual + i + stride);
+        }
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+            if (u == 1 && !two) break;
+            float f[8];
+            unpack8<F16>(ry[u], f);
+#pragma unroll
+            for (int k = 0; k < 8; ++k) f[k] = fmaf(f[k], sc[k], sh[k]);
+            if (residual) {
+                float g[8];
+                unpack8<F16>(rr[u], g);
+#pragma unroll
+                for (int k = 0; k < 8; ++k) f[k] += g[k];
+            }
+            if (relu) {
+#pragma unroll
+                for (int k = 0; k < 8; ++k) f[k] = fmaxf(f[k], 0.0f);
+            }
+            z[i + u * stride] = pack8<F16>(f);
+        }
+    }
+}
+
+// ---- BatchNorm backward --------------------------------------------------------------------------------------------
+// pass 1: g = dz * [z > 0] (ReLU mask when relu), sum_g[c] = sum g, sum_gx[c] = sum g * xhat, xhat = (y - mean) * invstd
+template <bool F16>
+__global__ void __launch_bounds__(TB) bn_bwd_reduce_kernel(const uint4* __restrict__ dz, const uint4* __restrict__ z,
+                                                           const uint4* __restrict__ y, const float* __restrict__ mean,
+                                                           const float* __restrict__ invstd, float* __restrict__ sum_g,
+                                                           float* __restrict__ sum_gx, long long nvec, int groups, int relu) {
+    const int c0 = (threadIdx.x % groups) * 8;
+    float mu[8], is[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) { mu[k] = mean[c0 + k]; is[k] = invstd[c0 + k]; }
+    float acc[16];
+#pragma unroll
+    for (int k = 0; k < 16; ++k) acc[k] = 0.0f;
+    const long long stride = (long long)gridDim.x * TB;
+    for (long long i = (long long)blockIdx.x * TB + threadIdx.x; i < nvec; i += 2 * stride) {
+        const bool two = i + stride < nvec;
+        uint4 rd[2], rz[2], ry[2];
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+            if (u == 1 && !two) break;
+            rd[u] = ld_stream(dz + i + u * stride);
+            ry[u] = ld_stream(y + i + u * stride);
+            if (relu) rz[u] = ld_stream(z + i + u * stride);
+        }
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+            if (u == 1 && !two) break;
+            float g[8], fy[8];
+            unpack8<F16>(rd[u], g);
+            unpack8<F16>(ry[u], fy);
+            if (relu) {
+                float fz[8];
+                unpack8<F16>(rz[u], fz);
+#pragma unroll
+                for (int k = 0; k < 8; ++k) g[k] = fz[k] > 0.0f ? g[k] : 0.0f;
+            }
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                acc[k] += g[k];
+                acc[8 + k] = fmaf(g[k], (fy[k] - mu[k]) * is[k], acc[8 + k]);
+            }
+        }
+    }
+    float* dst[2] = {sum_g, sum_gx};
+    block_reduce_to_global<16>(acc, groups, dst, c0);
+}
+
+// pass 2: dy = gamma * invstd * (g - sum_g / M - xhat * sum_gx / M); optionally stores g (the gradient that flows into
+// the block's identity branch); block 0 adds dgamma = sum_gx, dbeta = sum_g into the fp32 parameter gradients.
+template <bool F16>
+__global__ void __launch_bounds__(TB) bn_bwd_apply_kernel(const uint4* __restrict__ dz, const uint4* __restrict__ z,
+                                                          const uint4* __restrict__ y, const float* __restrict__ mean,
+                                                          const float* __restrict__ invstd, const float* __restrict__ gamma,
+                                                          const float* __restrict__ sum_g, const float* __restrict__ sum_gx,
+                                                          uint4* __restrict__ dy, uint4* __restrict__ g_out, float* dgamma,
+                                                          float* dbeta, float inv_count, long long nvec, int groups, int relu, int C) {
+    if (blockIdx.x == 0) {
+        for (int c = threadIdx.x; c < C; c += TB) {
+            if (dgamma) dgamma[c] += sum_gx[c];
+            if (dbeta) dbeta[c] += sum_g[c];
+        }
+    }
+    const int c0 = (threadIdx.x % groups) * 8;
+    float mu[8], is[8], k1[8], k2[8], k3[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        mu[k] = mean[c0 + k];
+        is[k] = invstd[c0 + k];
+        const float gi = (gamma ? gamma[c0 + k] : 1.0f) * is[k];
+        k1[k] = gi;                                          // dy = k1 * g - k2 - xhat * k3
+        k2[k] = gi * sum_g[c0 + k] * inv_count;
+        k3[k] = gi * sum_gx[c0 + k] * inv_count;
+    }
+    const long long stride = (long long)gridDim.x * TB;
+    for (long long i = (long long)blockIdx.x * TB + threadIdx.x; i < nvec; i += 2 * stride) {
+        const bool two = i + stride < nvec;
+        uint4 rd[2], rz[2], ry[2];
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+            if (u == 1 && !two) break;
+            rd[u] = ld_stream(dz + i + u * stride);
+            ry[u] = ld_stream(y + i + u * stride);
+            if (relu) rz[u] = ld_stream(z + i + u * stride);
+        }
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+            if (u == 1 && !two) break;
+            float g[8], fy[8];
+            unpack8<F16>(rd[u], g);
+            unpack8<F16>(ry[u], fy);
+            if (relu) {
+                float fz[8];
+                unpack8<F16>(rz[u], fz);
+#pragma unroll
+                for (int k = 0; k < 8; ++k) g[k] = fz[k] > 0.0f ? g[k] : 0.0f;
+            }
+            if (g_out) g_out[i + u * stride] = pack8<F16>(g);
+            float o[8];
+#pragma unroll
+            for (int k = 0; k < 8; ++k) o[k] = fmaf(k1[k], g[k], -k2[k]) - (fy[k] - mu[k]) * is[k] * k3[k];
+            dy[i + u * stride] = pack8<F16>(o);
+        }
+    }
+}
+
+// ---- max-pool 3x3 / stride 2 / pad 1 backward (torch semantics: the whole gradient goes to the first maximum in scan order) ----
+template <bool F16>
+__global__ void __launch_bounds__(TB) maxpool_bwd_kernel(const uint4* __restrict__ x, const uint4* __restrict__ dy, uint4* __restrict__ dx,
+                                                         int B, int H, int W, int CG, int P, int Q) {
+    const long long total = (long long)B * H * W * CG;
+    for (long long i = (long long)blockIdx.x * TB + threadIdx.x; i < total; i += (long long)gridDim.x * TB) {
+        const int cg = (int)(i % CG);
+        long long t = i / CG;
+        const int w = (int)(t % W);
+        t /= W;
+        const int h = (int)(t % H);
+        const int b = (int)(t / H);
+        float own[8], acc[8];
+        unpack8<F16>(__ldg(x + i), own);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) acc[k] = 0.0f;
+        // windows (p, q) that contain (h, w): 2p - 1 <= h <= 2p + 1
+        const int p_lo = max((h - 1 + 1) / 2, 0), p_hi = min((h + 1) / 2, P - 1);
+        const int q_lo = max((w - 1 + 1) / 2, 0), q_hi = min((w + 1) / 2, Q - 1);
+        for (int p = p_lo; p <= p_hi; ++p) {
+            for (int q = q_lo; q <= q_hi; ++q) {
+                // first maximum of the window in (row, column) scan order; position index of (h, w) in that order
+                float best[8];
+                int best_pos[8];
+#pragma unroll
+                for (int k = 0; k < 8; ++k) { best[k] = -INFINITY; best_pos[k] = -1; }
+                int my_pos = -1;
+                for (int r = 0; r < 3; ++r) {
+                    const int hh = 2 * p - 1 + r;
+                    if (hh < 0 || hh >= H) continue;
+                    for (int s = 0; s < 3; ++s) {
+                        const int ww = 2 * q - 1 + s;
+                        if (ww < 0 || ww >= W) continue;
+                        const int pos = r * 3 + s;
+                        if (hh == h && ww == w) my_pos = pos;
+                        float v[8];
+                        unpack8<F16>(__ldg(x + (((long long)b * H + hh) * W + ww) * CG + cg), v);
+#pragma unroll
+                        for (int k = 0; k < 8; ++k) {
+                            if (v[k] > best[k] || best_pos[k] < 0) { best[k] = v[k]; best_pos[k] = pos; }
+                        }
+                    }
+                }
+                float g[8];
+                unpack8<F16>(__ldg(dy + (((long long)b * P + p) * Q + q) * CG + cg), g);
+#pragma unroll
+                for (int k = 0; k < 8; ++k) acc[k] += (best_pos[k] == my_pos) ? g[k] : 0.0f;
+            }
+        }
+        (void)own;
+        dx[i] = pack8<F16>(acc);
+    }
+}
+
+// ---- zero insertion: up[b, 2p, 2q, :] = src[b, p, q, :], everything else 0 (data gradient of stride-2 convolutions) ----
+__global__ void __launch_bounds__(TB) zero_insert2_kernel(const uint4* __restrict__ src, uint4* __restrict__ up, int B, int H, int W,
+                                                          int CG, int P, int Q) {
+    const long long total = (long long)B * H * W * CG;
+    for (long long i = (long long)blockIdx.x * TB + threadIdx.x; i < total; i += (long long)gridDim.x * TB) {
+        const int cg = (int)(i % CG);
+        long long t = i / CG;
+        const int w = (int)(t % W);
+        t /= W;
+        const int h = (int)(t % H);
+        const int b = (int)(t / H);
+        uint4 v = make_uint4(0, 0, 0, 0);
+        if (!(h & 1) && !(w & 1) && (h >> 1) < P && (w >> 1) < Q) v = __ldg(src + (((long long)b * P + (h >> 1)) * Q + (w >> 1)) * CG + cg);
+        up[i] = v;
+    }
+}
+
+// ---- per-step weight re-layout: fp32 master (Cout, Cin, R, S) -> 16-bit forward operand (Cout, R, S, Cin) and the
+// data-gradient operand (Cin, R, S, Cout) with the taps flipped (dX = conv(dY, flip(W)^T)) ----
+struct PackEntry {
+    const float* src;
+    void* fwd;
+    void* dgrad;         // may be null
+    int Cout, Cin, R, S;
+    long long offset;    // first element of this layer in the concatenated index space
+};
+
+template <bool F16>
+__global__ void __launch_bounds__(TB) pack_weights_kernel(const PackEntry* __restrict__ table, int n_layers, long long total) {
+    for (long long i = (long long)blockIdx.x * TB + threadIdx.x; i < total; i += (long long)gridDim.x * TB) {
+        int lo = 0, hi = n_layers - 1;                       // last entry with offset <= i
+        while (lo < hi) {
+            const int mid = (lo + hi + 1) >> 1;
+            if (table[mid].offset <= i) lo = mid; else hi = mid - 1;
+        }
+        const PackEntry e = table[lo];
+        long long j = i - e.offset;                          // index in (Cout, R, S, Cin) order
+        const int ci = (int)(j % e.Cin);
+        j /= e.Cin;
+        const int s = (int)(j % e.S);
+        j /= e.S;
+        const int r = (int)(j % e.R);
+        const int co = (int)(j / e.R);
+        const float v = __ldg(e.src + (((long long)co * e.Cin + ci) * e.R + r) * e.S + s);
+        if (F16) {
+            const __half hv = __float2half_rn(v);
+            reinterpret_cast<__half*>(e.fwd)[i - e.offset] = hv;
+            if (e.dgrad) reinterpret_cast<__half*>(e.dgrad)[(((long long)ci * e.R + (e.R - 1 - r)) * e.S + (e.S - 1 - s)) * e.Cout + co] = hv;
+        } else {
+            const __nv_bfloat16 hv = __float2bfloat16_rn(v);
+            reinterpret_cast<__nv_bfloat16*>(e.fwd)[i - e.offset] = hv;
+            if (e.dgrad) reinterpret_cast<__nv_bfloat16*>(e.dgrad)[(((long long)ci * e.R + (e.R - 1 - r)) * e.S + (e.S - 1 - s)) * e.Cout + co] = hv;
+        }
+    }
+}
+
+// fp32 gradient in the kernel's (Cout, R, S, Cin) layout -> added into the parameter's (Cout, Cin, R, S) gradient
+__global__ void __launch_bounds__(TB) unpack_wgrad_kernel(const PackEntry* __restrict__ table, int n_layers, long long total) {
+    for (long long i = (long long)blockIdx.x * TB + threadIdx.x; i < total; i += (long long)gridDim.x * TB) {
+        int lo = 0, hi = n_layers - 1;
+        while (lo < hi) {
+            const int mid = (lo + hi + 1) >> 1;
+            if (table[mid].offset <= i) lo = mid; else hi = mid - 1;
+        }
+        const PackEntry e = table[lo];
+        long long j = i - e.offset;                          // index in the parameter's (Cout, Cin, R, S) order
+        const int s = (int)(j % e.S);
+        j /= e.S;
+        const int r = (int)(j % e.R);
+        j /= e.R;
+        const int ci = (int)(j % e.Cin);
+        const int co = (int)(j / e.Cin);
+        const float g = __ldg(e.src + (((long long)co * e.R + r) * e.S + s) * e.Cin + ci);
+        reinterpret_cast<float*>(e.fwd)[i - e.offset] += g;
+    }
+}
+
+int grid_for(long long n, int sms) {
+    long long blocks = (n + TB - 1) / TB;
+    const long long cap = (long long)sms * 8;
+    if (blocks > cap) blocks = cap;
+    if (blocks < 1) blocks = 1;
+    return (int)blocks;
+}
+
+int sm_count() {
+    static int n = 0;
+    if (!n) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+        if (n <= 0) n = 148;
+    }
+    return n;
+}
+
+}  // namespace
+}  // namespace dpft
+
+using namespace dpft;
+
+#define DPFT_REQUIRE_16BIT(what)                                                                    \
+    DPFT_REQUIRE(dtype == DPFT_BF16 || dtype == DPFT_F16, what ": dtype must be DPFT_BF16 or DPFT_F16"); \
+    const bool is_f16 = dtype == DPFT_F16
+
+static inline bool channels_ok(int C) { return C >= 8 && C % 8 == 0 && C / 8 <= TB && TB % (C / 8) == 0; }
+
+extern "C" int dpft_bn_stats(const void* y, float* sum, float* sumsq, long long M, int C, int dtype, void* stream) {
+    DPFT_REQUIRE_16BIT("bn_stats");
+    DPFT_REQUIRE(y && sum && sumsq && M > 0, "bn_stats: null pointer or empty input");
+    DPFT_REQUIRE(channels_ok(C), "bn_stats: C=%d must be a multiple of 8 with 256 %% (C/8) == 0", C);
+    const long long nvec = M * (C / 8);
+    const int grid = grid_for((nvec + 3) / 4, sm_count());
+    if (is_f16) bn_stats_kernel<true><<<grid, TB, 0, (cudaStream_t)stream>>>((const uint4*)y, sum, sumsq, nvec, C / 8);
+    else bn_stats_kernel<false><<<grid, TB, 0, (cudaStream_t)stream>>>((const uint4*)y, sum, sumsq, nvec, C / 8);
+    DPFT_LAUNCH_CHECK("bn_stats_kernel");
+    return DPFT_OK;
+}
+
+extern "C" int dpft_bn_finalize(const float* sum, const float* sumsq, const float* gamma, const float* beta, float* running_mean,
+                                float* running_var, float momentum, float eps, long long M, int C, float* scale, float* shift,
+                                float* mean, float* invstd, void* stream) {
+    DPFT_REQUIRE(sum && sumsq && scale && shift && mean && invstd && M > 0 && C > 0, "bn_finalize: null pointer or empty input");
+    bn_finalize_kernel<<<(C + 127) / 128, 128, 0, (cudaStream_t)stream>>>(sum, sumsq, gamma, beta, running_mean, running_var, momentum,
+                                                                          eps, (float)M, C, scale, shift, mean, invstd);
+    DPFT_LAUNCH_CHECK("bn_finalize_kernel");
+    return DPFT_OK;
+}
+
+extern "C" int dpft_bn_apply(const void* y, const float* scale, const float* shift, const void* residual, void* z, long long M, int C,
+                             int relu, int dtype, void* stream) {
+    DPFT_REQUIRE_16BIT("bn_apply");
+    DPFT_REQUIRE(y && scale && shift && z && M > 0, "bn_apply: null pointer or empty input");
+    DPFT_REQUIRE(channels_ok(C), "bn_apply: C=%d must be a multiple of 8 with 256 %% (C/8) == 0", C);
+    const long long nvec = M * (C / 8);
+    const int grid = grid_for((nvec + 1) / 2, sm_count());
+    if (is_f16) bn_apply_kernel<true><<<grid, TB, 0, (cudaStream_t)stream>>>((const uint4*)y, scale, shift, (const uint4*)residual, (uint4*)z, nvec, C / 8, relu);
+    else bn_apply_kernel<false><<<grid, TB, 0, (cudaStream_t)stream>>>((const uint4*)y, scale, shift, (const uint4*)residual, (uint4*)z, nvec, C / 8, relu);
+    DPFT_LAUNCH_CHECK("bn_apply_kernel");
+    return DPFT_OK;
+}
+
+extern "C" int dpft_bn_backward_reduce(const void* dz, const void* z, const void* y, const float* mean, const float* invstd,
+                                       float* sum_g, float* sum_gx, long long M, int C, int relu, int dtype, void* stream) {
+    DPFT_REQUIRE_16BIT("bn_backward_reduce");
+    DPFT_REQUIRE(dz && y && mean && invstd && sum_g && sum_gx && M > 0 && (!relu || z), "bn_backward_reduce: null pointer or empty input");
+    DPFT_REQUIRE(channels_ok(C), "bn_backward_reduce: C=%d must be a multiple of 8 with 256 %% (C/8) == 0", C);
+    const long long nvec = M * (C / 8);
+    const int grid = grid_for((nvec + 1) / 2, sm_count());
+    if (is_f16) bn_bwd_reduce_kernel<true><<<grid, TB, 0, (cudaStream_t)stream>>>((const uint4*)dz, (const uint4*)z, (const uint4*)y, mean, invstd, sum_g, sum_gx, nvec, C / 8, relu);
+    else bn_bwd_reduce_kernel<false><<<grid, TB, 0, (cudaStream_t)stream>>>((const uint4*)dz, (const uint4*)z, (const uint4*)y, mean, invstd, sum_g, sum_gx, nvec, C / 8, relu);
+    DPFT_LAUNCH_CHECK("bn_bwd_reduce_kernel");
+    return DPFT_OK;
+}
+
+extern "C" int dpft_bn_backward_apply(const void* dz, const void* z, const void* y, const float* mean, const float* invstd,
+                                      const float* gamma, const float* sum_g, const float* sum_gx, void* dy, void* g_out,
+                                      float* dgamma, float* dbeta, long long M, int C, int relu, int dtype, void* stream) {
+    DPFT_REQUIRE_16BIT("bn_backward_apply");
+    DPFT_REQUIRE(dz && y && mean && invstd && sum_g && sum_gx && dy && M > 0 && (!relu || z), "bn_backward_apply: null pointer or empty input");
+    DPFT_REQUIRE(channels_ok(C), "bn_backward_apply: C=%d must be a multiple of 8 with 256 %% (C/8) == 0", C);
+    const long long nvec = M * (C / 8);
+    const int grid = grid_for((nvec + 1) / 2, sm_count());
+    const float inv = 1.0f / (float)M;
+    if (is_f16) bn_bwd_apply_kernel<true><<<grid, TB, 0, (cudaStream_t)stream>>>((const uint4*)dz, (const uint4*)z, (const uint4*)y, mean, invstd, gamma, sum_g, sum_gx, (uint4*)dy, (uint4*)g_out, dgamma, dbeta, inv, nvec, C / 8, relu, C);
+    else bn_bwd_apply_kernel<false><<<grid, TB, 0, (cudaStream_t)stream>>>((const uint4*)dz, (const uint4*)z, (const uint4*)y, mean, invstd, gamma, sum_g, sum_gx, (uint4*)dy, (uint4*)g_out, dgamma, dbeta, inv, nvec, C / 8, relu, C);
+    DPFT_LAUNCH_CHECK("bn_bwd_apply_kernel");
+    return DPFT_OK;
+}
+
+extern "C" int dpft_maxpool3x3s2_backward(const void* x, const void* dy, void* dx, int B, int H, int W, int C, int dtype, void* stream) {
+    DPFT_REQUIRE_16BIT("maxpool_backward");
+    DPFT_REQUIRE(x && dy && dx && B > 0 && H > 0 && W > 0 && C % 8 == 0, "maxpool_backward: bad arguments");
+    const int P = (H - 1) / 2 + 1, Q = (W - 1) / 2 + 1;
+    const long long total = (long long)B * H * W * (C / 8);
+    const int grid = grid_for(total, sm_count());
+    if (is_f16) maxpool_bwd_kernel<true><<<grid, TB, 0, (cudaStream_t)stream>>>((const uint4*)x, (const uint4*)dy, (uint4*)dx, B, H, W, C / 8, P, Q);
+    else maxpool_bwd_kernel<false><<<grid, TB, 0, (cudaStream_t)stream>>>((const uint4*)x, (const uint4*)dy, (uint4*)dx, B, H, W, C / 8, P, Q);
+    DPFT_LAUNCH_CHECK("maxpool_bwd_kernel");
+    return DPFT_OK;
+}
+
+extern "C" int dpft_zero_insert2_nhwc(const void* src, void* up, int B, int H, int W, int C, int P, int Q, void* stream) {
+    DPFT_REQUIRE(src && up && B > 0 && H > 0 && W > 0 && C % 8 == 0 && P > 0 && Q > 0, "zero_insert2: bad arguments");
+    DPFT_REQUIRE(2 * (P - 1) < H && 2 * (Q - 1) < W, "zero_insert2: (P, Q) = (%d, %d) does not fit (H, W) = (%d, %d)", P, Q, H, W);
+    const long long total = (long long)B * H * W * (C / 8);
+    zero_insert2_kernel<<<grid_for(total, sm_count()), TB, 0, (cudaStream_t)stream>>>((const uint4*)src, (uint4*)up, B, H, W, C / 8, P, Q);
+    DPFT_LAUNCH_CHECK("zero_insert2_kernel");
+    return DPFT_OK;
+}
+
+extern "C" int dpft_pack_conv_weights(const void* table, int n_layers, long long total, int dtype, void* stream) {
+    DPFT_REQUIRE_16BIT("pack_conv_weights");
+    DPFT_REQUIRE(table && n_layers > 0 && total > 0, "pack_conv_weights: bad arguments");
+    static_assert(sizeof(PackEntry) == 48, "PackEntry layout is part of the ABI (dpft_pack_entry)");
+    const int grid = grid_for(total, sm_count());
+    if (is_f16) pack_weights_kernel<true><<<grid, TB, 0, (cudaStream_t)stream>>>((const PackEntry*)table, n_layers, total);
+    else pack_weights_kernel<false><<<grid, TB, 0, (cudaStream_t)stream>>>((const PackEntry*)table, n_layers, total);
+    DPFT_LAUNCH_CHECK("pack_weights_kernel");
+    return DPFT_OK;
+}
+
+extern "C" int dpft_unpack_conv_wgrads(const void* table, int n_layers, long long total, void* stream) {
+    DPFT_REQUIRE(table && n_layers > 0 && total > 0, "unpack_conv_wgrads: bad arguments");
+    unpack_wgrad_kernel<<<grid_for(total, sm_count()), TB, 0, (cudaStream_t)stream>>>((const PackEntry*)table, n_layers, total);
+    DPFT_LAUNCH_CHECK("unpack_wgrad_kernel");
+    return DPFT_OK;
+}

@@ -105,6 +105,9 @@ class Backbone(nn.Module):
         else:
             self.adjustment_layer = nn.Conv2d(in_channels, 3, 1, bias=False)
         self.body = ResNetBody(arch, multi_scale, _norm(norm_layer))
+        self.native_train = False             # train(): run layer1.. through the sm_100a training kernels (16-bit activations)
+        self.train_dtype = torch.bfloat16
+        self._stages = None
         if weights:
             self._load_weights(name, weights)
 
@@ -125,7 +128,41 @@ class Backbone(nn.Module):
     def from_config(cls, config: Dict[str, Any]):
         return cls(**config)
 
+    def __getstate__(self):            # torch.save(model) must not pickle the device-side launch plan
+        state = self.__dict__.copy()
+        state["_stages"] = None
+        return state
+
+    def _native_stages(self):
+        """The native training plan of layer1.. (dpft_b200/train_backbone.py), or None when it does not apply."""
+        from ..train_backbone import NativeStages
+        st = self._stages
+        if st is not None and st.device == self.body.conv1.weight.device and st.dtype == self.train_dtype:
+            return st
+        if NativeStages.ineligible_reason(self.body) is not None:
+            return None
+        self._stages = NativeStages(self.body, self.train_dtype)
+        return self._stages
+
+    def forward_native_train(self, batch: torch.Tensor, stages) -> "OrderedDict[str, torch.Tensor]":
+        """Stem through torch autograd, layer1.. as one native autograd node; same outputs as ``forward`` (fp32)."""
+        from ..train_backbone import stages_forward
+        x = batch.movedim(-1, 1) if self.channel_last else batch
+        body = self.body
+        x = F.relu(body.bn1(body.conv1(self.adjustment_layer(x))))
+        x = F.max_pool2d(x, kernel_size=3, stride=2, padding=1)
+        pooled = x.permute(0, 2, 3, 1).to(self.train_dtype).contiguous()
+        outs = stages_forward(stages, pooled)
+        feats = OrderedDict((str(i + 1), o.float()) for i, o in enumerate(outs))
+        if not self.channel_last:
+            feats = OrderedDict((k, v.movedim(-1, 1)) for k, v in feats.items())
+        return feats
+
     def forward(self, batch: torch.Tensor) -> "OrderedDict[str, torch.Tensor]":
+        if self.native_train and self.training and batch.is_cuda and torch.is_grad_enabled():
+            stages = self._native_stages()
+            if stages is not None:
+                return self.forward_native_train(batch, stages)
         x = batch.movedim(-1, 1) if self.channel_last else batch
         feats = self.body(self.adjustment_layer(x))
         if self.channel_last:

@@ -1,0 +1,205 @@
+"""Native (sm_100a) training path of the ResNet stages: forward with batch-statistics BatchNorm and the whole backward,
+as ONE autograd node per backbone.
+
+Replaces, under ``model.train()``, the cuDNN convolution / batch-norm / ReLU forward+backward launches autograd records for
+the torchvision Bottleneck blocks the reference trains (src/dprt/models/backbones/resnet.py:54-55,101; the backward is
+driven from src/dprt/training/trainer.py:125-133).  Activations and activation gradients are NHWC 16-bit (bf16 by
+default: gradients need the exponent range), accumulation and every parameter gradient fp32.
+
+Per block (x = block input, 16-bit):
+    y1 = conv1(x)            z1 = relu(bn1(y1))
+    y2 = conv2(z1)           z2 = relu(bn2(y2))
+    y3 = conv3(z2)           z3 = relu(bn3(y3) + idn)         idn = x  or  bn_d(conv_d(x))
+Kernels: ``dpft_conv2d_nhwc`` (tcgen05 implicit GEMM; also the data gradients, on flipped/transposed weights),
+``dpft_conv2d_wgrad`` (tcgen05 GEMM over the pixels), ``dpft_bn_*`` (streaming passes), ``dpft_zero_insert2_nhwc``,
+``dpft_pack_conv_weights`` (one launch per step re-lays out every weight after the optimiser update).
+"""
+from __future__ import annotations
+
+from typing import List, Optional, Tuple
+
+import torch
+from torch import nn
+
+from . import train_ops as T
+from .conv import conv2d_nhwc
+
+
+class _ConvSpec:
+    __slots__ = ("conv", "bn", "idx", "stride", "pad", "r", "cin", "cout", "bn_off")
+
+    def __init__(self, conv: nn.Conv2d, bn: nn.BatchNorm2d, idx: int, bn_off: int):
+        self.conv, self.bn, self.idx, self.bn_off = conv, bn, idx, bn_off
+        self.stride, self.pad, self.r = conv.stride[0], conv.padding[0], conv.kernel_size[0]
+        self.cout, self.cin = conv.weight.shape[0], conv.weight.shape[1]
+
+
+class NativeStages:
+    """Prepared launch sequence of ``body.layer1 .. layer<n>`` for training."""
+
+    @staticmethod
+    def ineligible_reason(body) -> Optional[str]:
+        for m in body.modules():
+            if isinstance(m, nn.Conv2d) and m is not body.conv1:
+                if m.bias is not None or m.groups != 1 or m.dilation[0] != 1 or m.weight.shape[0] % 64 or m.weight.shape[1] % 64:
+                    return "convolution outside the bottleneck family"
+        if not isinstance(body.bn1, nn.BatchNorm2d):
+            return "norm layer is not BatchNorm2d"
+        for m in body.modules():
+            if isinstance(m, nn.BatchNorm2d) and (m.momentum is None or not m.affine or not m.track_running_stats):
+                return "BatchNorm2d variant without momentum / affine / running statistics"
+        return None
+
+    def __init__(self, body, dtype: torch.dtype = torch.bfloat16):
+        self.dtype = dtype
+        self.blocks: List[Tuple[_ConvSpec, _ConvSpec, _ConvSpec, Optional[_ConvSpec]]] = []
+        self.stage_ends: List[int] = []
+        self.specs: List[_ConvSpec] = []
+        bn_off = 0
+
+        def spec(conv, bn):
+            nonlocal bn_off
+            s = _ConvSpec(conv, bn, len(self.specs), bn_off)
+            bn_off += s.cout
+            self.specs.append(s)
+            return s
+
+        for st in range(body.n_stages):
+            for blk in getattr(body, f"layer{st + 1}"):
+                ds = spec(blk.downsample[0], blk.downsample[1]) if blk.downsample is not None else None
+                self.blocks.append((spec(blk.conv1, blk.bn1), spec(blk.conv2, blk.bn2), spec(blk.conv3, blk.bn3), ds))
+            self.stage_ends.append(len(self.blocks) - 1)
+        self.bn_channels = bn_off
+        self.device = self.specs[0].conv.weight.device
+        self.packer = T.WeightPacker([s.conv.weight for s in self.specs], dtype, [True] * len(self.specs))
+        self.wgrad_offsets, o = [], 0
+        for s in self.specs:
+            self.wgrad_offsets.append(o)
+            o += s.conv.weight.numel()
+        self.wgrad_total = o
+        self.zero_bias = torch.zeros(4096, dtype=torch.float32, device=self.device)
+        self._packed_version = None
+
+    # parameters in the order the autograd node receives them / returns their gradients
+    def parameters(self) -> List[torch.Tensor]:
+        out = []
+        for s in self.specs:
+            out += [s.conv.weight, s.bn.weight, s.bn.bias]
+        return out
+
+    def _refresh_weights(self) -> None:
+        version = tuple(s.conv.weight._version for s in self.specs)
+        if version != self._packed_version or self.packer._ptrs != [w.data_ptr() for w in self.packer.weights]:
+            self.packer.refresh()
+            self._packed_version = version
+
+    # ---- forward ---------------------------------------------------------------------------------------------------
+    def _conv(self, s: _ConvSpec, x: torch.Tensor) -> torch.Tensor:
+        return conv2d_nhwc(x, self.packer.fwd[s.idx], self.zero_bias, s.stride, s.pad, False)
+
+    def _bn(self, s: _ConvSpec, y: torch.Tensor, states: torch.Tensor, relu: bool, residual=None):
+        bn = s.bn
+        buf = states[6 * s.bn_off: 6 * (s.bn_off + s.cout)].view(6, s.cout)
+        return T.bn_forward(y, bn.weight, bn.bias, bn.running_mean, bn.running_var, bn.momentum, bn.eps, relu, residual, buf)
+
+    def forward(self, x: torch.Tensor):
+        """x (B,H,W,64) 16-bit (the max-pooled stem output) -> (stage outputs, tape)."""
+        self._refresh_weights()
+        states = torch.zeros(6 * self.bn_channels, dtype=torch.float32, device=x.device)
+        tape = []
+        outs = []
+        for bi, (c1, c2, c3, ds) in enumerate(self.blocks):
+            y1 = self._conv(c1, x)
+            z1, s1 = self._bn(c1, y1, states, True)
+            y2 = self._conv(c2, z1)
+            z2, s2 = self._bn(c2, y2, states, True)
+            y3 = self._conv(c3, z2)
+            if ds is not None:
+                yd = self._conv(ds, x)
+                idn, sd = self._bn(ds, yd, states, False)
+            else:
+                yd, sd, idn = None, None, x
+            z3, s3 = self._bn(c3, y3, states, True, residual=idn)
+            tape.append((x, y1, z1, s1, y2, z2, s2, y3, z3, s3, yd, sd))
+            x = z3
+            if bi in self.stage_ends:
+                outs.append(z3)
+        nbt = [s.bn.num_batches_tracked for s in self.specs if s.bn.num_batches_tracked is not None]
+        if nbt:
+            torch._foreach_add_(nbt, 1)
+        return outs, tape
+
+    # ---- backward --------------------------------------------------------------------------------------------------
+    def backward(self, tape, grad_outs: List[Optional[torch.Tensor]]):
+        dev = self.device
+        wg = torch.zeros(self.wgrad_total, dtype=torch.float32, device=dev)
+        bng = torch.zeros(2 * self.bn_channels, dtype=torch.float32, device=dev)       # dgamma | dbeta
+        sums = torch.zeros(2 * self.bn_channels, dtype=torch.float32, device=dev)
+
+        def bn_bwd(s: _ConvSpec, dz, z, y, state, relu, want_g=False):
+            sm = sums[2 * s.bn_off: 2 * (s.bn_off + s.cout)].view(2, s.cout)
+            return T.bn_backward(dz, z, y, state, s.bn.weight, relu, bng[s.bn_off: s.bn_off + s.cout],
+                                 bng[self.bn_channels + s.bn_off: self.bn_channels + s.bn_off + s.cout], want_g, sm)
+
+        def wgrad(s: _ConvSpec, x, dy):
+            o = self.wgrad_offsets[s.idx]
+            T.conv2d_wgrad(x, dy, s.r, s.r, s.stride, s.pad, out=wg[o: o + s.conv.weight.numel()])
+
+        def dgrad(s: _ConvSpec, dy, x, residual=None):
+            return T.conv2d_dgrad(dy, self.packer.dgrad[s.idx], self.zero_bias, (x.shape[1], x.shape[2]), s.stride, s.pad, residual)
+
+        dz = None
+        stage_of = {b: i for i, b in enumerate(self.stage_ends)}
+        for bi in range(len(self.blocks) - 1, -1, -1):
+            c1, c2, c3, ds = self.blocks[bi]
+            x, y1, z1, s1, y2, z2, s2, y3, z3, s3, yd, sd = tape[bi]
+            if bi in stage_of and grad_outs[stage_of[bi]] is not None:
+                g_out = grad_outs[stage_of[bi]]
+                dz = g_out if dz is None else dz.add_(g_out)
+            if dz is None:                                   # nothing downstream of this block needs a gradient
+                dz = torch.zeros_like(z3)
+            dy3, g = bn_bwd(c3, dz, z3, y3, s3, True, want_g=True)
+            wgrad(c3, z2, dy3)
+            dz2 = dgrad(c3, dy3, z2)
+            dy2, _ = bn_bwd(c2, dz2, z2, y2, s2, True)
+            wgrad(c2, z1, dy2)
+            dz1 = dgrad(c2, dy2, z1)
+            dy1, _ = bn_bwd(c1, dz1, z1, y1, s1, True)
+            wgrad(c1, x, dy1)
+            if ds is not None:
+                dyd, _ = bn_bwd(ds, g, None, yd, sd, False)
+                wgrad(ds, x, dyd)
+                res = dgrad(ds, dyd, x)
+            else:
+                res = g
+            dz = dgrad(c1, dy1, x, residual=res)
+            tape[bi] = None                                  # release the block's activations as the sweep passes
+        grads = []
+        for s in self.specs:
+            o = self.wgrad_offsets[s.idx]
+            co, ci, r = s.cout, s.cin, s.r
+            grads.append(wg[o: o + co * ci * r * r].view(co, r, r, ci).permute(0, 3, 1, 2))
+            grads.append(bng[s.bn_off: s.bn_off + co])
+            grads.append(bng[self.bn_channels + s.bn_off: self.bn_channels + s.bn_off + co])
+        return dz, grads
+
+
+class _StagesFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, runner: NativeStages, x: torch.Tensor, *params):
+        outs, tape = runner.forward(x)
+        ctx.runner, ctx.tape = runner, tape
+        ctx.mark_non_differentiable()
+        return tuple(outs)
+
+    @staticmethod
+    def backward(ctx, *grad_outs):
+        gos = [None if g is None else g.contiguous() for g in grad_outs]
+        dx, grads = ctx.runner.backward(ctx.tape, gos)
+        ctx.tape = None
+        return (None, dx, *grads)
+
+
+def stages_forward(runner: NativeStages, pooled: torch.Tensor) -> Tuple[torch.Tensor, ...]:
+    """pooled (B,H,W,64) 16-bit NHWC (autograd-tracked) -> tuple of stage outputs (B,h,w,C) 16-bit NHWC."""
+    return _StagesFn.apply(runner, pooled, *runner.parameters())

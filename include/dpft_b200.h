@@ -195,6 +195,67 @@ DPFT_API int dpft_decoder_head_forward(const float* views, const float* weights,
                                        float* size_out, float* angle_out, float* class_out, int B, int V, int N,
                                        int n_cls, int reduction, int weight_floats, void* stream);
 
+/* ---------------------------------------------------------------------------------------------------------------
+ * Training path of the backbone (autograd of the torchvision Bottleneck blocks the reference trains,
+ * src/dprt/models/backbones/resnet.py:54-55,101 under src/dprt/training/trainer.py:125-133): BatchNorm with batch
+ * statistics is not folded, so a block is conv -> statistics -> normalise(+residual)(+ReLU), and backward is the
+ * mirrored chain.  Data gradients reuse dpft_conv2d_nhwc on the flipped/transposed weights produced by
+ * dpft_pack_conv_weights (stride-2 layers go through dpft_zero_insert2_nhwc first).
+ * ------------------------------------------------------------------------------------------------------------- */
+
+/*
+ * Weight gradient: dw[n, r, s, c] += sum_{b,p,q} dy[b,p,q,n] * x[b, p*stride-pad+r, q*stride-pad+s, c]   (fp32, ADDED into dw;
+ * the caller zero-fills).  tcgen05 GEMM over the pixel dimension with MN-major operands, split across `splits` work
+ * items per tile (0 = choose).
+ *   x (B, H, W, Cin) 16-bit, Cin % 64 == 0;  dy (B, P, Q, Cout) 16-bit, Cout % 64 == 0;  dw (Cout, R, S, Cin) f32
+ */
+DPFT_API int dpft_conv2d_wgrad(const void* x, const void* dy, float* dw, int B, int H, int W, int Cin, int Cout, int R, int S,
+                               int stride, int pad, int splits, int dtype, void* stream);
+
+/* BatchNorm2d (train) forward, three passes over y (M, C) 16-bit, C % 8 == 0 and 256 % (C/8) == 0:
+ *   dpft_bn_stats     sum[c] += sum_m y, sumsq[c] += sum_m y^2              (caller zero-fills sum / sumsq)
+ *   dpft_bn_finalize  mean, invstd = 1/sqrt(var_biased + eps), scale = gamma*invstd, shift = beta - mean*scale;
+ *                     running_mean/var momentum update with the unbiased variance (may be NULL)
+ *   dpft_bn_apply     z = [relu]( y*scale + shift (+ residual) )
+ */
+DPFT_API int dpft_bn_stats(const void* y, float* sum, float* sumsq, long long M, int C, int dtype, void* stream);
+DPFT_API int dpft_bn_finalize(const float* sum, const float* sumsq, const float* gamma, const float* beta, float* running_mean,
+                              float* running_var, float momentum, float eps, long long M, int C, float* scale, float* shift,
+                              float* mean, float* invstd, void* stream);
+DPFT_API int dpft_bn_apply(const void* y, const float* scale, const float* shift, const void* residual, void* z, long long M, int C,
+                           int relu, int dtype, void* stream);
+
+/* BatchNorm2d (train) backward through z = [relu](bn(y) (+ residual)), two passes:
+ *   dpft_bn_backward_reduce  g = dz * [z > 0] (when relu);  sum_g[c] += sum g,  sum_gx[c] += sum g * (y-mean)*invstd
+ *   dpft_bn_backward_apply   dy = gamma*invstd*(g - sum_g/M - xhat*sum_gx/M);  g_out = g (gradient of the residual branch,
+ *                            may be NULL);  dgamma += sum_gx, dbeta += sum_g (fp32, may be NULL)
+ */
+DPFT_API int dpft_bn_backward_reduce(const void* dz, const void* z, const void* y, const float* mean, const float* invstd,
+                                     float* sum_g, float* sum_gx, long long M, int C, int relu, int dtype, void* stream);
+DPFT_API int dpft_bn_backward_apply(const void* dz, const void* z, const void* y, const float* mean, const float* invstd,
+                                    const float* gamma, const float* sum_g, const float* sum_gx, void* dy, void* g_out,
+                                    float* dgamma, float* dbeta, long long M, int C, int relu, int dtype, void* stream);
+
+/* Backward of dpft_maxpool3x3s2_nhwc: x (B, H, W, C) is the pooled input, dy (B, P, Q, C); the gradient of a window goes to its
+ * first maximum in (row, column) order, as torch.nn.functional.max_pool2d does. */
+DPFT_API int dpft_maxpool3x3s2_backward(const void* x, const void* dy, void* dx, int B, int H, int W, int C, int dtype, void* stream);
+
+/* up[b, 2p, 2q, :] = src[b, p, q, :], zero elsewhere; src (B, P, Q, C), up (B, H, W, C), 16-bit, C % 8 == 0. */
+DPFT_API int dpft_zero_insert2_nhwc(const void* src, void* up, int B, int H, int W, int C, int P, int Q, void* stream);
+
+/* One launch re-lays out every convolution weight of a model after an optimiser step.  `table` is a DEVICE array of: */
+typedef struct dpft_pack_entry {
+    const float* src;      /* fp32 master weights (Cout, Cin, R, S) (torch layout) */
+    void* fwd;             /* 16-bit (Cout, R, S, Cin): operand of dpft_conv2d_nhwc / layout of dpft_conv2d_wgrad */
+    void* dgrad;           /* 16-bit (Cin, R, S, Cout), taps flipped: operand of the data-gradient convolution; may be NULL */
+    int Cout, Cin, R, S;
+    long long offset;      /* first element of this entry in the concatenated index space, ascending */
+} dpft_pack_entry;
+DPFT_API int dpft_pack_conv_weights(const void* table, int n_layers, long long total, int dtype, void* stream);
+/* The reverse for gradients: entry.src = fp32 (Cout, R, S, Cin) gradient from dpft_conv2d_wgrad, entry.fwd = fp32 parameter
+ * gradient (Cout, Cin, R, S) which is ADDED to. */
+DPFT_API int dpft_unpack_conv_wgrads(const void* table, int n_layers, long long total, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
