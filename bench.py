@@ -262,6 +262,8 @@ def run_train(args, cfg, sizes, rank, world, dev):
     model = models.build("dprt", cfg_t)
     model.load_state_dict(synthetic.seeded_state_dict(model.state_dict(), seed=1))
     model = model.to(dev).train()
+    model.native_train = args.dtype != "f32"          # --dtype f32: every dense layer through torch/cuDNN autograd
+    model.train_dtype = torch.bfloat16 if args.dtype == "bf16" else torch.float16
     if world > 1:
         ddp.broadcast_parameters(model, src=0)
     bucket = ddp.GradientBucket(model, n_chunks=6)
@@ -300,7 +302,10 @@ def run_train(args, cfg, sizes, rank, world, dev):
         print(json.dumps({"metric": "train_frames_per_sec", "value": B * world * args.steps / secs, "unit": UNIT,
                           "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
                           "ms_per_step": 1e3 * secs / args.steps, "higher_is_better": True, "scaling": "weak",
-                          "vs_baseline": None, "dtype": "f32 (torch TF32 convs allowed, as the reference's default)",
+                          "vs_baseline": None,
+                          "dtype": ("f16 activations / fp32 accumulate + master weights in the ResNet stages (native sm_100a training "
+                                    "kernels); stem, FPN, decoder fp32 through torch") if args.dtype != "f32"
+                                   else "f32 (torch TF32 convs allowed, as the reference's default)",
                           "data": "synthetic",
                           "config": {"workload": WORKLOAD.replace("eval forward", "training step (fwd+bwd+all-reduce+AdamW)"),
                                      "frames_per_gpu": B, "parallelism": f"dp{world}", "loss": "sum_k mean(out_k^2)",

@@ -12,6 +12,7 @@ namespace dpft {
 namespace {
 
 constexpr int TB = 256;
+constexpr int RB = 512;           // threads per block of the reduction passes (<= 2 blocks per SM)
 
 template <bool F16> struct H2;
 template <> struct H2<true> {
@@ -54,37 +55,49 @@ __device__ __forceinline__ uint4 ld_stream(const void* p) {
     return r;
 }
 
-// Block-level reduction of per-thread partial sums that belong to channel group (threadIdx.x % groups): NV values per thread.
-// Result is added to global memory by the first `groups` threads.
+// Block-level reduction of per-thread partial sums that belong to channel group (threadIdx.x % groups): NV values per thread
+// (NV = 16: two quantities x 8 channels).  The block's result goes to row blockIdx.x of a [gridDim.x][2][C] partial buffer; a
+// second small kernel sums the rows.  (Atomics on the 2C result addresses from ~1000 blocks serialise in L2: ~80 us per launch.)
 template <int NV>
-__device__ __forceinline__ void block_reduce_to_global(const float (&v)[NV], int groups, float* const* dst, int c0) {
-    __shared__ float red[TB][NV + 1];
+__device__ __forceinline__ void block_reduce_to_partials(const float (&v)[NV], int groups, float* partials, int C) {
+    __shared__ float red[RB][NV + 1];
 #pragma unroll
     for (int k = 0; k < NV; ++k) red[threadIdx.x][k] = v[k];
     __syncthreads();
-    if ((int)threadIdx.x < groups) {
-        float acc[NV];
-#pragma unroll
-        for (int k = 0; k < NV; ++k) acc[k] = 0.0f;
-        for (int t = threadIdx.x; t < TB; t += groups) {
-#pragma unroll
-            for (int k = 0; k < NV; ++k) acc[k] += red[t][k];
-        }
-#pragma unroll
-        for (int k = 0; k < NV; ++k) atomicAdd(dst[k / 8] + c0 + (k % 8), acc[k]);
+    // thread t < groups * NV sums value k = t % NV of channel group t / NV over the RB / groups threads that own it
+    for (int t = threadIdx.x; t < groups * NV; t += RB) {
+        const int grp = t / NV, k = t - grp * NV;
+        float acc = 0.0f;
+        for (int u = grp; u < RB; u += groups) acc += red[u][k];
+        partials[(size_t)blockIdx.x * 2 * C + (k / 8) * C + grp * 8 + (k % 8)] = acc;
     }
+}
+
+// column sums of a [nparts][n] partial buffer; blockDim = (32, 8), one block per 32 columns
+__device__ __forceinline__ float column_sum(const float* __restrict__ partials, int nparts, int n, int col) {
+    __shared__ float part[8][33];
+    float acc = 0.0f;
+    if (col < n) {
+        for (int r = threadIdx.y; r < nparts; r += 8) acc += partials[(size_t)r * n + col];
+    }
+    part[threadIdx.y][threadIdx.x] = acc;
+    __syncthreads();
+    float tot = 0.0f;
+#pragma unroll
+    for (int r = 0; r < 8; ++r) tot += part[r][threadIdx.x];
+    __syncthreads();
+    return tot;
 }
 
 // ---- BatchNorm forward ---------------------------------------------------------------------------------------------
 // pass 1: per-channel sum and sum of squares of y (M, C)
 template <bool F16>
-__global__ void __launch_bounds__(TB) bn_stats_kernel(const uint4* __restrict__ y, float* __restrict__ sum, float* __restrict__ sumsq,
-                                                      long long nvec, int groups) {
+__global__ void __launch_bounds__(RB) bn_stats_kernel(const uint4* __restrict__ y, float* __restrict__ partials, long long nvec, int groups) {
     float acc[16];
 #pragma unroll
     for (int k = 0; k < 16; ++k) acc[k] = 0.0f;
-    const long long stride = (long long)gridDim.x * TB;
-    long long i = (long long)blockIdx.x * TB + threadIdx.x;
+    const long long stride = (long long)gridDim.x * RB;
+    long long i = (long long)blockIdx.x * RB + threadIdx.x;
     for (; i + 3 * stride < nvec; i += 4 * stride) {          // four independent 16-byte loads in flight per thread
         uint4 r[4];
 #pragma unroll
@@ -103,20 +116,21 @@ __global__ void __launch_bounds__(TB) bn_stats_kernel(const uint4* __restrict__ 
 #pragma unroll
         for (int k = 0; k < 8; ++k) { acc[k] += f[k]; acc[8 + k] = fmaf(f[k], f[k], acc[8 + k]); }
     }
-    float* dst[2] = {sum, sumsq};
-    block_reduce_to_global<16>(acc, groups, dst, (threadIdx.x % groups) * 8);
+    block_reduce_to_partials<16>(acc, groups, partials, groups * 8);
 }
 
 // pass 2 (C threads): batch mean / inverse std, the affine form used by the apply pass, and the running statistics
 // (momentum update with the unbiased variance, torch.nn.BatchNorm2d semantics).
-__global__ void bn_finalize_kernel(const float* __restrict__ sum, const float* __restrict__ sumsq, const float* __restrict__ gamma,
+__global__ void bn_finalize_kernel(const float* __restrict__ partials, int nparts, const float* __restrict__ gamma,
                                    const float* __restrict__ beta, float* running_mean, float* running_var, float momentum, float eps,
                                    float count, int C, float* __restrict__ scale, float* __restrict__ shift, float* __restrict__ mean_out,
                                    float* __restrict__ invstd_out) {
-    const int c = blockIdx.x * blockDim.x + threadIdx.x;
-    if (c >= C) return;
-    const float mean = sum[c] / count;
-    const float var = fmaxf(sumsq[c] / count - mean * mean, 0.0f);
+    const int c = blockIdx.x * 32 + threadIdx.x;
+    const float sum = column_sum(partials, nparts, 2 * C, c);
+    const float sumsq = column_sum(partials, nparts, 2 * C, C + c);
+    if (c >= C || threadIdx.y != 0) return;
+    const float mean = sum / count;
+    const float var = fmaxf(sumsq / count - mean * mean, 0.0f);
     const float invstd = rsqrtf(var + eps);
     const float g = gamma ? gamma[c] : 1.0f, b = beta ? beta[c] : 0.0f;
     scale[c] = g * invstd;
@@ -171,10 +185,10 @@ __global__ void __launch_bounds__(TB) bn_apply_kernel(const uint4* __restrict__ 
 // ---- BatchNorm backward --------------------------------------------------------------------------------------------
 // pass 1: g = dz * [z > 0] (ReLU mask when relu), sum_g[c] = sum g, sum_gx[c] = sum g * xhat, xhat = (y - mean) * invstd
 template <bool F16>
-__global__ void __launch_bounds__(TB) bn_bwd_reduce_kernel(const uint4* __restrict__ dz, const uint4* __restrict__ z,
+__global__ void __launch_bounds__(RB) bn_bwd_reduce_kernel(const uint4* __restrict__ dz, const uint4* __restrict__ z,
                                                            const uint4* __restrict__ y, const float* __restrict__ mean,
-                                                           const float* __restrict__ invstd, float* __restrict__ sum_g,
-                                                           float* __restrict__ sum_gx, long long nvec, int groups, int relu) {
+                                                           const float* __restrict__ invstd, float* __restrict__ partials,
+                                                           long long nvec, int groups, int relu) {
     const int c0 = (threadIdx.x % groups) * 8;
     float mu[8], is[8];
 #pragma unroll
@@ -182,8 +196,8 @@ __global__ void __launch_bounds__(TB) bn_bwd_reduce_kernel(const uint4* __restri
     float acc[16];
 #pragma unroll
     for (int k = 0; k < 16; ++k) acc[k] = 0.0f;
-    const long long stride = (long long)gridDim.x * TB;
-    for (long long i = (long long)blockIdx.x * TB + threadIdx.x; i < nvec; i += 2 * stride) {
+    const long long stride = (long long)gridDim.x * RB;
+    for (long long i = (long long)blockIdx.x * RB + threadIdx.x; i < nvec; i += 2 * stride) {
         const bool two = i + stride < nvec;
         uint4 rd[2], rz[2], ry[2];
 #pragma unroll
@@ -212,25 +226,32 @@ __global__ void __launch_bounds__(TB) bn_bwd_reduce_kernel(const uint4* __restri
             }
         }
     }
-    float* dst[2] = {sum_g, sum_gx};
-    block_reduce_to_global<16>(acc, groups, dst, c0);
+    block_reduce_to_partials<16>(acc, groups, partials, groups * 8);
 }
 
+// column sums of the partial rows -> sum_g | sum_gx, and the affine parameter gradients dgamma += sum_gx, dbeta += sum_g
+__global__ void bn_bwd_sums_kernel(const float* __restrict__ partials, int nparts, int C, float* __restrict__ sum_g,
+                                   float* __restrict__ sum_gx, float* dgamma, float* dbeta) {
+    const int c = blockIdx.x * 32 + threadIdx.x;
+    const float sg = column_sum(partials, nparts, 2 * C, c);
+    const float sgx = column_sum(partials, nparts, 2 * C, C + c);
+    if (c >= C || threadIdx.y != 0) return;
+    sum_g[c] = sg;
+    sum_gx[c] = sgx;
+    if (dgamma) dgamma[c] += sgx;
+    if (dbeta) dbeta[c] += sg;
+}
+
+
 // pass 2: dy = gamma * invstd * (g - sum_g / M - xhat * sum_gx / M); optionally stores g (the gradient that flows into
-// the block's identity branch); block 0 adds dgamma = sum_gx, dbeta = sum_g into the fp32 parameter gradients.
+// the block's identity branch).
 template <bool F16>
 __global__ void __launch_bounds__(TB) bn_bwd_apply_kernel(const uint4* __restrict__ dz, const uint4* __restrict__ z,
                                                           const uint4* __restrict__ y, const float* __restrict__ mean,
                                                           const float* __restrict__ invstd, const float* __restrict__ gamma,
                                                           const float* __restrict__ sum_g, const float* __restrict__ sum_gx,
-                                                          uint4* __restrict__ dy, uint4* __restrict__ g_out, float* dgamma,
-                                                          float* dbeta, float inv_count, long long nvec, int groups, int relu, int C) {
-    if (blockIdx.x == 0) {
-        for (int c = threadIdx.x; c < C; c += TB) {
-            if (dgamma) dgamma[c] += sum_gx[c];
-            if (dbeta) dbeta[c] += sum_g[c];
-        }
-    }
+                                                          uint4* __restrict__ dy, uint4* __restrict__ g_out, float inv_count,
+                                                          long long nvec, int groups, int relu) {
     const int c0 = (threadIdx.x % groups) * 8;
     float mu[8], is[8], k1[8], k2[8], k3[8];
 #pragma unroll
@@ -435,24 +456,27 @@ using namespace dpft;
 
 static inline bool channels_ok(int C) { return C >= 8 && C % 8 == 0 && C / 8 <= TB && TB % (C / 8) == 0; }
 
-extern "C" int dpft_bn_stats(const void* y, float* sum, float* sumsq, long long M, int C, int dtype, void* stream) {
-    DPFT_REQUIRE_16BIT("bn_stats");
-    DPFT_REQUIRE(y && sum && sumsq && M > 0, "bn_stats: null pointer or empty input");
-    DPFT_REQUIRE(channels_ok(C), "bn_stats: C=%d must be a multiple of 8 with 256 %% (C/8) == 0", C);
-    const long long nvec = M * (C / 8);
-    const int grid = grid_for((nvec + 3) / 4, sm_count());
-    if (is_f16) bn_stats_kernel<true><<<grid, TB, 0, (cudaStream_t)stream>>>((const uint4*)y, sum, sumsq, nvec, C / 8);
-    else bn_stats_kernel<false><<<grid, TB, 0, (cudaStream_t)stream>>>((const uint4*)y, sum, sumsq, nvec, C / 8);
-    DPFT_LAUNCH_CHECK("bn_stats_kernel");
-    return DPFT_OK;
+static inline int reduce_grid(long long nvec, int per_thread) {
+    long long blocks = (nvec + (long long)RB * per_thread - 1) / ((long long)RB * per_thread);
+    const long long cap = DPFT_BN_MAX_PARTS < 2 * sm_count() ? DPFT_BN_MAX_PARTS : 2 * sm_count();
+    if (blocks > cap) blocks = cap;
+    if (blocks < 1) blocks = 1;
+    return (int)blocks;
 }
 
-extern "C" int dpft_bn_finalize(const float* sum, const float* sumsq, const float* gamma, const float* beta, float* running_mean,
-                                float* running_var, float momentum, float eps, long long M, int C, float* scale, float* shift,
-                                float* mean, float* invstd, void* stream) {
-    DPFT_REQUIRE(sum && sumsq && scale && shift && mean && invstd && M > 0 && C > 0, "bn_finalize: null pointer or empty input");
-    bn_finalize_kernel<<<(C + 127) / 128, 128, 0, (cudaStream_t)stream>>>(sum, sumsq, gamma, beta, running_mean, running_var, momentum,
-                                                                          eps, (float)M, C, scale, shift, mean, invstd);
+extern "C" int dpft_bn_forward_stats(const void* y, float* workspace, const float* gamma, const float* beta, float* running_mean,
+                                     float* running_var, float momentum, float eps, long long M, int C, float* scale, float* shift,
+                                     float* mean, float* invstd, int dtype, void* stream) {
+    DPFT_REQUIRE_16BIT("bn_forward_stats");
+    DPFT_REQUIRE(y && workspace && scale && shift && mean && invstd && M > 0, "bn_forward_stats: null pointer or empty input");
+    DPFT_REQUIRE(channels_ok(C), "bn_forward_stats: C=%d must be a multiple of 8 with 256 %% (C/8) == 0", C);
+    const long long nvec = M * (C / 8);
+    const int grid = reduce_grid(nvec, 8);
+    if (is_f16) bn_stats_kernel<true><<<grid, RB, 0, (cudaStream_t)stream>>>((const uint4*)y, workspace, nvec, C / 8);
+    else bn_stats_kernel<false><<<grid, RB, 0, (cudaStream_t)stream>>>((const uint4*)y, workspace, nvec, C / 8);
+    DPFT_LAUNCH_CHECK("bn_stats_kernel");
+    bn_finalize_kernel<<<(C + 31) / 32, dim3(32, 8), 0, (cudaStream_t)stream>>>(workspace, grid, gamma, beta, running_mean, running_var,
+                                                                               momentum, eps, (float)M, C, scale, shift, mean, invstd);
     DPFT_LAUNCH_CHECK("bn_finalize_kernel");
     return DPFT_OK;
 }
@@ -471,29 +495,33 @@ extern "C" int dpft_bn_apply(const void* y, const float* scale, const float* shi
 }
 
 extern "C" int dpft_bn_backward_reduce(const void* dz, const void* z, const void* y, const float* mean, const float* invstd,
-                                       float* sum_g, float* sum_gx, long long M, int C, int relu, int dtype, void* stream) {
+                                       float* workspace, float* sum_g, float* sum_gx, float* dgamma, float* dbeta, long long M, int C,
+                                       int relu, int dtype, void* stream) {
     DPFT_REQUIRE_16BIT("bn_backward_reduce");
-    DPFT_REQUIRE(dz && y && mean && invstd && sum_g && sum_gx && M > 0 && (!relu || z), "bn_backward_reduce: null pointer or empty input");
+    DPFT_REQUIRE(dz && y && mean && invstd && workspace && sum_g && sum_gx && M > 0 && (!relu || z),
+                 "bn_backward_reduce: null pointer or empty input");
     DPFT_REQUIRE(channels_ok(C), "bn_backward_reduce: C=%d must be a multiple of 8 with 256 %% (C/8) == 0", C);
     const long long nvec = M * (C / 8);
-    const int grid = grid_for((nvec + 1) / 2, sm_count());
-    if (is_f16) bn_bwd_reduce_kernel<true><<<grid, TB, 0, (cudaStream_t)stream>>>((const uint4*)dz, (const uint4*)z, (const uint4*)y, mean, invstd, sum_g, sum_gx, nvec, C / 8, relu);
-    else bn_bwd_reduce_kernel<false><<<grid, TB, 0, (cudaStream_t)stream>>>((const uint4*)dz, (const uint4*)z, (const uint4*)y, mean, invstd, sum_g, sum_gx, nvec, C / 8, relu);
+    const int grid = reduce_grid(nvec, 4);
+    if (is_f16) bn_bwd_reduce_kernel<true><<<grid, RB, 0, (cudaStream_t)stream>>>((const uint4*)dz, (const uint4*)z, (const uint4*)y, mean, invstd, workspace, nvec, C / 8, relu);
+    else bn_bwd_reduce_kernel<false><<<grid, RB, 0, (cudaStream_t)stream>>>((const uint4*)dz, (const uint4*)z, (const uint4*)y, mean, invstd, workspace, nvec, C / 8, relu);
     DPFT_LAUNCH_CHECK("bn_bwd_reduce_kernel");
+    bn_bwd_sums_kernel<<<(C + 31) / 32, dim3(32, 8), 0, (cudaStream_t)stream>>>(workspace, grid, C, sum_g, sum_gx, dgamma, dbeta);
+    DPFT_LAUNCH_CHECK("bn_bwd_sums_kernel");
     return DPFT_OK;
 }
 
 extern "C" int dpft_bn_backward_apply(const void* dz, const void* z, const void* y, const float* mean, const float* invstd,
                                       const float* gamma, const float* sum_g, const float* sum_gx, void* dy, void* g_out,
-                                      float* dgamma, float* dbeta, long long M, int C, int relu, int dtype, void* stream) {
+                                      long long M, int C, int relu, int dtype, void* stream) {
     DPFT_REQUIRE_16BIT("bn_backward_apply");
     DPFT_REQUIRE(dz && y && mean && invstd && sum_g && sum_gx && dy && M > 0 && (!relu || z), "bn_backward_apply: null pointer or empty input");
     DPFT_REQUIRE(channels_ok(C), "bn_backward_apply: C=%d must be a multiple of 8 with 256 %% (C/8) == 0", C);
     const long long nvec = M * (C / 8);
     const int grid = grid_for((nvec + 1) / 2, sm_count());
     const float inv = 1.0f / (float)M;
-    if (is_f16) bn_bwd_apply_kernel<true><<<grid, TB, 0, (cudaStream_t)stream>>>((const uint4*)dz, (const uint4*)z, (const uint4*)y, mean, invstd, gamma, sum_g, sum_gx, (uint4*)dy, (uint4*)g_out, dgamma, dbeta, inv, nvec, C / 8, relu, C);
-    else bn_bwd_apply_kernel<false><<<grid, TB, 0, (cudaStream_t)stream>>>((const uint4*)dz, (const uint4*)z, (const uint4*)y, mean, invstd, gamma, sum_g, sum_gx, (uint4*)dy, (uint4*)g_out, dgamma, dbeta, inv, nvec, C / 8, relu, C);
+    if (is_f16) bn_bwd_apply_kernel<true><<<grid, TB, 0, (cudaStream_t)stream>>>((const uint4*)dz, (const uint4*)z, (const uint4*)y, mean, invstd, gamma, sum_g, sum_gx, (uint4*)dy, (uint4*)g_out, inv, nvec, C / 8, relu);
+    else bn_bwd_apply_kernel<false><<<grid, TB, 0, (cudaStream_t)stream>>>((const uint4*)dz, (const uint4*)z, (const uint4*)y, mean, invstd, gamma, sum_g, sum_gx, (uint4*)dy, (uint4*)g_out, inv, nvec, C / 8, relu);
     DPFT_LAUNCH_CHECK("bn_bwd_apply_kernel");
     return DPFT_OK;
 }

@@ -106,7 +106,7 @@ class Backbone(nn.Module):
             self.adjustment_layer = nn.Conv2d(in_channels, 3, 1, bias=False)
         self.body = ResNetBody(arch, multi_scale, _norm(norm_layer))
         self.native_train = False             # train(): run layer1.. through the sm_100a training kernels (16-bit activations)
-        self.train_dtype = torch.bfloat16
+        self.train_dtype = torch.float16      # float16 (gradients carried with a power-of-two scale) or bfloat16
         self._stages = None
         if weights:
             self._load_weights(name, weights)
@@ -151,9 +151,8 @@ class Backbone(nn.Module):
         body = self.body
         x = F.relu(body.bn1(body.conv1(self.adjustment_layer(x))))
         x = F.max_pool2d(x, kernel_size=3, stride=2, padding=1)
-        pooled = x.permute(0, 2, 3, 1).to(self.train_dtype).contiguous()
-        outs = stages_forward(stages, pooled)
-        feats = OrderedDict((str(i + 1), o.float()) for i, o in enumerate(outs))
+        outs = stages_forward(stages, x.permute(0, 2, 3, 1))
+        feats = OrderedDict((str(i + 1), o) for i, o in enumerate(outs))
         if not self.channel_last:
             feats = OrderedDict((k, v.movedim(-1, 1)) for k, v in feats.items())
         return feats

@@ -61,6 +61,9 @@ class DPRT(nn.Module):
         self.pyramid_dtype = torch.float16    # storage of the native (B, S, 16) feature pyramid: float16 or float32
         self.use_cuda_graph = True     # fused pipeline: replay a captured graph once an input shape repeats
         self.parallel_views = True     # fused pipeline: run the per-view feature extractors on forked streams
+        self.native_train = True       # train() on CUDA: ResNet stages through the sm_100a training kernels (16-bit
+                                       # activations, dpft_b200/train_backbone.py); False = torch/cuDNN autograd in fp32
+        self.train_dtype = torch.float16
         self._engine = None
 
     @classmethod
@@ -84,7 +87,10 @@ class DPRT(nn.Module):
     def extract_features(self, batch: Dict[str, torch.Tensor], only=None) -> Dict[str, "OrderedDict[str, torch.Tensor]"]:
         feats = {}
         for name in (self.inputs if only is None else only):
-            f = self.backbones[name](batch[name])
+            bb = self.backbones[name]
+            if hasattr(bb, "native_train"):
+                bb.native_train, bb.train_dtype = self.native_train, self.train_dtype
+            f = bb(batch[name])
             if self.skiplinks[name]:
                 f = OrderedDict([("0", batch[name])] + list(f.items()))
             f = self.necks[name](f)

@@ -3,8 +3,8 @@ as ONE autograd node per backbone.
 
 Replaces, under ``model.train()``, the cuDNN convolution / batch-norm / ReLU forward+backward launches autograd records for
 the torchvision Bottleneck blocks the reference trains (src/dprt/models/backbones/resnet.py:54-55,101; the backward is
-driven from src/dprt/training/trainer.py:125-133).  Activations and activation gradients are NHWC 16-bit (bf16 by
-default: gradients need the exponent range), accumulation and every parameter gradient fp32.
+driven from src/dprt/training/trainer.py:125-133).  Activations and activation gradients are NHWC 16-bit (float16 with a
+power-of-two gradient scale, or bfloat16), accumulation and every parameter gradient fp32.
 
 Per block (x = block input, 16-bit):
     y1 = conv1(x)            z1 = relu(bn1(y1))
@@ -99,13 +99,13 @@ class NativeStages:
 
     def _bn(self, s: _ConvSpec, y: torch.Tensor, states: torch.Tensor, relu: bool, residual=None):
         bn = s.bn
-        buf = states[6 * s.bn_off: 6 * (s.bn_off + s.cout)].view(6, s.cout)
+        buf = states[4 * s.bn_off: 4 * (s.bn_off + s.cout)].view(4, s.cout)
         return T.bn_forward(y, bn.weight, bn.bias, bn.running_mean, bn.running_var, bn.momentum, bn.eps, relu, residual, buf)
 
     def forward(self, x: torch.Tensor):
         """x (B,H,W,64) 16-bit (the max-pooled stem output) -> (stage outputs, tape)."""
         self._refresh_weights()
-        states = torch.zeros(6 * self.bn_channels, dtype=torch.float32, device=x.device)
+        states = torch.empty(4 * self.bn_channels, dtype=torch.float32, device=x.device)
         tape = []
         outs = []
         for bi, (c1, c2, c3, ds) in enumerate(self.blocks):
@@ -134,7 +134,7 @@ class NativeStages:
         dev = self.device
         wg = torch.zeros(self.wgrad_total, dtype=torch.float32, device=dev)
         bng = torch.zeros(2 * self.bn_channels, dtype=torch.float32, device=dev)       # dgamma | dbeta
-        sums = torch.zeros(2 * self.bn_channels, dtype=torch.float32, device=dev)
+        sums = torch.empty(2 * self.bn_channels, dtype=torch.float32, device=dev)
 
         def bn_bwd(s: _ConvSpec, dz, z, y, state, relu, want_g=False):
             sm = sums[2 * s.bn_off: 2 * (s.bn_off + s.cout)].view(2, s.cout)
@@ -181,25 +181,45 @@ class NativeStages:
             grads.append(wg[o: o + co * ci * r * r].view(co, r, r, ci).permute(0, 3, 1, 2))
             grads.append(bng[s.bn_off: s.bn_off + co])
             grads.append(bng[self.bn_channels + s.bn_off: self.bn_channels + s.bn_off + co])
-        return dz, grads
+        return dz, grads, (wg, bng)
+
+
+GRAD_TARGET_AMAX = 64.0      # f16 gradients: the incoming gradients are scaled so that their largest element is ~2^6
 
 
 class _StagesFn(torch.autograd.Function):
+    """fp32 in / fp32 out at the autograd boundary; 16-bit inside.  With f16 the activation gradients are carried with a
+    power-of-two scale S (computed on the device from the incoming gradients, no host sync) so that they stay inside
+    f16's exponent range; every backward kernel is linear in the gradient, so the parameter gradients and the input
+    gradient are multiplied by 1/S at the end."""
+
     @staticmethod
     def forward(ctx, runner: NativeStages, x: torch.Tensor, *params):
-        outs, tape = runner.forward(x)
+        outs, tape = runner.forward(x.to(runner.dtype).contiguous())
         ctx.runner, ctx.tape = runner, tape
-        ctx.mark_non_differentiable()
-        return tuple(outs)
+        return tuple(o.float() for o in outs)
 
     @staticmethod
     def backward(ctx, *grad_outs):
-        gos = [None if g is None else g.contiguous() for g in grad_outs]
-        dx, grads = ctx.runner.backward(ctx.tape, gos)
+        runner = ctx.runner
+        scale = None
+        if runner.dtype == torch.float16:
+            amax = torch.stack([g.abs().max() for g in grad_outs if g is not None]).max()
+            scale = torch.exp2(torch.floor(torch.log2(GRAD_TARGET_AMAX / amax.clamp_min(1e-30)))).clamp(2.0 ** -40, 2.0 ** 40)
+            gos = [None if g is None else (g * scale).to(runner.dtype).contiguous() for g in grad_outs]
+        else:
+            gos = [None if g is None else g.to(runner.dtype).contiguous() for g in grad_outs]
+        dx, grads, flats = runner.backward(ctx.tape, gos)
         ctx.tape = None
+        dx = dx.float()
+        if scale is not None:
+            inv = 1.0 / scale
+            dx = dx * inv
+            for f in flats:
+                f.mul_(inv)
         return (None, dx, *grads)
 
 
 def stages_forward(runner: NativeStages, pooled: torch.Tensor) -> Tuple[torch.Tensor, ...]:
-    """pooled (B,H,W,64) 16-bit NHWC (autograd-tracked) -> tuple of stage outputs (B,h,w,C) 16-bit NHWC."""
+    """pooled (B,H,W,64) fp32 NHWC (autograd-tracked) -> tuple of stage outputs (B,h,w,C) fp32 NHWC."""
     return _StagesFn.apply(runner, pooled, *runner.parameters())

@@ -82,12 +82,25 @@ def conv2d_dgrad(dy: torch.Tensor, w_dgrad: torch.Tensor, zero_bias: torch.Tenso
     return conv2d_nhwc(up, w_dgrad, zero_bias, 1, R - 1 - pad, False, residual)
 
 
+BN_MAX_PARTS = 296          # DPFT_BN_MAX_PARTS
+_workspaces = {}
+
+
+def bn_workspace(device) -> torch.Tensor:
+    """Partial-sum scratch shared by every BatchNorm call on a device (calls are stream-ordered)."""
+    key = torch.device(device)
+    ws = _workspaces.get(key)
+    if ws is None:
+        ws = _workspaces[key] = torch.empty(BN_MAX_PARTS * 2 * 2048, dtype=torch.float32, device=device)
+    return ws
+
+
 class BNState:
-    """fp32 per-channel buffers of one BatchNorm call: [sum, sumsq, scale, shift, mean, invstd] rows of one (6, C) tensor."""
+    """fp32 per-channel buffers of one BatchNorm call: [scale, shift, mean, invstd] rows of one (4, C) tensor."""
 
     def __init__(self, buf: torch.Tensor):
         self.buf = buf
-        self.sum, self.sumsq, self.scale, self.shift, self.mean, self.invstd = buf.unbind(0)
+        self.scale, self.shift, self.mean, self.invstd = buf.unbind(0)
 
 
 def bn_forward(y: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, running_mean: Optional[torch.Tensor],
@@ -97,17 +110,18 @@ def bn_forward(y: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, running
     _check16(y)
     C = y.shape[-1]
     M = y.numel() // C
+    if C > 2048:
+        raise RuntimeError("bn_forward: at most 2048 channels")
     if state_buf is None:
-        state_buf = torch.zeros((6, C), dtype=torch.float32, device=y.device)
+        state_buf = torch.empty((4, C), dtype=torch.float32, device=y.device)
     st8 = BNState(state_buf)
     lib = _lib()
     code, stream = native.dtype_code(y), native.stream_ptr(y.device)
     with torch.cuda.device(y.device):
-        native.check(lib.dpft_bn_stats(native.ptr(y), native.ptr(st8.sum), native.ptr(st8.sumsq), M, C, code, stream), "dpft_bn_stats")
-        native.check(lib.dpft_bn_finalize(native.ptr(st8.sum), native.ptr(st8.sumsq), native.ptr(gamma), native.ptr(beta),
-                                          native.ptr(running_mean), native.ptr(running_var), float(momentum), float(eps), M, C,
-                                          native.ptr(st8.scale), native.ptr(st8.shift), native.ptr(st8.mean), native.ptr(st8.invstd),
-                                          stream), "dpft_bn_finalize")
+        native.check(lib.dpft_bn_forward_stats(native.ptr(y), native.ptr(bn_workspace(y.device)), native.ptr(gamma), native.ptr(beta),
+                                               native.ptr(running_mean), native.ptr(running_var), float(momentum), float(eps), M, C,
+                                               native.ptr(st8.scale), native.ptr(st8.shift), native.ptr(st8.mean), native.ptr(st8.invstd),
+                                               code, stream), "dpft_bn_forward_stats")
         z = torch.empty_like(y)
         native.check(lib.dpft_bn_apply(native.ptr(y), native.ptr(st8.scale), native.ptr(st8.shift), native.ptr(residual), native.ptr(z),
                                        M, C, int(relu), code, stream), "dpft_bn_apply")
@@ -124,20 +138,20 @@ def bn_backward(dz: torch.Tensor, z: Optional[torch.Tensor], y: torch.Tensor, st
     C = y.shape[-1]
     M = y.numel() // C
     if sums is None:
-        sums = torch.zeros((2, C), dtype=torch.float32, device=y.device)
+        sums = torch.empty((2, C), dtype=torch.float32, device=y.device)
     dy = torch.empty_like(y)
     g = torch.empty_like(y) if want_g else None
     lib = _lib()
     code, stream = native.dtype_code(y), native.stream_ptr(y.device)
     with torch.cuda.device(y.device):
         native.check(lib.dpft_bn_backward_reduce(native.ptr(dz), native.ptr(z), native.ptr(y), native.ptr(state.mean),
-                                                 native.ptr(state.invstd), native.ptr(sums[0]), native.ptr(sums[1]), M, C, int(relu),
+                                                 native.ptr(state.invstd), native.ptr(bn_workspace(y.device)), native.ptr(sums[0]),
+                                                 native.ptr(sums[1]), native.ptr(dgamma), native.ptr(dbeta), M, C, int(relu),
                                                  code, stream), "dpft_bn_backward_reduce")
         native.check(lib.dpft_bn_backward_apply(native.ptr(dz), native.ptr(z), native.ptr(y), native.ptr(state.mean),
                                                 native.ptr(state.invstd), native.ptr(gamma), native.ptr(sums[0]), native.ptr(sums[1]),
-                                                native.ptr(dy), native.ptr(g), native.ptr(dgamma), native.ptr(dbeta), M, C, int(relu),
-                                                code, stream), "dpft_bn_backward_apply")
-    native.count_launch(2)
+                                                native.ptr(dy), native.ptr(g), M, C, int(relu), code, stream), "dpft_bn_backward_apply")
+    native.count_launch(3)
     return dy, g
 
 

@@ -212,29 +212,32 @@ DPFT_API int dpft_decoder_head_forward(const float* views, const float* weights,
 DPFT_API int dpft_conv2d_wgrad(const void* x, const void* dy, float* dw, int B, int H, int W, int Cin, int Cout, int R, int S,
                                int stride, int pad, int splits, int dtype, void* stream);
 
-/* BatchNorm2d (train) forward, three passes over y (M, C) 16-bit, C % 8 == 0 and 256 % (C/8) == 0:
- *   dpft_bn_stats     sum[c] += sum_m y, sumsq[c] += sum_m y^2              (caller zero-fills sum / sumsq)
- *   dpft_bn_finalize  mean, invstd = 1/sqrt(var_biased + eps), scale = gamma*invstd, shift = beta - mean*scale;
- *                     running_mean/var momentum update with the unbiased variance (may be NULL)
- *   dpft_bn_apply     z = [relu]( y*scale + shift (+ residual) )
+/* BatchNorm2d (train) forward over y (M, C) 16-bit, C % 8 == 0 and 256 % (C/8) == 0:
+ *   dpft_bn_forward_stats  per-block partial sums of y and y^2 into `workspace` (>= DPFT_BN_MAX_PARTS * 2 * C floats, no atomics,
+ *                          deterministic), then mean, invstd = 1/sqrt(var_biased + eps), scale = gamma*invstd,
+ *                          shift = beta - mean*scale, and the running_mean/var momentum update with the unbiased variance
+ *                          (running_* may be NULL)
+ *   dpft_bn_apply          z = [relu]( y*scale + shift (+ residual) )
  */
-DPFT_API int dpft_bn_stats(const void* y, float* sum, float* sumsq, long long M, int C, int dtype, void* stream);
-DPFT_API int dpft_bn_finalize(const float* sum, const float* sumsq, const float* gamma, const float* beta, float* running_mean,
-                              float* running_var, float momentum, float eps, long long M, int C, float* scale, float* shift,
-                              float* mean, float* invstd, void* stream);
+#define DPFT_BN_MAX_PARTS 296
+DPFT_API int dpft_bn_forward_stats(const void* y, float* workspace, const float* gamma, const float* beta, float* running_mean,
+                                   float* running_var, float momentum, float eps, long long M, int C, float* scale, float* shift,
+                                   float* mean, float* invstd, int dtype, void* stream);
 DPFT_API int dpft_bn_apply(const void* y, const float* scale, const float* shift, const void* residual, void* z, long long M, int C,
                            int relu, int dtype, void* stream);
 
 /* BatchNorm2d (train) backward through z = [relu](bn(y) (+ residual)), two passes:
- *   dpft_bn_backward_reduce  g = dz * [z > 0] (when relu);  sum_g[c] += sum g,  sum_gx[c] += sum g * (y-mean)*invstd
+ *   dpft_bn_backward_reduce  g = dz * [z > 0] (when relu);  sum_g[c] = sum g,  sum_gx[c] = sum g * (y-mean)*invstd (partials in
+ *                            `workspace` as above);  dgamma += sum_gx, dbeta += sum_g (fp32, may be NULL)
  *   dpft_bn_backward_apply   dy = gamma*invstd*(g - sum_g/M - xhat*sum_gx/M);  g_out = g (gradient of the residual branch,
- *                            may be NULL);  dgamma += sum_gx, dbeta += sum_g (fp32, may be NULL)
+ *                            may be NULL)
  */
 DPFT_API int dpft_bn_backward_reduce(const void* dz, const void* z, const void* y, const float* mean, const float* invstd,
-                                     float* sum_g, float* sum_gx, long long M, int C, int relu, int dtype, void* stream);
+                                     float* workspace, float* sum_g, float* sum_gx, float* dgamma, float* dbeta, long long M, int C,
+                                     int relu, int dtype, void* stream);
 DPFT_API int dpft_bn_backward_apply(const void* dz, const void* z, const void* y, const float* mean, const float* invstd,
                                     const float* gamma, const float* sum_g, const float* sum_gx, void* dy, void* g_out,
-                                    float* dgamma, float* dbeta, long long M, int C, int relu, int dtype, void* stream);
+                                    long long M, int C, int relu, int dtype, void* stream);
 
 /* Backward of dpft_maxpool3x3s2_nhwc: x (B, H, W, C) is the pooled input, dy (B, P, Q, C); the gradient of a window goes to its
  * first maximum in (row, column) order, as torch.nn.functional.max_pool2d does. */
