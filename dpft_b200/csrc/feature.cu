@@ -30,7 +30,7 @@ constexpr int STEM_COUT = 64;
 template <int CIN, typename OT>
 __global__ void __launch_bounds__(256)
 stem_conv7x7_kernel(const float* __restrict__ x, const float* __restrict__ w /* [49*CIN][64] */,
-                    const float* __restrict__ bias, OT* __restrict__ y, int H, int W, int P, int Q) {
+                    const float* __restrict__ bias, OT* __restrict__ y, int H, int W, int P, int Q, float lo) {
     extern __shared__ __align__(16) float smem[];
     float* s_w = smem;                               // [49*CIN][64]
     float* s_x = smem + 49 * CIN * STEM_COUT;        // [PH][PW][CIN]
@@ -84,7 +84,7 @@ stem_conv7x7_kernel(const float* __restrict__ x, const float* __restrict__ w /* 
             uint4 pk;
 #pragma unroll
             for (int t = 0; t < 4; ++t) {
-                const float a0 = fmaxf(acc[8 * o8 + 2 * t], 0.0f), a1 = fmaxf(acc[8 * o8 + 2 * t + 1], 0.0f);
+                const float a0 = fmaxf(acc[8 * o8 + 2 * t], lo), a1 = fmaxf(acc[8 * o8 + 2 * t + 1], lo);   // lo = 0: ReLU
                 if constexpr (sizeof(OT) == 2 && std::is_same<OT, __half>::value)
                     reinterpret_cast<__half2*>(&pk)[t] = __floats2half2_rn(fminf(a0, 65504.0f), fminf(a1, 65504.0f));
                 else
@@ -494,7 +494,7 @@ __global__ void stem_pack_weights_kernel(const float* __restrict__ w, __half* __
 template <int CIN, typename OT>
 __global__ void __launch_bounds__(ST_THREADS)
 stem_tc_kernel(const float* __restrict__ x, const uint4* __restrict__ w_packed, const float* __restrict__ bias,
-               OT* __restrict__ y, int H, int W, int P, int Q) {
+               OT* __restrict__ y, int H, int W, int P, int Q, float lo) {
     extern __shared__ __align__(128) uint8_t tsm[];
     uint8_t* s_a = tsm;
     uint8_t* s_b = tsm + ST_A_BYTES;
@@ -586,8 +586,8 @@ stem_tc_kernel(const float* __restrict__ x, const uint4* __restrict__ w_packed, 
                     const float bb[8] = {b0v.x, b0v.y, b0v.z, b0v.w, b1v.x, b1v.y, b1v.z, b1v.w};
 #pragma unroll
                     for (int t = 0; t < 4; ++t) {
-                        const float a0f = fmaxf(__uint_as_float(v[8 * o8 + 2 * t]) + bb[2 * t], 0.0f);
-                        const float a1f = fmaxf(__uint_as_float(v[8 * o8 + 2 * t + 1]) + bb[2 * t + 1], 0.0f);
+                        const float a0f = fmaxf(__uint_as_float(v[8 * o8 + 2 * t]) + bb[2 * t], lo);      // lo = 0: ReLU
+                        const float a1f = fmaxf(__uint_as_float(v[8 * o8 + 2 * t + 1]) + bb[2 * t + 1], lo);
                         if constexpr (std::is_same<OT, __half>::value)
                             reinterpret_cast<__half2*>(&pk)[t] = __floats2half2_rn(fminf(a0f, 65504.0f), fminf(a1f, 65504.0f));
                         else
@@ -608,7 +608,7 @@ stem_tc_kernel(const float* __restrict__ x, const uint4* __restrict__ w_packed, 
 
 template <int CIN, typename OT>
 static int launch_stem_tc(const float* x, const void* w_packed, const float* bias, void* y, int B, int H, int W, int P, int Q,
-                          cudaStream_t s) {
+                          float lo, cudaStream_t s) {
     auto kern = stem_tc_kernel<CIN, OT>;
     const size_t smem = ST_A_BYTES + ST_B_BYTES + ST_TH * 8 + 16;
     static bool configured = false;
@@ -618,7 +618,7 @@ static int launch_stem_tc(const float* x, const void* w_packed, const float* bia
         configured = true;
     }
     const dim3 grid((Q + ST_TW - 1) / ST_TW, (P + ST_TH - 1) / ST_TH, B);
-    kern<<<grid, ST_THREADS, smem, s>>>(x, (const uint4*)w_packed, bias, (OT*)y, H, W, P, Q);
+    kern<<<grid, ST_THREADS, smem, s>>>(x, (const uint4*)w_packed, bias, (OT*)y, H, W, P, Q, lo);
     return 0;
 }
 
@@ -628,7 +628,7 @@ static int launch_stem_tc(const float* x, const void* w_packed, const float* bia
 using namespace dpft;
 
 template <int CIN, typename OT>
-static int launch_stem(const float* x, const float* w, const float* bias, void* y, int H, int W, int P, int Q, dim3 grid,
+static int launch_stem(const float* x, const float* w, const float* bias, void* y, int H, int W, int P, int Q, float lo, dim3 grid,
                        size_t smem, cudaStream_t s) {
     auto kern = stem_conv7x7_kernel<CIN, OT>;
     static bool configured = false;
@@ -637,7 +637,7 @@ static int launch_stem(const float* x, const float* w, const float* bias, void* 
         if (st) return st;
         configured = true;
     }
-    kern<<<grid, 256, smem, s>>>(x, w, bias, (OT*)y, H, W, P, Q);
+    kern<<<grid, 256, smem, s>>>(x, w, bias, (OT*)y, H, W, P, Q, lo);
     return 0;
 }
 
@@ -653,6 +653,12 @@ extern "C" int dpft_stem_pack_weights(const float* w, void* packed, int Cin, voi
 
 extern "C" int dpft_stem_conv7x7_forward(const float* x, const float* w, const void* w_packed, const float* bias, void* y,
                                          int B, int H, int W, int Cin, int dtype, int impl, void* stream) {
+    return dpft_stem_conv7x7_forward_ex(x, w, w_packed, bias, y, B, H, W, Cin, dtype, impl, 1, stream);
+}
+
+extern "C" int dpft_stem_conv7x7_forward_ex(const float* x, const float* w, const void* w_packed, const float* bias, void* y,
+                                            int B, int H, int W, int Cin, int dtype, int impl, int relu, void* stream) {
+    const float lo = relu ? 0.0f : (dtype == DPFT_F16 ? -65504.0f : -3.0e38f);
     DPFT_REQUIRE(impl != 2 || w_packed, "stem: the tensor-core kernel needs the packed weights (dpft_stem_pack_weights)");
     DPFT_REQUIRE(impl >= 0 && impl <= 2, "stem: impl must be 0 (auto), 1 (CUDA cores) or 2 (tensor cores)");
     DPFT_REQUIRE(x && w && bias && y, "stem: null pointer");
@@ -665,18 +671,18 @@ extern "C" int dpft_stem_conv7x7_forward(const float* x, const float* w, const v
     cudaStream_t s = (cudaStream_t)stream;
     int st;
     if (impl == 2 || (impl == 0 && Q >= 64 && w_packed)) {
-        if (Cin == 3) st = dtype == DPFT_F16 ? launch_stem_tc<3, __half>(x, w_packed, bias, y, B, H, W, P, Q, s)
-                                             : launch_stem_tc<3, __nv_bfloat16>(x, w_packed, bias, y, B, H, W, P, Q, s);
-        else st = dtype == DPFT_F16 ? launch_stem_tc<6, __half>(x, w_packed, bias, y, B, H, W, P, Q, s)
-                                    : launch_stem_tc<6, __nv_bfloat16>(x, w_packed, bias, y, B, H, W, P, Q, s);
+        if (Cin == 3) st = dtype == DPFT_F16 ? launch_stem_tc<3, __half>(x, w_packed, bias, y, B, H, W, P, Q, lo, s)
+                                             : launch_stem_tc<3, __nv_bfloat16>(x, w_packed, bias, y, B, H, W, P, Q, lo, s);
+        else st = dtype == DPFT_F16 ? launch_stem_tc<6, __half>(x, w_packed, bias, y, B, H, W, P, Q, lo, s)
+                                    : launch_stem_tc<6, __nv_bfloat16>(x, w_packed, bias, y, B, H, W, P, Q, lo, s);
         if (st) return st;
         DPFT_LAUNCH_CHECK("stem_tc_kernel");
         return DPFT_OK;
     }
-    if (Cin == 3) st = dtype == DPFT_F16 ? launch_stem<3, __half>(x, w, bias, y, H, W, P, Q, grid, smem, s)
-                                         : launch_stem<3, __nv_bfloat16>(x, w, bias, y, H, W, P, Q, grid, smem, s);
-    else st = dtype == DPFT_F16 ? launch_stem<6, __half>(x, w, bias, y, H, W, P, Q, grid, smem, s)
-                                : launch_stem<6, __nv_bfloat16>(x, w, bias, y, H, W, P, Q, grid, smem, s);
+    if (Cin == 3) st = dtype == DPFT_F16 ? launch_stem<3, __half>(x, w, bias, y, H, W, P, Q, lo, grid, smem, s)
+                                         : launch_stem<3, __nv_bfloat16>(x, w, bias, y, H, W, P, Q, lo, grid, smem, s);
+    else st = dtype == DPFT_F16 ? launch_stem<6, __half>(x, w, bias, y, H, W, P, Q, lo, grid, smem, s)
+                                : launch_stem<6, __nv_bfloat16>(x, w, bias, y, H, W, P, Q, lo, grid, smem, s);
     if (st) return st;
     DPFT_LAUNCH_CHECK("stem_conv7x7_kernel");
     return DPFT_OK;

@@ -78,7 +78,16 @@ __device__ __forceinline__ float column_sum(const float* __restrict__ partials, 
     __shared__ float part[8][33];
     float acc = 0.0f;
     if (col < n) {
-        for (int r = threadIdx.y; r < nparts; r += 8) acc += partials[(size_t)r * n + col];
+        float a0 = 0.0f, a1 = 0.0f, a2 = 0.0f, a3 = 0.0f;                 // four independent loads in flight
+        int r = threadIdx.y;
+        for (; r + 24 < nparts; r += 32) {
+            a0 += partials[(size_t)r * n + col];
+            a1 += partials[(size_t)(r + 8) * n + col];
+            a2 += partials[(size_t)(r + 16) * n + col];
+            a3 += partials[(size_t)(r + 24) * n + col];
+        }
+        for (; r < nparts; r += 8) a0 += partials[(size_t)r * n + col];
+        acc = (a0 + a1) + (a2 + a3);
     }
     part[threadIdx.y][threadIdx.x] = acc;
     __syncthreads();
@@ -296,9 +305,12 @@ __global__ void __launch_bounds__(TB) bn_bwd_apply_kernel(const uint4* __restric
 }
 
 // ---- max-pool 3x3 / stride 2 / pad 1 backward (torch semantics: the whole gradient goes to the first maximum in scan order) ----
+// One thread per input position and 8 channels.  With the pooled output at hand a position only has to look at its <= 4
+// windows (maximum + gradient) and, where it equals the maximum, at the positions that precede it in the window's scan order.
 template <bool F16>
-__global__ void __launch_bounds__(TB) maxpool_bwd_kernel(const uint4* __restrict__ x, const uint4* __restrict__ dy, uint4* __restrict__ dx,
-                                                         int B, int H, int W, int CG, int P, int Q) {
+__global__ void __launch_bounds__(TB) maxpool_bwd_kernel(const uint4* __restrict__ x, const uint4* __restrict__ pooled,
+                                                         const uint4* __restrict__ dy, uint4* __restrict__ dx, int B, int H, int W,
+                                                         int CG, int P, int Q) {
     const long long total = (long long)B * H * W * CG;
     for (long long i = (long long)blockIdx.x * TB + threadIdx.x; i < total; i += (long long)gridDim.x * TB) {
         const int cg = (int)(i % CG);
@@ -312,39 +324,38 @@ __global__ void __launch_bounds__(TB) maxpool_bwd_kernel(const uint4* __restrict
 #pragma unroll
         for (int k = 0; k < 8; ++k) acc[k] = 0.0f;
         // windows (p, q) that contain (h, w): 2p - 1 <= h <= 2p + 1
-        const int p_lo = max((h - 1 + 1) / 2, 0), p_hi = min((h + 1) / 2, P - 1);
-        const int q_lo = max((w - 1 + 1) / 2, 0), q_hi = min((w + 1) / 2, Q - 1);
+        const int p_lo = h / 2, p_hi = min((h + 1) / 2, P - 1);
+        const int q_lo = w / 2, q_hi = min((w + 1) / 2, Q - 1);
         for (int p = p_lo; p <= p_hi; ++p) {
             for (int q = q_lo; q <= q_hi; ++q) {
-                // first maximum of the window in (row, column) scan order; position index of (h, w) in that order
-                float best[8];
-                int best_pos[8];
+                const long long o = (((long long)b * P + p) * Q + q) * CG + cg;
+                float mx[8], g[8];
+                unpack8<F16>(__ldg(pooled + o), mx);
+                unpack8<F16>(__ldg(dy + o), g);
+                bool win[8];
+                bool any = false;
 #pragma unroll
-                for (int k = 0; k < 8; ++k) { best[k] = -INFINITY; best_pos[k] = -1; }
-                int my_pos = -1;
-                for (int r = 0; r < 3; ++r) {
-                    const int hh = 2 * p - 1 + r;
-                    if (hh < 0 || hh >= H) continue;
-                    for (int s = 0; s < 3; ++s) {
-                        const int ww = 2 * q - 1 + s;
-                        if (ww < 0 || ww >= W) continue;
-                        const int pos = r * 3 + s;
-                        if (hh == h && ww == w) my_pos = pos;
-                        float v[8];
-                        unpack8<F16>(__ldg(x + (((long long)b * H + hh) * W + ww) * CG + cg), v);
+                for (int k = 0; k < 8; ++k) { win[k] = own[k] == mx[k]; any |= win[k]; }
+                if (any) {
+                    const int r_me = h - (2 * p - 1), s_me = w - (2 * q - 1);
+                    for (int r = 0; r <= r_me; ++r) {
+                        const int hh = 2 * p - 1 + r;
+                        if (hh < 0) continue;
+                        const int s_end = r < r_me ? 3 : s_me;               // positions strictly before (r_me, s_me)
+                        for (int sx = 0; sx < s_end; ++sx) {
+                            const int ww = 2 * q - 1 + sx;
+                            if (ww < 0 || ww >= W) continue;
+                            float v[8];
+                            unpack8<F16>(__ldg(x + (((long long)b * H + hh) * W + ww) * CG + cg), v);
 #pragma unroll
-                        for (int k = 0; k < 8; ++k) {
-                            if (v[k] > best[k] || best_pos[k] < 0) { best[k] = v[k]; best_pos[k] = pos; }
+                            for (int k = 0; k < 8; ++k) win[k] = win[k] && v[k] != mx[k];
                         }
                     }
-                }
-                float g[8];
-                unpack8<F16>(__ldg(dy + (((long long)b * P + p) * Q + q) * CG + cg), g);
 #pragma unroll
-                for (int k = 0; k < 8; ++k) acc[k] += (best_pos[k] == my_pos) ? g[k] : 0.0f;
+                    for (int k = 0; k < 8; ++k) acc[k] += win[k] ? g[k] : 0.0f;
+                }
             }
         }
-        (void)own;
         dx[i] = pack8<F16>(acc);
     }
 }
@@ -424,6 +435,98 @@ __global__ void __launch_bounds__(TB) unpack_wgrad_kernel(const PackEntry* __res
         const float g = __ldg(e.src + (((long long)co * e.R + r) * e.S + s) * e.Cin + ci);
         reinterpret_cast<float*>(e.fwd)[i - e.offset] += g;
     }
+}
+
+
+// ---- stem (conv 7x7 / stride 2 / pad 3, Cin = 3 | 6) weight gradient on the CUDA cores ---------------------------------
+//   dw[r][s][c][o] += sum_{b,p,q} dy[b,p,q,o] * x[b, 2p-3+r, 2q-3+s, c]          (same [7][7][Cin][64] layout as the forward)
+// Persistent CTAs walk 8x32-pixel output tiles: the dy tile (16-bit) and the fp32 input patch are staged in shared memory;
+// thread (r, o) keeps the 7*Cin gradients of filter row r / output channel o in registers: per pixel one dy value and one
+// contiguous 7*Cin-float input segment (a warp shares r, so the segment loads are broadcasts).  Each CTA writes its
+// partial gradient once; stem_wgrad_reduce_kernel adds the rows into dw.  (K = pixels with 3 input channels does not map
+// onto the im2col TMA path: the inner dimension is 12 bytes.)
+constexpr int SW_TP = 8, SW_TQ = 32, SW_THREADS = 448, SW_ROWS = 2 * SW_TP + 5, SW_COLS = 2 * SW_TQ + 5;
+template <int CIN> struct SwLayout {
+    static constexpr int kRowF = ((SW_COLS * CIN + 3) / 4) * 4 + (CIN == 3 ? 0 : 0);     // 208 (Cin 3) / 416 (Cin 6) floats
+    static constexpr int kDyBytes = SW_TP * SW_TQ * 64 * 2;
+    static constexpr int kXBytes = SW_ROWS * kRowF * 4;
+    static constexpr int kTotal = kDyBytes + kXBytes;
+};
+
+template <int CIN, bool F16>
+__global__ void __launch_bounds__(SW_THREADS, CIN == 3 ? 2 : 1)
+stem_wgrad_kernel(const float* __restrict__ x, const uint16_t* __restrict__ dy, float* __restrict__ partials, int B, int H, int W,
+                  int P, int Q) {
+    using L = SwLayout<CIN>;
+    constexpr int NJ = 7 * CIN;                    // gradients per thread
+    constexpr int VEC = CIN == 3 ? 2 : 4;          // floats per shared-memory load of the input segment
+    constexpr int NV = (NJ + VEC - 1) / VEC;
+    extern __shared__ __align__(16) uint8_t sw_smem[];
+    uint16_t* s_dy = reinterpret_cast<uint16_t*>(sw_smem);
+    float* s_x = reinterpret_cast<float*>(sw_smem + L::kDyBytes);
+    const int tid = threadIdx.x;
+    const int r = tid >> 6, o = tid & 63;
+    const int tiles_q = (Q + SW_TQ - 1) / SW_TQ, tiles_p = (P + SW_TP - 1) / SW_TP;
+    const int n_tiles = B * tiles_p * tiles_q;
+    float acc[NV * VEC];
+#pragma unroll
+    for (int j = 0; j < NV * VEC; ++j) acc[j] = 0.0f;
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const int b = tile / (tiles_p * tiles_q);
+        const int rem = tile - b * tiles_p * tiles_q;
+        const int p0 = (rem / tiles_q) * SW_TP, q0 = (rem % tiles_q) * SW_TQ;
+        __syncthreads();                           // the previous tile has been consumed
+        for (int i = tid; i < SW_TP * SW_TQ * 8; i += SW_THREADS) {
+            const int px = i >> 3, part = i & 7;
+            const int p = p0 + (px >> 5), q = q0 + (px & 31);
+            uint4 v = make_uint4(0, 0, 0, 0);
+            if (p < P && q < Q) v = ld_stream(dy + (((long long)b * P + p) * Q + q) * 64 + part * 8);
+            reinterpret_cast<uint4*>(s_dy)[i] = v;
+        }
+        const int h0 = 2 * p0 - 3, w0 = 2 * q0 - 3;
+        for (int i = tid; i < SW_ROWS * L::kRowF; i += SW_THREADS) {
+            const int rr = i / L::kRowF, j = i - rr * L::kRowF;
+            const int h = h0 + rr, w = w0 + j / CIN;
+            float v = 0.0f;
+            if (j < SW_COLS * CIN && h >= 0 && h < H && w >= 0 && w < W) v = __ldg(x + ((long long)b * H + h) * W * CIN + (long long)w0 * CIN + j);
+            s_x[i] = v;
+        }
+        __syncthreads();
+#pragma unroll 2
+        for (int px = 0; px < SW_TP * SW_TQ; ++px) {
+            const int pl = px >> 5, ql = px & 31;
+            const uint16_t raw = s_dy[px * 64 + o];
+            const float d = F16 ? __half2float(__ushort_as_half(raw)) : __bfloat162float(__ushort_as_bfloat16(raw));
+            const float* seg = s_x + (2 * pl + r) * L::kRowF + 2 * ql * CIN;
+            if constexpr (VEC == 2) {
+#pragma unroll
+                for (int v = 0; v < NV; ++v) {
+                    const float2 f = *reinterpret_cast<const float2*>(seg + 2 * v);
+                    acc[2 * v] = fmaf(d, f.x, acc[2 * v]);
+                    acc[2 * v + 1] = fmaf(d, f.y, acc[2 * v + 1]);
+                }
+            } else {
+#pragma unroll
+                for (int v = 0; v < NV; ++v) {
+                    const float4 f = *reinterpret_cast<const float4*>(seg + 4 * v);
+                    acc[4 * v] = fmaf(d, f.x, acc[4 * v]);
+                    acc[4 * v + 1] = fmaf(d, f.y, acc[4 * v + 1]);
+                    acc[4 * v + 2] = fmaf(d, f.z, acc[4 * v + 2]);
+                    acc[4 * v + 3] = fmaf(d, f.w, acc[4 * v + 3]);
+                }
+            }
+        }
+    }
+    float* row = partials + (size_t)blockIdx.x * 49 * CIN * 64;
+#pragma unroll
+    for (int j = 0; j < NJ; ++j) row[(r * NJ + j) * 64 + o] = acc[j];
+}
+
+// out[col] += sum over rows of partials[row][col]; blockDim = (32, 8)
+__global__ void rows_sum_add_kernel(const float* __restrict__ partials, int nparts, int n, float* __restrict__ out) {
+    const int col = blockIdx.x * 32 + threadIdx.x;
+    const float tot = column_sum(partials, nparts, n, col);
+    if (col < n && threadIdx.y == 0) out[col] += tot;
 }
 
 int grid_for(long long n, int sms) {
@@ -526,14 +629,15 @@ extern "C" int dpft_bn_backward_apply(const void* dz, const void* z, const void*
     return DPFT_OK;
 }
 
-extern "C" int dpft_maxpool3x3s2_backward(const void* x, const void* dy, void* dx, int B, int H, int W, int C, int dtype, void* stream) {
+extern "C" int dpft_maxpool3x3s2_backward(const void* x, const void* pooled, const void* dy, void* dx, int B, int H, int W, int C,
+                                          int dtype, void* stream) {
     DPFT_REQUIRE_16BIT("maxpool_backward");
-    DPFT_REQUIRE(x && dy && dx && B > 0 && H > 0 && W > 0 && C % 8 == 0, "maxpool_backward: bad arguments");
+    DPFT_REQUIRE(x && pooled && dy && dx && B > 0 && H > 0 && W > 0 && C % 8 == 0, "maxpool_backward: bad arguments");
     const int P = (H - 1) / 2 + 1, Q = (W - 1) / 2 + 1;
     const long long total = (long long)B * H * W * (C / 8);
     const int grid = grid_for(total, sm_count());
-    if (is_f16) maxpool_bwd_kernel<true><<<grid, TB, 0, (cudaStream_t)stream>>>((const uint4*)x, (const uint4*)dy, (uint4*)dx, B, H, W, C / 8, P, Q);
-    else maxpool_bwd_kernel<false><<<grid, TB, 0, (cudaStream_t)stream>>>((const uint4*)x, (const uint4*)dy, (uint4*)dx, B, H, W, C / 8, P, Q);
+    if (is_f16) maxpool_bwd_kernel<true><<<grid, TB, 0, (cudaStream_t)stream>>>((const uint4*)x, (const uint4*)pooled, (const uint4*)dy, (uint4*)dx, B, H, W, C / 8, P, Q);
+    else maxpool_bwd_kernel<false><<<grid, TB, 0, (cudaStream_t)stream>>>((const uint4*)x, (const uint4*)pooled, (const uint4*)dy, (uint4*)dx, B, H, W, C / 8, P, Q);
     DPFT_LAUNCH_CHECK("maxpool_bwd_kernel");
     return DPFT_OK;
 }
@@ -562,5 +666,38 @@ extern "C" int dpft_unpack_conv_wgrads(const void* table, int n_layers, long lon
     DPFT_REQUIRE(table && n_layers > 0 && total > 0, "unpack_conv_wgrads: bad arguments");
     unpack_wgrad_kernel<<<grid_for(total, sm_count()), TB, 0, (cudaStream_t)stream>>>((const PackEntry*)table, n_layers, total);
     DPFT_LAUNCH_CHECK("unpack_wgrad_kernel");
+    return DPFT_OK;
+}
+
+extern "C" int dpft_stem_conv7x7_wgrad(const float* x, const void* dy, float* workspace, long long workspace_floats, float* dw, int B,
+                                       int H, int W, int Cin, int dtype, void* stream) {
+    DPFT_REQUIRE_16BIT("stem_wgrad");
+    DPFT_REQUIRE(x && dy && workspace && dw && B > 0 && H > 0 && W > 0, "stem_wgrad: bad arguments");
+    DPFT_REQUIRE(Cin == 3 || Cin == 6, "stem_wgrad: Cin=%d (3 or 6 supported)", Cin);
+    const int P = (H - 1) / 2 + 1, Q = (W - 1) / 2 + 1;
+    const int n = 49 * Cin * 64;
+    const int tiles = B * ((P + SW_TP - 1) / SW_TP) * ((Q + SW_TQ - 1) / SW_TQ);
+    int grid = sm_count() * (Cin == 3 ? 2 : 1);
+    if (grid > tiles) grid = tiles;
+    DPFT_REQUIRE(workspace_floats >= (long long)grid * n, "stem_wgrad: workspace of %lld floats, need %lld", workspace_floats, (long long)grid * n);
+    cudaStream_t s = (cudaStream_t)stream;
+#define DPFT_SW_LAUNCH(CIN, F16)                                                                                              \
+    do {                                                                                                                      \
+        auto kern = stem_wgrad_kernel<CIN, F16>;                                                                              \
+        static bool configured = false;                                                                                       \
+        if (!configured) {                                                                                                    \
+            int st = cuda_status(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SwLayout<CIN>::kTotal), \
+                                 "cudaFuncSetAttribute(stem_wgrad_kernel)");                                                  \
+            if (st) return st;                                                                                                \
+            configured = true;                                                                                                \
+        }                                                                                                                     \
+        kern<<<grid, SW_THREADS, SwLayout<CIN>::kTotal, s>>>(x, (const uint16_t*)dy, workspace, B, H, W, P, Q);               \
+    } while (0)
+    if (Cin == 3) { if (is_f16) DPFT_SW_LAUNCH(3, true); else DPFT_SW_LAUNCH(3, false); }
+    else { if (is_f16) DPFT_SW_LAUNCH(6, true); else DPFT_SW_LAUNCH(6, false); }
+#undef DPFT_SW_LAUNCH
+    DPFT_LAUNCH_CHECK("stem_wgrad_kernel");
+    rows_sum_add_kernel<<<(n + 31) / 32, dim3(32, 8), 0, s>>>(workspace, grid, n, dw);
+    DPFT_LAUNCH_CHECK("rows_sum_add_kernel");
     return DPFT_OK;
 }

@@ -107,7 +107,9 @@ class Backbone(nn.Module):
         self.body = ResNetBody(arch, multi_scale, _norm(norm_layer))
         self.native_train = False             # train(): run layer1.. through the sm_100a training kernels (16-bit activations)
         self.train_dtype = torch.float16      # float16 (gradients carried with a power-of-two scale) or bfloat16
+        self.native_stem = True               # ... and the stem (conv 7x7 + bn1 + relu + max-pool) as well
         self._stages = None
+        self._stem = None
         if weights:
             self._load_weights(name, weights)
 
@@ -131,6 +133,7 @@ class Backbone(nn.Module):
     def __getstate__(self):            # torch.save(model) must not pickle the device-side launch plan
         state = self.__dict__.copy()
         state["_stages"] = None
+        state["_stem"] = None
         return state
 
     def _native_stages(self):
@@ -145,13 +148,20 @@ class Backbone(nn.Module):
         return self._stages
 
     def forward_native_train(self, batch: torch.Tensor, stages) -> "OrderedDict[str, torch.Tensor]":
-        """Stem through torch autograd, layer1.. as one native autograd node; same outputs as ``forward`` (fp32)."""
-        from ..train_backbone import stages_forward
-        x = batch.movedim(-1, 1) if self.channel_last else batch
-        body = self.body
-        x = F.relu(body.bn1(body.conv1(self.adjustment_layer(x))))
-        x = F.max_pool2d(x, kernel_size=3, stride=2, padding=1)
-        outs = stages_forward(stages, x.permute(0, 2, 3, 1))
+        """The whole backbone as one native autograd node (stem through torch autograd when the stem kernels do not cover
+        it, or when the raw input itself needs a gradient); same outputs as ``forward`` (fp32)."""
+        from ..train_backbone import NativeStem, backbone_forward, stages_forward
+        if self.native_stem and not batch.requires_grad and NativeStem.ineligible_reason(self) is None:
+            x = batch if self.channel_last else batch.movedim(1, -1)
+            if self._stem is None or self._stem.dtype != self.train_dtype or self._stem.zero_bias.device != x.device:
+                self._stem = NativeStem(self, self.train_dtype)
+            outs = backbone_forward(stages, self._stem, x)
+        else:
+            x = batch.movedim(-1, 1) if self.channel_last else batch
+            body = self.body
+            x = F.relu(body.bn1(body.conv1(self.adjustment_layer(x))))
+            x = F.max_pool2d(x, kernel_size=3, stride=2, padding=1)
+            outs = stages_forward(stages, x.permute(0, 2, 3, 1))
         feats = OrderedDict((str(i + 1), o) for i, o in enumerate(outs))
         if not self.channel_last:
             feats = OrderedDict((k, v.movedim(-1, 1)) for k, v in feats.items())

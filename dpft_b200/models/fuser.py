@@ -71,6 +71,7 @@ class MSDeformAttn(nn.Module):
         self.attention_weights = nn.Linear(d_model, n_heads * n_levels * n_points)
         self.value_proj = nn.Linear(d_model, d_model)
         self.output_proj = nn.Linear(d_model, d_model)
+        self.gather_then_project = True      # composed path: project the sampled features instead of all S positions
         self._reset_parameters()
 
     def _reset_parameters(self) -> None:
@@ -112,14 +113,41 @@ class MSDeformAttn(nn.Module):
         if not (reference_points.shape[2] == input_spatial_shapes.shape[0] == input_level_start_index.shape[0]
                 == self.n_levels):
             raise AssertionError("reference_points / spatial_shapes / level_start_index do not match n_levels")
+        loc, aw = self.sampling(query, reference_points, input_spatial_shapes)
+        if self.gather_then_project and input_padding_mask is None:
+            return self.output_proj(self._gather_then_project(input_flatten, input_spatial_shapes, input_level_start_index,
+                                                              loc, aw))
         value = self.value_proj(input_flatten)
         if input_padding_mask is not None:
             value = value.masked_fill(input_padding_mask[..., None], 0.0)
         value = value.view(B, S, self.n_heads, self.d_model // self.n_heads)
-        loc, aw = self.sampling(query, reference_points, input_spatial_shapes)
         out = msda_ops.MSDeformAttnFunction.apply(value, input_spatial_shapes, input_level_start_index, loc, aw,
                                                   self.im2col_step)
         return self.output_proj(out)
+
+    def _gather_then_project(self, x, shapes_t, lsi_t, loc, aw):
+        """Same result as sampling ``value_proj(x)`` (ms_deform_attn.py:172 then :206-214), without the dense pass over all
+        S positions and its weight-gradient reduction over B*S rows: sampling is linear, so
+            out[b,q,m,:] = Wv[m] @ G[b,q,m,:] + bv[m] * mass[b,q,m]
+        with G = the attention-weighted bilinear samples of the UNPROJECTED features (one launch of the op: the M heads
+        become extra queries over a single shared 'head' of all C channels) and mass = the attention-weighted sum of the
+        in-bounds bilinear weights (zero padding drops the bias where a corner falls outside)."""
+        B, S, C = x.shape
+        _, N, M, L, P, _ = loc.shape
+        D = self.d_model // M
+        G = msda_ops.MSDeformAttnFunction.apply(x.reshape(B, S, 1, C), shapes_t, lsi_t, loc.reshape(B, N * M, 1, L, P, 2),
+                                                aw.reshape(B, N * M, 1, L, P), self.im2col_step).view(B, N, M, C)
+        wh = shapes_t.to(loc.dtype).flip(-1).view(1, 1, 1, L, 1, 2)            # (W, H) per level
+        pix = loc * wh - 0.5
+        lo = torch.floor(pix)
+        frac = pix - lo
+        inb0 = ((lo >= 0) & (lo <= wh - 1)).to(loc.dtype)                      # corner lo inside the map
+        inb1 = ((lo + 1 >= 0) & (lo + 1 <= wh - 1)).to(loc.dtype)              # corner lo + 1 inside the map
+        axis = (1 - frac) * inb0 + frac * inb1                                 # in-bounds weight along x and y
+        mass = (aw * axis[..., 0] * axis[..., 1]).sum((-1, -2))                # (B, N, M)
+        wv = self.value_proj.weight.view(M, D, C)
+        out = torch.einsum("bnmc,mdc->bnmd", G, wv) + self.value_proj.bias.view(1, 1, M, D) * mass.unsqueeze(-1)
+        return out.reshape(B, N, M * D)
 
 
 class MLFusion(nn.Module):

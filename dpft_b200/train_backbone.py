@@ -187,21 +187,96 @@ class NativeStages:
 GRAD_TARGET_AMAX = 64.0      # f16 gradients: the incoming gradients are scaled so that their largest element is ~2^6
 
 
-class _StagesFn(torch.autograd.Function):
+class NativeStem:
+    """[adjustment 1x1 (radar, C -> 3) folded into] conv1 7x7/2 -> bn1 (batch statistics) -> ReLU -> max-pool, forward and
+    backward (reference src/dprt/models/backbones/resnet.py:98-101 in train()).  The input needs no gradient; the adjustment
+    layer is linear and bias-free, so the kernels see the composed 7x7 weight W'[o,c] = sum_k W1[o,k] A[k,c] and the chain
+    rule back to W1 and A is two small einsums on the 7x7 gradient."""
+
+    @staticmethod
+    def ineligible_reason(backbone) -> Optional[str]:
+        if backbone.in_channels not in (3, 6):
+            return f"in_channels={backbone.in_channels}"
+        adj = backbone.adjustment_layer
+        if backbone.in_channels != 3 and not (isinstance(adj, nn.Conv2d) and adj.kernel_size == (1, 1) and adj.bias is None):
+            return "adjustment layer is not a bias-free 1x1 convolution"
+        c1 = backbone.body.conv1
+        if c1.kernel_size != (7, 7) or c1.stride != (2, 2) or c1.padding != (3, 3) or c1.bias is not None or c1.weight.shape[0] != 64:
+            return "stem is not conv 7x7 / stride 2 / pad 3 -> 64"
+        return None
+
+    def __init__(self, backbone, dtype: torch.dtype):
+        self.backbone, self.dtype = backbone, dtype
+        self.cin = backbone.in_channels
+        self.zero_bias = torch.zeros(64, dtype=torch.float32, device=backbone.body.conv1.weight.device)
+
+    def parameters(self) -> List[torch.Tensor]:
+        body = self.backbone.body
+        ps = [body.conv1.weight, body.bn1.weight, body.bn1.bias]
+        if self.cin != 3:
+            ps.append(self.backbone.adjustment_layer.weight)
+        return ps
+
+    def _composed_weight(self) -> torch.Tensor:
+        w1 = self.backbone.body.conv1.weight.detach()                       # (64, 3, 7, 7)
+        if self.cin == 3:
+            return w1.permute(2, 3, 1, 0).contiguous()                      # [7][7][3][64]
+        a = self.backbone.adjustment_layer.weight.detach()[:, :, 0, 0]      # (3, Cin)
+        return torch.einsum("okrs,kc->rsco", w1, a).contiguous()
+
+    def forward(self, x: torch.Tensor):
+        from . import features as Fe
+        bn = self.backbone.body.bn1
+        w = self._composed_weight()
+        y0 = Fe.stem_forward(x, w, self.zero_bias, self.dtype, w_packed=Fe.stem_pack_weights(w), relu=False)
+        z0, s0 = T.bn_forward(y0, bn.weight, bn.bias, bn.running_mean, bn.running_var, bn.momentum, bn.eps, True)
+        if bn.num_batches_tracked is not None:
+            bn.num_batches_tracked.add_(1)
+        pooled = Fe.maxpool_forward(z0)
+        return pooled, (x, y0, z0, s0, pooled)
+
+    def backward(self, tape, dpooled: torch.Tensor):
+        """-> (gradients in ``parameters()`` order, flat buffers that carry the gradient scale)."""
+        x, y0, z0, s0, pooled = tape
+        bn = self.backbone.body.bn1
+        dz0 = T.maxpool_backward(z0, pooled, dpooled)
+        bng = torch.zeros(2, 64, dtype=torch.float32, device=x.device)
+        dy0, _ = T.bn_backward(dz0, z0, y0, s0, bn.weight, True, bng[0], bng[1])
+        dw = T.stem_wgrad(x, dy0)                                           # [7][7][Cin][64]
+        return dw, bng
+
+    def chain_to_parameters(self, dw: torch.Tensor, bng: torch.Tensor) -> List[torch.Tensor]:
+        if self.cin == 3:
+            return [dw.permute(3, 2, 0, 1), bng[0], bng[1]]
+        w1 = self.backbone.body.conv1.weight.detach()
+        a = self.backbone.adjustment_layer.weight.detach()[:, :, 0, 0]
+        dw1 = torch.einsum("rsco,kc->okrs", dw, a)
+        da = torch.einsum("rsco,okrs->kc", dw, w1)
+        return [dw1, bng[0], bng[1], da[:, :, None, None]]
+
+
+class _BackboneFn(torch.autograd.Function):
     """fp32 in / fp32 out at the autograd boundary; 16-bit inside.  With f16 the activation gradients are carried with a
     power-of-two scale S (computed on the device from the incoming gradients, no host sync) so that they stay inside
     f16's exponent range; every backward kernel is linear in the gradient, so the parameter gradients and the input
-    gradient are multiplied by 1/S at the end."""
+    gradient are multiplied by 1/S at the end.
+
+    ``stem`` given: x is the raw input (B,H,W,Cin) fp32 (no gradient) and the node covers the whole backbone;
+    otherwise x is the max-pooled stem output (B,h,w,64) fp32 computed (and differentiated) by torch."""
 
     @staticmethod
-    def forward(ctx, runner: NativeStages, x: torch.Tensor, *params):
-        outs, tape = runner.forward(x.to(runner.dtype).contiguous())
-        ctx.runner, ctx.tape = runner, tape
+    def forward(ctx, runner: NativeStages, stem: Optional[NativeStem], x: torch.Tensor, *params):
+        if stem is not None:
+            pooled, stem_tape = stem.forward(x.contiguous())
+        else:
+            pooled, stem_tape = x.to(runner.dtype).contiguous(), None
+        outs, tape = runner.forward(pooled)
+        ctx.runner, ctx.stem, ctx.tape, ctx.stem_tape = runner, stem, tape, stem_tape
         return tuple(o.float() for o in outs)
 
     @staticmethod
     def backward(ctx, *grad_outs):
-        runner = ctx.runner
+        runner, stem = ctx.runner, ctx.stem
         scale = None
         if runner.dtype == torch.float16:
             amax = torch.stack([g.abs().max() for g in grad_outs if g is not None]).max()
@@ -209,17 +284,32 @@ class _StagesFn(torch.autograd.Function):
             gos = [None if g is None else (g * scale).to(runner.dtype).contiguous() for g in grad_outs]
         else:
             gos = [None if g is None else g.to(runner.dtype).contiguous() for g in grad_outs]
-        dx, grads, flats = runner.backward(ctx.tape, gos)
+        dpooled, grads, flats = runner.backward(ctx.tape, gos)
         ctx.tape = None
-        dx = dx.float()
+        flats = list(flats)
+        stem_flats = None
+        if stem is not None:
+            stem_flats = stem.backward(ctx.stem_tape, dpooled)
+            ctx.stem_tape = None
+            flats += list(stem_flats)
+            dx = None
+        else:
+            dx = dpooled.float()
         if scale is not None:
             inv = 1.0 / scale
-            dx = dx * inv
+            if dx is not None:
+                dx = dx * inv
             for f in flats:
                 f.mul_(inv)
-        return (None, dx, *grads)
+        stem_grads = stem.chain_to_parameters(*stem_flats) if stem is not None else []
+        return (None, None, dx, *stem_grads, *grads)
 
 
 def stages_forward(runner: NativeStages, pooled: torch.Tensor) -> Tuple[torch.Tensor, ...]:
     """pooled (B,H,W,64) fp32 NHWC (autograd-tracked) -> tuple of stage outputs (B,h,w,C) fp32 NHWC."""
-    return _StagesFn.apply(runner, pooled, *runner.parameters())
+    return _BackboneFn.apply(runner, None, pooled, *runner.parameters())
+
+
+def backbone_forward(runner: NativeStages, stem: NativeStem, x: torch.Tensor) -> Tuple[torch.Tensor, ...]:
+    """x (B,H,W,Cin) fp32 raw input -> tuple of stage outputs (B,h,w,C) fp32 NHWC; the whole backbone is one autograd node."""
+    return _BackboneFn.apply(runner, stem, x, *stem.parameters(), *runner.parameters())

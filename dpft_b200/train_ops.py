@@ -155,12 +155,33 @@ def bn_backward(dz: torch.Tensor, z: Optional[torch.Tensor], y: torch.Tensor, st
     return dy, g
 
 
-def maxpool_backward(x: torch.Tensor, dy: torch.Tensor) -> torch.Tensor:
-    _check16(x, dy)
+def stem_wgrad(x: torch.Tensor, dy: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """x (B,H,W,Cin) fp32, dy (B,P,Q,64) 16-bit -> fp32 [7][7][Cin][64], ADDED into ``out`` (zeros if not given)."""
+    _check16(dy)
+    native.require_cuda(x)
+    if x.dtype != torch.float32 or not x.is_contiguous():
+        raise RuntimeError("stem_wgrad: x must be a contiguous fp32 tensor")
+    B, H, W, Cin = x.shape
+    if out is None:
+        out = torch.zeros((7, 7, Cin, 64), dtype=torch.float32, device=x.device)
+    n = 49 * Cin * 64
+    sms = torch.cuda.get_device_properties(x.device).multi_processor_count
+    ws = torch.empty(2 * sms * n, dtype=torch.float32, device=x.device)
+    with torch.cuda.device(x.device):
+        st = _lib().dpft_stem_conv7x7_wgrad(native.ptr(x), native.ptr(dy), native.ptr(ws), ws.numel(), native.ptr(out), B, H, W, Cin,
+                                            native.dtype_code(dy), native.stream_ptr(x.device))
+    native.check(st, "dpft_stem_conv7x7_wgrad")
+    native.count_launch(2)
+    return out
+
+
+def maxpool_backward(x: torch.Tensor, pooled: torch.Tensor, dy: torch.Tensor) -> torch.Tensor:
+    """x (B,H,W,C) input of the 3x3/2 max-pool, pooled (B,P,Q,C) its output, dy (B,P,Q,C) -> dx (B,H,W,C)."""
+    _check16(x, pooled, dy)
     B, H, W, C = x.shape
     dx = torch.empty_like(x)
     with torch.cuda.device(x.device):
-        st = _lib().dpft_maxpool3x3s2_backward(native.ptr(x), native.ptr(dy), native.ptr(dx), B, H, W, C, native.dtype_code(x),
+        st = _lib().dpft_maxpool3x3s2_backward(native.ptr(x), native.ptr(pooled), native.ptr(dy), native.ptr(dx), B, H, W, C, native.dtype_code(x),
                                                native.stream_ptr(x.device))
     native.check(st, "dpft_maxpool3x3s2_backward")
     native.count_launch()

@@ -107,6 +107,9 @@ DPFT_API int dpft_conv2d_nhwc(const void* x, const void* w, const float* bias, c
  */
 DPFT_API int dpft_stem_conv7x7_forward(const float* x, const float* w, const void* w_packed, const float* bias, void* y,
                                        int B, int H, int W, int Cin, int dtype, int impl, void* stream);
+/* Same with the ReLU optional (relu = 0: y = conv + bias, the pre-BatchNorm activation the training path stores). */
+DPFT_API int dpft_stem_conv7x7_forward_ex(const float* x, const float* w, const void* w_packed, const float* bias, void* y,
+                                          int B, int H, int W, int Cin, int dtype, int impl, int relu, void* stream);
 /* w [7][7][Cin][64] f32 -> the 57344-byte f16 operand image the tcgen05 stem kernel stages (done once per model). */
 DPFT_API int dpft_stem_pack_weights(const float* w, void* packed, int Cin, void* stream);
 
@@ -239,9 +242,15 @@ DPFT_API int dpft_bn_backward_apply(const void* dz, const void* z, const void* y
                                     const float* gamma, const float* sum_g, const float* sum_gx, void* dy, void* g_out,
                                     long long M, int C, int relu, int dtype, void* stream);
 
-/* Backward of dpft_maxpool3x3s2_nhwc: x (B, H, W, C) is the pooled input, dy (B, P, Q, C); the gradient of a window goes to its
- * first maximum in (row, column) order, as torch.nn.functional.max_pool2d does. */
-DPFT_API int dpft_maxpool3x3s2_backward(const void* x, const void* dy, void* dx, int B, int H, int W, int C, int dtype, void* stream);
+/* Weight gradient of the stem (dpft_stem_conv7x7_forward): dw [7][7][Cin][64] f32 += sum dy[b,p,q,o] * x[b,2p-3+r,2q-3+s,c];
+ * x (B, H, W, Cin) f32, dy (B, P, Q, 64) 16-bit; workspace >= 2 * sm_count * 49*Cin*64 floats (per-CTA partial gradients). */
+DPFT_API int dpft_stem_conv7x7_wgrad(const float* x, const void* dy, float* workspace, long long workspace_floats, float* dw, int B,
+                                     int H, int W, int Cin, int dtype, void* stream);
+
+/* Backward of dpft_maxpool3x3s2_nhwc: x (B, H, W, C) is the input of the pooling, pooled (B, P, Q, C) its output, dy (B, P, Q, C);
+ * the gradient of a window goes to its first maximum in (row, column) order, as torch.nn.functional.max_pool2d does. */
+DPFT_API int dpft_maxpool3x3s2_backward(const void* x, const void* pooled, const void* dy, void* dx, int B, int H, int W, int C,
+                                        int dtype, void* stream);
 
 /* up[b, 2p, 2q, :] = src[b, p, q, :], zero elsewhere; src (B, P, Q, C), up (B, H, W, C), 16-bit, C % 8 == 0. */
 DPFT_API int dpft_zero_insert2_nhwc(const void* src, void* up, int B, int H, int W, int C, int P, int Q, void* stream);

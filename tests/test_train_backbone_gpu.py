@@ -33,9 +33,9 @@ def _rel(a, b):
     return float((a - b).norm() / b.norm().clamp_min(1e-30))
 
 
-@pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16])
+@pytest.mark.parametrize("dtype,native_stem", [(torch.float16, True), (torch.float16, False), (torch.bfloat16, True)])
 @pytest.mark.parametrize("arch,cin,size", SIZES)
-def test_native_stages_match_torch_autograd(arch, cin, size, dtype):
+def test_native_stages_match_torch_autograd(arch, cin, size, dtype, native_stem):
     """Yardstick: the same module through cuDNN with TF32 convolutions (PyTorch's default, i.e. what the reference's own
     GPU training computes; 10-bit mantissa like float16).  These randomly initialised train-mode networks amplify any
     rounding by 3-5x per stage (cuDNN-TF32 itself is 60-90 % off the fp32 gradients at full depth), so the bound is
@@ -53,6 +53,7 @@ def test_native_stages_match_torch_autograd(arch, cin, size, dtype):
     nat = copy.deepcopy(ref)
     nat.native_train = True
     nat.train_dtype = dtype
+    nat.native_stem = native_stem
     B, H, W = size
     x = torch.rand(B, H, W, cin, device=DEV) * 255
 
@@ -64,6 +65,7 @@ def test_native_stages_match_torch_autograd(arch, cin, size, dtype):
     torch.backends.cudnn.allow_tf32 = False
     out_nat, g_nat = _run(nat, x)
     assert nat._stages is not None and nat._stages.dtype == dtype, "the native training plan was not built"
+    assert (nat._stem is not None) == native_stem
 
     for k in out_ref:
         assert out_nat[k].shape == out_ref[k].shape

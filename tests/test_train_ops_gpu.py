@@ -137,10 +137,46 @@ def test_maxpool_backward_matches_torch(shape):
     out = F.max_pool2d(xf, 3, 2, 1)
     out.backward(dy.float().permute(0, 3, 1, 2))
     assert torch.equal(features.maxpool_forward(x).float(), out.detach().permute(0, 2, 3, 1))
-    got = train_ops.maxpool_backward(x, dy)
+    got = train_ops.maxpool_backward(x, features.maxpool_forward(x), dy)
     torch.cuda.synchronize()
     want = xf.grad.permute(0, 2, 3, 1)
     assert (got.float() - want).abs().max().item() <= 2.0 ** -7 * want.abs().max().item()
+
+
+@pytest.mark.parametrize("cin,shape", [(3, (2, 70, 150)), (6, (2, 37, 107)), (3, (1, 256, 320)), (6, (3, 64, 64))])
+@pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16])
+def test_stem_train_forward_and_wgrad(cin, shape, dtype):
+    """Stem without ReLU (pre-BatchNorm activation) and its weight gradient vs torch fp32 on the same inputs.  The tensor-core
+    stem rounds x and w to f16 (11-bit mantissa): forward within 2e-3 of the output scale for f16 storage (1e-2 for bf16);
+    the weight gradient reads x in fp32: 1e-4 of its scale."""
+    from dpft_b200 import features, train_ops
+    _no_tf32()
+    B, H, W = shape
+    g = torch.Generator(device=DEV).manual_seed(cin + H)
+    x = torch.rand(B, H, W, cin, generator=g, device=DEV) * 255
+    w = torch.randn(64, cin, 7, 7, generator=g, device=DEV) / (49 * cin) ** 0.5 / 64
+    w_k = w.permute(2, 3, 1, 0).contiguous()                              # [7][7][Cin][64]
+    want = F.conv2d(x.permute(0, 3, 1, 2), w, stride=2, padding=3).permute(0, 2, 3, 1)
+    zero = torch.zeros(64, device=DEV)
+    for impl in (1, 2):
+        if impl == 2 and want.shape[2] < 8:
+            continue
+        got = features.stem_forward(x, w_k, zero, dtype, impl=impl, w_packed=features.stem_pack_weights(w_k), relu=False)
+        torch.cuda.synchronize()
+        assert got.dtype == dtype and got.shape == want.shape
+        assert (got.float() < 0).any(), "the ReLU was applied"
+        tol = 2e-3 if dtype == torch.float16 else 1e-2
+        assert (got.float() - want).abs().max().item() <= tol * want.abs().max().item(), impl
+    P, Q = want.shape[1], want.shape[2]
+    dy = torch.randn(B, P, Q, 64, generator=g, device=DEV).to(dtype)
+    ref = torch.nn.grad.conv2d_weight(x.permute(0, 3, 1, 2), (64, cin, 7, 7), dy.float().permute(0, 3, 1, 2), stride=2, padding=3)
+    got = train_ops.stem_wgrad(x, dy)
+    torch.cuda.synchronize()
+    assert got.shape == (7, 7, cin, 64)
+    assert (got.permute(3, 2, 0, 1) - ref).abs().max().item() <= 1e-4 * ref.abs().max().item()
+    got2 = train_ops.stem_wgrad(x, dy, out=got.clone())                    # accumulates
+    torch.cuda.synchronize()
+    assert (got2.permute(3, 2, 0, 1) - 2 * ref).abs().max().item() <= 2e-4 * ref.abs().max().item()
 
 
 def test_weight_packer_layouts():

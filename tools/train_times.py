@@ -20,9 +20,20 @@ if "--radar" in sys.argv:
 native = "--torch" not in sys.argv
 cin = 6 if "--radar" in sys.argv else 3
 torch.manual_seed(0)
-m = Backbone(arch, in_channels=cin, multi_scale=4).to(dev).train()
-m.native_train = native
-x = torch.rand(B, H, W, cin, device=dev) * 255
+if "--full" in sys.argv:
+    # the whole DPRT training step of the bench workload (three views + FPN + decoder), loss = sum_k mean(out_k^2)
+    from dpft_b200 import configs, models, synthetic
+    cfg = synthetic.offline_config(configs.make_config("kradar"), n_queries=(20, 15, 1))
+    m = models.build("dprt", cfg)
+    m.load_state_dict(synthetic.seeded_state_dict(m.state_dict(), seed=1))
+    m = m.to(dev).train()
+    m.native_train = native
+    x = synthetic.synthetic_batch(cfg, B, seed=1, sizes=dict(synthetic.BASELINE_SIZES), device=dev)
+    arch = "dprt-kradar"
+else:
+    m = Backbone(arch, in_channels=cin, multi_scale=4).to(dev).train()
+    m.native_train = native
+    x = torch.rand(B, H, W, cin, device=dev) * 255
 
 
 def loss_of(out):
@@ -73,7 +84,8 @@ for ev in prof.key_averages():
     if t and ev.device_type is not None and "DeviceType.CUDA" in str(ev.device_type):
         rows.append((t, ev.count, ev.key))
 rows.sort(reverse=True)
+n_rows = 45 if '--full' in sys.argv else 25
 tot = sum(r[0] for r in rows)
 print(f"kernel time total {tot / 1e3:.2f} ms")
-for t, n, k in rows[:25]:
+for t, n, k in rows[:n_rows]:
     print(f"{t / 1e3:9.3f} ms  {100 * t / tot:5.1f}%  x{n:<5d} {k[:110]}")
