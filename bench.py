@@ -49,6 +49,7 @@ def parse():
     ap.add_argument("--small", action="store_true", help="debug: tiny inputs (NOT a valid bench number)")
     ap.add_argument("--mode", default="infer", choices=["infer", "train"],
                     help="infer: eval forward (headline).  train: fwd+bwd+gradient all-reduce+AdamW (BASELINE config 4)")
+    ap.add_argument("--no-graph", action="store_true", help="train mode: issue the step eagerly instead of replaying one CUDA graph")
     ap.add_argument("--dtype", default="f16", choices=["f16", "bf16", "f32"],
                     help="activation type of the native backbone (f32 = fused decoder on torch fp32 features)")
     return ap.parse_args()
@@ -187,8 +188,20 @@ def conv_roofline(model, resident, dev, tf_peak, peak_src):
     tensor_bound = [p for p in prof if p[0] / (tf_peak * 1e12) >= p[1] / (hbm_peak * 1e9)]
     tb_secs = sum(p[2].elapsed_time(p[3]) for p in tensor_bound) * 1e-3
     tb_flops = sum(p[0] for p in tensor_bound)
+    # DRAM traffic of the same launches from the committed ncu pass (tools/gpu_round23.sh -> tools/ncu_summaries.py); it is
+    # evidence captured under the profiler, reported beside the live numbers, never a timing
+    traffic, traffic_src = None, None
+    for name in sorted(os.listdir(os.path.join(ROOT, "profiles")), reverse=True):
+        if name.endswith("_ncu_conv_traffic.json"):
+            with open(os.path.join(ROOT, "profiles", name)) as f:
+                t = json.load(f)
+            traffic, traffic_src = t["dram_bytes"], f"profiles/{name}: dram__bytes_read.sum + dram__bytes_write.sum over " \
+                f"{t['launches']} conv_gemm_kernel launches of one step (ncu, bs 8 bench workload); tensor pipe active " \
+                f"{t['tensor_pipe_active_pct_time_weighted']:.1f} % time-weighted"
+            break
     return {"kernel": "conv_gemm_kernel (all %d backbone conv launches of one step)" % len(prof), "bound": "tensor",
-            "achieved": achieved, "peak": tf_peak, "unit": "TFLOP/s", "frac": achieved / tf_peak, "traffic": None,
+            "achieved": achieved, "peak": tf_peak, "unit": "TFLOP/s", "frac": achieved / tf_peak, "traffic": traffic,
+            "traffic_source": traffic_src,
             "peak_source": peak_src + ", bf16_tflops_sustained (kernel timed inside a long step)",
             "algorithmic_flops_per_step": flops, "algorithmic_bytes_per_step": nbytes, "ms_in_kernel_per_step": secs * 1e3,
             "gbps": nbytes / secs / 1e9, "launches": len(prof),
@@ -266,19 +279,18 @@ def run_train(args, cfg, sizes, rank, world, dev):
     model.train_dtype = torch.bfloat16 if args.dtype == "bf16" else torch.float16
     if world > 1:
         ddp.broadcast_parameters(model, src=0)
+    from dpft_b200.train_step import GraphedTrainStep
     bucket = ddp.GradientBucket(model, n_chunks=6)
-    opt = torch.optim.AdamW(bucket.params, lr=1e-4)
+    graphed = not args.no_graph
+    opt = torch.optim.AdamW(bucket.params, lr=1e-4, capturable=graphed)
     B = args.batch
     batch = synthetic.synthetic_batch(cfg_t, B, seed=42 + rank, sizes=sizes, device=dev)
+    # the whole step (zero -> fwd -> loss -> bwd + all-reduce -> AdamW) is one CUDA graph, replayed per step
+    train_step = GraphedTrainStep(model, bucket, opt, lambda out, _b: sum((v ** 2).mean() for v in out.values()),
+                                  graph=graphed, warmup=3)
 
     def step():
-        bucket.zero()
-        out = model(batch)
-        loss = sum((v ** 2).mean() for v in out.values())
-        loss.backward()
-        bucket.finish()
-        opt.step()
-        return loss
+        return train_step(batch)
 
     for _ in range(max(args.warmup, 3)):
         step()
@@ -309,8 +321,10 @@ def run_train(args, cfg, sizes, rank, world, dev):
                           "data": "synthetic",
                           "config": {"workload": WORKLOAD.replace("eval forward", "training step (fwd+bwd+all-reduce+AdamW)"),
                                      "frames_per_gpu": B, "parallelism": f"dp{world}", "loss": "sum_k mean(out_k^2)",
-                                     "gradient_bucket_bytes": bucket.bytes(), "bucket_chunks": bucket.n_chunks},
-                          "gpu_launches": native.launches() - l0, "final_loss": float(loss)}), flush=True)
+                                     "gradient_bucket_bytes": bucket.bytes(), "bucket_chunks": bucket.n_chunks,
+                                     "launch": "one CUDA graph per step" if graphed else "eager"},
+                          "gpu_launches": (train_step.native_launches_per_step * args.steps if graphed
+                                           else native.launches() - l0), "final_loss": float(loss)}), flush=True)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()

@@ -89,7 +89,9 @@ class NativeStages:
 
     def _refresh_weights(self) -> None:
         version = tuple(s.conv.weight._version for s in self.specs)
-        if version != self._packed_version or self.packer._ptrs != [w.data_ptr() for w in self.packer.weights]:
+        # under CUDA-graph capture the host cannot know whether the replayed step follows an optimiser update: always re-pack
+        if (version != self._packed_version or self.packer._ptrs != [w.data_ptr() for w in self.packer.weights]
+                or torch.cuda.is_current_stream_capturing()):
             self.packer.refresh()
             self._packed_version = version
 

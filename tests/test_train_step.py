@@ -1,0 +1,96 @@
+"""GraphedTrainStep (dpft_b200/train_step.py): the eager sequence on the CPU against a hand-written loop (driver loop of
+reference src/dprt/training/trainer.py:116-135), and on the GPU the captured CUDA graph against the eager sequence."""
+import copy
+
+import pytest
+import torch
+
+from dpft_b200 import configs, ddp, models, synthetic
+from dpft_b200.train_step import GraphedTrainStep
+from helpers import oracle_op_injected
+
+
+def _loss(out, _batch):
+    return sum((v ** 2).mean() for v in out.values())
+
+
+def _small(dropout=0.0):
+    cfg = synthetic.offline_config(configs.make_config("kradar_radar_bev"), n_queries=(6, 5, 1))
+    cfg["model"]["fuser"]["dropout"] = dropout
+    sizes = {"radar_bev": (64, 64, 6)}
+    return cfg, sizes
+
+
+def test_eager_sequence_equals_manual_loop_cpu():
+    cfg, sizes = _small()
+    torch.manual_seed(0)
+    a = models.build("dprt", cfg).train()
+    b = copy.deepcopy(a)
+    batch = synthetic.synthetic_batch(cfg, 2, seed=5, sizes=sizes)
+    with oracle_op_injected():
+        bucket = ddp.GradientBucket(a, n_chunks=2)
+        opt = torch.optim.AdamW(bucket.params, lr=1e-3)
+        step = GraphedTrainStep(a, bucket, opt, _loss, graph=False)
+        losses = [float(step(batch)) for _ in range(2)]
+        skip = set(ddp.unused_parameter_names(b))
+        opt_b = torch.optim.AdamW([p for n, p in reversed(list(b.named_parameters())) if n not in skip], lr=1e-3)
+        ref = []
+        for _ in range(2):
+            opt_b.zero_grad()
+            l = _loss(b(batch), batch)
+            l.backward()
+            opt_b.step()
+            ref.append(float(l))
+    assert losses == pytest.approx(ref, rel=1e-6)
+    for (n, p), (_, q) in zip(a.named_parameters(), b.named_parameters()):
+        assert torch.allclose(p, q, rtol=1e-5, atol=1e-7), n
+
+
+def test_graph_needs_capturable_optimizer():
+    cfg, _ = _small()
+    m = models.build("dprt", cfg).train()
+    with oracle_op_injected():
+        bucket = ddp.GradientBucket(m, n_chunks=2)
+    with pytest.raises(ValueError, match="capturable"):
+        GraphedTrainStep(m, bucket, torch.optim.AdamW(bucket.params, lr=1e-3), _loss, graph=True)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("native_train", [True, False])
+def test_graph_replay_matches_eager_gpu(native_train):
+    """Same model, same batches: five steps replayed from one CUDA graph vs five eager steps.  The steps are identical launch
+    sequences; the only difference allowed is the order of fp32 atomic accumulation in the split-K weight gradients and
+    the deformable-attention scatter (tolerance 2e-3 on the loss after five AdamW updates, lr 1e-3)."""
+    dev = "cuda:0"
+    cfg, sizes = _small()
+    torch.manual_seed(0)
+    base = models.build("dprt", cfg)
+    base.load_state_dict(synthetic.seeded_state_dict(base.state_dict(), seed=1))
+    batches = [synthetic.synthetic_batch(cfg, 2, seed=10 + i, sizes=sizes, device=dev) for i in range(2)]
+    results = []
+    for graph in (False, True):
+        m = copy.deepcopy(base).to(dev).train()
+        m.native_train = native_train
+        bucket = ddp.GradientBucket(m, n_chunks=3)
+        opt = torch.optim.AdamW(bucket.params, lr=1e-3, capturable=True)
+        step = GraphedTrainStep(m, bucket, opt, _loss, graph=graph, warmup=3)
+        losses = []
+        if not graph:                                     # the capture warm-up is three real steps on the first batch
+            for _ in range(3):
+                step(batches[0])
+        for i in range(5):
+            losses.append(float(step(batches[i % 2]).clone()))
+        torch.cuda.synchronize()
+        if graph:
+            assert step.warmup_steps_taken == 3
+            assert (step.native_launches_per_step > 0) and step._graph is not None
+        results.append((losses, {n: p.detach().clone() for n, p in m.named_parameters()},
+                        {n: b.detach().clone() for n, b in m.named_buffers()}))
+    (l_e, p_e, b_e), (l_g, p_g, b_g) = results
+    assert l_g == pytest.approx(l_e, rel=2e-3), (l_e, l_g)
+    assert l_g[0] != l_g[-1]                              # the replayed optimiser really updates the weights
+    for n in b_e:
+        if n.endswith("num_batches_tracked"):
+            assert int(b_e[n]) == int(b_g[n]) == 8, n     # 3 warm-up + 5 steps, also under replay
+    with pytest.raises(RuntimeError, match="shapes"):
+        step({k: v[:1] for k, v in batches[0].items()})
