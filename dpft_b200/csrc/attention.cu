@@ -79,7 +79,15 @@ template <int DP, bool SPLIT> struct AttnSmem {
     static constexpr int kTotal = oBar + 32;
 };
 
-template <typename T, bool SPLIT, int DP>
+// 16 bytes of T -> floats
+template <typename T> struct Vec16 { static constexpr int kElems = 16 / sizeof(T); };
+template <typename T> __device__ __forceinline__ void unpack16(const uint4& raw, float* x) {
+    const T* e = reinterpret_cast<const T*>(&raw);
+#pragma unroll
+    for (int i = 0; i < Vec16<T>::kElems; ++i) x[i] = to_acc<T>(e[i]);
+}
+
+template <typename T, bool SPLIT, int DP, bool VECLOAD>
 __global__ void __launch_bounds__(128) flash_attn_fwd_kernel(const AttnParams prm) {
     using MT = typename std::conditional<std::is_same<T, __nv_bfloat16>::value, __nv_bfloat16, __half>::type;
     using L = AttnSmem<DP, SPLIT>;
@@ -104,50 +112,85 @@ __global__ void __launch_bounds__(128) flash_attn_fwd_kernel(const AttnParams pr
         fence_barrier_init();
     }
     if (warp == 0) tmem_alloc(tmem_slot, 256);      // columns [0,128) = S, [128, 128+DP) = P.V of the current key block
-    // ---- Q tile -> shared memory (row t = query n0 + t; rows past N and channels past D are zero) ----
-    {
-        const int n = n0 + t;
+    // ---- operand tiles -> shared memory.  Rows past N and channels past D are zero.
+    // VECLOAD (D a multiple of 16 bytes of T, aligned strides): consecutive threads fetch consecutive 16-byte pieces of a row
+    // (coalesced), otherwise thread t walks row t element by element (the 2-channel heads of the shipped configuration).
+    constexpr int VE = Vec16<T>::kElems;                      // elements per 16-byte global load
+    auto load_rows = [&](const T* src, long long row_stride, int first, int off) {   // [128 rows][DP] -> [DP/8][128][16 B]
+        if constexpr (VECLOAD) {
+#pragma unroll 2
+            for (int idx = t; idx < 128 * (DP / VE); idx += 128) {
+                const int r = idx / (DP / VE), cc = idx - r * (DP / VE);
+                const int j = first + r, d0 = cc * VE;
+                uint4 raw = make_uint4(0u, 0u, 0u, 0u);
+                if (j < N && d0 < D) raw = __ldg(reinterpret_cast<const uint4*>(src + (long long)j * row_stride + d0));
+                uint8_t* dst = smem + off + (d0 >> 3) * (128 * 16) + r * 16 + (d0 & 7) * 2;
+                if constexpr (std::is_same<T, MT>::value) {
+                    *reinterpret_cast<uint4*>(dst) = raw;     // already the MMA type: a straight copy
+                } else {
+                    float x[VE];
+                    unpack16<T>(raw, x);
+                    unsigned short hi[VE], lo[VE];
 #pragma unroll
-        for (int c = 0; c < DC; ++c) {
-            float x[8];
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-                const int d = c * 8 + i;
-                x[i] = (n < N && d < D) ? to_acc<T>(qg[(long long)n * prm.q_row + d]) : 0.0f;
+                    for (int i = 0; i < VE; ++i) {
+                        hi[i] = to_bits<MT>(x[i]);
+                        lo[i] = SPLIT ? to_bits<MT>(x[i] - from_bits<MT>(hi[i])) : (unsigned short)0;
+                    }
+                    *reinterpret_cast<uint2*>(dst) = make_uint2(hi[0] | (uint32_t)hi[1] << 16, hi[2] | (uint32_t)hi[3] << 16);
+                    if (SPLIT)
+                        *reinterpret_cast<uint2*>(dst + 128 * DP * 2) =
+                            make_uint2(lo[0] | (uint32_t)lo[1] << 16, lo[2] | (uint32_t)lo[3] << 16);
+                }
             }
-            uint4 hi, lo;
-            pack8<MT, SPLIT>(x, hi, lo);
-            *reinterpret_cast<uint4*>(smem + L::oQ + c * (ATT_BM * 16) + t * 16) = hi;
-            if (SPLIT) *reinterpret_cast<uint4*>(smem + L::oQ + L::kQ + c * (ATT_BM * 16) + t * 16) = lo;
-        }
-    }
-    auto load_k = [&](int j0) {                     // row t = key j0 + t
-        const int j = j0 + t;
+        } else {
+            const int j = first + t;
 #pragma unroll
-        for (int c = 0; c < DC; ++c) {
-            float x[8];
+            for (int c = 0; c < DC; ++c) {
+                float x[8];
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
-                const int d = c * 8 + i;
-                x[i] = (j < N && d < D) ? to_acc<T>(kg[(long long)j * prm.k_row + d]) : 0.0f;
+                for (int i = 0; i < 8; ++i) {
+                    const int d = c * 8 + i;
+                    x[i] = (j < N && d < D) ? to_acc<T>(src[(long long)j * row_stride + d]) : 0.0f;
+                }
+                uint4 hi, lo;
+                pack8<MT, SPLIT>(x, hi, lo);
+                *reinterpret_cast<uint4*>(smem + off + c * (128 * 16) + t * 16) = hi;
+                if (SPLIT) *reinterpret_cast<uint4*>(smem + off + 128 * DP * 2 + c * (128 * 16) + t * 16) = lo;
             }
-            uint4 hi, lo;
-            pack8<MT, SPLIT>(x, hi, lo);
-            *reinterpret_cast<uint4*>(smem + L::oK + c * (ATT_BN * 16) + t * 16) = hi;
-            if (SPLIT) *reinterpret_cast<uint4*>(smem + L::oK + L::kK + c * (ATT_BN * 16) + t * 16) = lo;
         }
     };
-    auto load_v = [&](int j0) {                     // V^T: row d, K index = key; thread t transposes key j0 + t
-        const int j = j0 + t;
-        uint8_t* base = smem + L::oV + (t >> 3) * (DP * 16) + (t & 7) * 2;
+    auto load_k = [&](int j0) { load_rows(kg, prm.k_row, j0, L::oK); };
+    auto load_v = [&](int j0) {                     // V^T: row d, K index = key  ->  [128/8][DP][16 B]
+        if constexpr (VECLOAD) {
+#pragma unroll 2
+            for (int idx = t; idx < 128 * (DP / VE); idx += 128) {
+                const int r = idx / (DP / VE), cc = idx - r * (DP / VE);
+                const int j = j0 + r, d0 = cc * VE;
+                uint4 raw = make_uint4(0u, 0u, 0u, 0u);
+                if (j < N && d0 < D) raw = __ldg(reinterpret_cast<const uint4*>(vg + (long long)j * prm.v_row + d0));
+                float x[VE];
+                unpack16<T>(raw, x);
+                uint8_t* base = smem + L::oV + (r >> 3) * (DP * 16) + (r & 7) * 2;
+#pragma unroll
+                for (int i = 0; i < VE; ++i) {
+                    const unsigned short hi = to_bits<MT>(x[i]);
+                    *reinterpret_cast<unsigned short*>(base + (d0 + i) * 16) = hi;
+                    if (SPLIT) *reinterpret_cast<unsigned short*>(base + L::kV + (d0 + i) * 16) = to_bits<MT>(x[i] - from_bits<MT>(hi));
+                }
+            }
+        } else {
+            const int j = j0 + t;
+            uint8_t* base = smem + L::oV + (t >> 3) * (DP * 16) + (t & 7) * 2;
 #pragma unroll 4
-        for (int d = 0; d < DP; ++d) {
-            const float x = (j < N && d < D) ? to_acc<T>(vg[(long long)j * prm.v_row + d]) : 0.0f;
-            const unsigned short hi = to_bits<MT>(x);
-            *reinterpret_cast<unsigned short*>(base + d * 16) = hi;
-            if (SPLIT) *reinterpret_cast<unsigned short*>(base + L::kV + d * 16) = to_bits<MT>(x - from_bits<MT>(hi));
+            for (int d = 0; d < DP; ++d) {
+                const float x = (j < N && d < D) ? to_acc<T>(vg[(long long)j * prm.v_row + d]) : 0.0f;
+                const unsigned short hi = to_bits<MT>(x);
+                *reinterpret_cast<unsigned short*>(base + d * 16) = hi;
+                if (SPLIT) *reinterpret_cast<unsigned short*>(base + L::kV + d * 16) = to_bits<MT>(x - from_bits<MT>(hi));
+            }
         }
     };
+    load_rows(qg, prm.q_row, n0, L::oQ);
     load_k(0);
     load_v(0);
     fence_proxy_async();
@@ -279,9 +322,9 @@ __global__ void __launch_bounds__(128) flash_attn_fwd_kernel(const AttnParams pr
     }
 }
 
-template <typename T, bool SPLIT, int DP> int launch_attn(const AttnParams& prm, cudaStream_t stream) {
+template <typename T, bool SPLIT, int DP, bool VECLOAD> int launch_attn(const AttnParams& prm, cudaStream_t stream) {
     using L = AttnSmem<DP, SPLIT>;
-    auto kern = flash_attn_fwd_kernel<T, SPLIT, DP>;
+    auto kern = flash_attn_fwd_kernel<T, SPLIT, DP, VECLOAD>;
     static bool configured = false;
     if (!configured) {
         int st = cuda_status(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kTotal),
@@ -296,9 +339,14 @@ template <typename T, bool SPLIT, int DP> int launch_attn(const AttnParams& prm,
 }
 
 template <typename T, bool SPLIT> int dispatch_dp(const AttnParams& prm, cudaStream_t stream) {
-    if (prm.D <= 16) return launch_attn<T, SPLIT, 16>(prm, stream);
-    if (prm.D <= 32) return launch_attn<T, SPLIT, 32>(prm, stream);
-    return launch_attn<T, SPLIT, 64>(prm, stream);
+    // 16-byte row pieces: head dim, strides and base addresses must all be multiples of 16 bytes of T
+    constexpr long long ve = 16 / sizeof(T);
+    const bool vec = prm.D % ve == 0 && prm.q_row % ve == 0 && prm.k_row % ve == 0 && prm.v_row % ve == 0 &&
+                     prm.q_batch % ve == 0 && prm.k_batch % ve == 0 && prm.v_batch % ve == 0 &&
+                     (((uintptr_t)prm.q | (uintptr_t)prm.k | (uintptr_t)prm.v) & 15) == 0;
+    if (prm.D <= 16) return vec ? launch_attn<T, SPLIT, 16, true>(prm, stream) : launch_attn<T, SPLIT, 16, false>(prm, stream);
+    if (prm.D <= 32) return vec ? launch_attn<T, SPLIT, 32, true>(prm, stream) : launch_attn<T, SPLIT, 32, false>(prm, stream);
+    return vec ? launch_attn<T, SPLIT, 64, true>(prm, stream) : launch_attn<T, SPLIT, 64, false>(prm, stream);
 }
 
 }  // namespace

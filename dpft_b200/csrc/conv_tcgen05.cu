@@ -20,6 +20,7 @@
 // The accumulator is double-buffered in TMEM (2 x BLOCK_N columns) so the epilogue of tile i overlaps the
 // main loop of tile i+1.  Stages: a ring of STAGES {A 16 KB, B BLOCK_N*128 B} buffers with full/empty mbarriers.
 #include <cuda.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 #include "tcgen05.cuh"
@@ -205,6 +206,11 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     else __syncthreads();
     tcgen05_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    // Programmatic dependent launch: everything above (barrier init, TMEM allocation, tensor-map prefetch) touches no global
+    // data, so it may overlap the tail of the previous kernel in the stream; the next kernel's CTAs may start their own set-up
+    // as soon as SMs free up.  No global read or write happens before this wait.  (No-ops without the launch attribute.)
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    asm volatile("griddepcontrol.wait;" ::: "memory");
 
     // CG == 2: a tile is 256 rows (this CTA owns rows rank*128 .. +128 of it) and the pair shares the B tile
     const int big_m_tiles = (prm.m_tiles + CG - 1) / CG;
@@ -503,6 +509,16 @@ int encode_2d(CUtensorMap* map, const void* base, uint64_t inner, uint64_t outer
     return 0;
 }
 
+// Programmatic dependent launch of the convolution chain; DPFT_CONV_PDL=0 in the environment turns it off (A/B timing).
+bool use_pdl() {
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("DPFT_CONV_PDL");
+        v = (e && e[0] == '0') ? 0 : 1;
+    }
+    return v != 0;
+}
+
 template <int BLOCK_N, int STAGES, int RES_BUFS, int CG = 1>
 int launch(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& td, const CUtensorMap& tr, const ConvParams& prm,
            cudaStream_t stream) {
@@ -519,24 +535,29 @@ int launch(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& td, 
     const int tiles = ((prm.m_tiles + CG - 1) / CG) * prm.n_tiles;
     const int max_ctas = g_sm_count / CG;
     const int grid = CG * (tiles < max_ctas ? tiles : max_ctas);
-    if (CG == 1) {
-        kern<<<grid, kNumThreads, L::kTotal, stream>>>(ta, tb, td, tr, prm);
-    } else {
-        cudaLaunchConfig_t cfg{};
-        cfg.gridDim = dim3(grid);
-        cfg.blockDim = dim3(kNumThreads);
-        cfg.dynamicSmemBytes = L::kTotal;
-        cfg.stream = stream;
-        cudaLaunchAttribute attr[1];
-        attr[0].id = cudaLaunchAttributeClusterDimension;
-        attr[0].val.clusterDim.x = CG;
-        attr[0].val.clusterDim.y = 1;
-        attr[0].val.clusterDim.z = 1;
-        cfg.attrs = attr;
-        cfg.numAttrs = 1;
-        int st = cuda_status(cudaLaunchKernelEx(&cfg, kern, ta, tb, td, tr, prm), "cudaLaunchKernelEx(conv_gemm_kernel, cluster 2)");
-        if (st) return st;
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(kNumThreads);
+    cfg.dynamicSmemBytes = L::kTotal;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[2];
+    int n_attr = 0;
+    if (CG == 2) {
+        attr[n_attr].id = cudaLaunchAttributeClusterDimension;
+        attr[n_attr].val.clusterDim.x = CG;
+        attr[n_attr].val.clusterDim.y = 1;
+        attr[n_attr].val.clusterDim.z = 1;
+        ++n_attr;
     }
+    if (use_pdl()) {       // overlap this kernel's set-up with the previous kernel's tail (griddepcontrol.wait in the kernel)
+        attr[n_attr].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[n_attr].val.programmaticStreamSerializationAllowed = 1;
+        ++n_attr;
+    }
+    cfg.attrs = attr;
+    cfg.numAttrs = n_attr;
+    int st = cuda_status(cudaLaunchKernelEx(&cfg, kern, ta, tb, td, tr, prm), "cudaLaunchKernelEx(conv_gemm_kernel)");
+    if (st) return st;
     DPFT_LAUNCH_CHECK("conv_gemm_kernel");
     return DPFT_OK;
 }

@@ -26,6 +26,7 @@ import torch
 import torch.nn.functional as F
 from torch import nn
 
+from .. import attention as attention_ops
 from .. import msda as msda_ops
 from .geometry import cart2spher
 
@@ -179,9 +180,15 @@ class MLFusion(nn.Module):
     def from_config(cls, config: Dict[str, Any]):
         return cls(**config)
 
+    native_self_attn = True      # inference on CUDA: attention core in the tcgen05 flash-attention kernel (dpft_b200/attention.py)
+
     def forward_self_attn(self, query, query_positions=None):
         qk = query if query_positions is None else query + query_positions
-        out = query + self.dropout1(self.self_attn(query=qk, key=qk, value=query, need_weights=False)[0])
+        if self.native_self_attn and attention_ops.mha_eligible(self.self_attn, query):
+            attn = attention_ops.multihead_self_attention(self.self_attn, qk, query)
+        else:
+            attn = self.self_attn(query=qk, key=qk, value=query, need_weights=False)[0]
+        out = query + self.dropout1(attn)
         return self.norm1(out) if self.norm else out
 
     def forward_cross_attn(self, query, batch, reference_points, query_positions=None):

@@ -198,6 +198,22 @@ DPFT_API int dpft_decoder_head_forward(const float* views, const float* weights,
                                        float* size_out, float* angle_out, float* class_out, int B, int V, int N,
                                        int n_cls, int reduction, int weight_floats, void* stream);
 
+/*
+ * Decoder self-attention core as a tcgen05 flash-attention kernel (csrc/attention.cu): the scaled-dot-product step of the
+ * nn.MultiheadAttention the reference's decoder layer builds at src/dprt/models/fusers/mpfusion.py:56-57 and calls at
+ * :139 (q = k = query + pos, v = query, need_weights=False), eval mode (no attention dropout):
+ *     out[b, n, h, :] = sum_j softmax_j(scale * <q[b,n,h,:], k[b,j,h,:]>) v[b,j,h,:]
+ *   q, k, v: element [b, n, h, d] at  base + b * batch_stride + n * row_stride + h * D + d  (so the q/k/v slices of a packed
+ *   in-projection are passed without a copy); out (B, N, H, D) contiguous; all four of `dtype` (DPFT_F32, DPFT_F16, DPFT_BF16).
+ *   D <= 64, any N.  S = Q K^T and P V run on tcgen05.mma kind::f16 with fp32 accumulation in TMEM, the online softmax in
+ *   registers.  precise != 0 (DPFT_F32 only): operands are split hi + lo and every product is three MMAs, which carries
+ *   ~22 mantissa bits (fp32-grade results, |err| ~ 1e-6); precise == 0: single f16 operands (16-bit tier, ~1e-3).
+ */
+DPFT_API int dpft_self_attention_forward(const void* q, const void* k, const void* v, void* out, int B, int H, int N, int D,
+                                         long long q_row_stride, long long k_row_stride, long long v_row_stride,
+                                         long long q_batch_stride, long long k_batch_stride, long long v_batch_stride,
+                                         float scale, int dtype, int precise, void* stream);
+
 /* ---------------------------------------------------------------------------------------------------------------
  * Training path of the backbone (autograd of the torchvision Bottleneck blocks the reference trains,
  * src/dprt/models/backbones/resnet.py:54-55,101 under src/dprt/training/trainer.py:125-133): BatchNorm with batch
