@@ -326,8 +326,17 @@ def run_train(args, cfg, sizes, rank, world, dev):
                           "gpu_launches": (train_step.native_launches_per_step * args.steps if graphed
                                            else native.launches() - l0), "final_loss": float(loss)}), flush=True)
     if world > 1:
+        # A captured graph holds NCCL kernels of this communicator: release it before the communicator goes away, and do not
+        # let a stuck teardown (seen once: destroy_process_group never returned after graph capture) keep the job alive.
         dist.barrier()
+        torch.cuda.synchronize()
+        train_step.release()
+        sys.stdout.flush()
+        watchdog = threading.Timer(20.0, lambda: os._exit(0))
+        watchdog.daemon = True
+        watchdog.start()
         dist.destroy_process_group()
+        watchdog.cancel()
 
 
 def main():

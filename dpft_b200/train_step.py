@@ -95,7 +95,11 @@ class GraphedTrainStep:
         self._graph.replay()
         return self._loss
 
+    def release(self) -> None:
+        """Drops the captured graph and its memory pool (call before tearing down the process group it captured)."""
+        self._graph, self._loss, self._static, self._signature = None, None, None, None
+
     @property
     def warmup_steps_taken(self) -> int:
         """Optimiser updates applied by the capture warm-up (they are real training steps on the first batch)."""
-        return self.warmup if self._graph is not None else 0
+        return self.warmup if self._signature is not None or self._graph is not None else 0

@@ -113,6 +113,27 @@ def test_decoder_layer_uses_the_kernel_in_eval_and_matches_torch():
     assert _err(a, b.double()) < 2e-5
 
 
+@pytest.mark.gpu
+def test_decoder_self_attention_matches_the_oracle_restatement():
+    """The whole self-attention sub-layer of MLFusion (in-projection, kernel, out-projection, residual, LayerNorm) against
+    oracle/dprt_oracle.py::self_attention, the CPU restatement of mpfusion.py:122-148 pinned by the golden vectors."""
+    from oracle import dprt_oracle
+    from dpft_b200.models.fuser import MLFusion
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.manual_seed(5)
+    layer = MLFusion(d_model=16, d_ffn=32, n_levels=1, n_heads=8, n_points=4, norm=True, dropout=0.1, activation="Mish").eval()
+    with torch.no_grad():
+        layer.self_attn.in_proj_bias.normal_(0, 0.3)
+        layer.self_attn.out_proj.bias.normal_(0, 0.3)
+    sd = {"l." + k: v for k, v in layer.state_dict().items()}
+    x, pos = torch.randn(3, 400, 16), torch.rand(3, 400, 16)
+    with torch.no_grad():
+        want = x + dprt_oracle.self_attention(sd, "l.self_attn", x, pos, 8)
+        want = torch.nn.functional.layer_norm(want, (16,), sd["l.norm1.weight"], sd["l.norm1.bias"], 1e-5)
+        got = layer.to(DEV).forward_self_attn(x.to(DEV), pos.to(DEV)).cpu()
+    assert float((got - want).abs().max()) < 1e-5
+
+
 def test_rejects_cpu_tensors_and_wide_heads():
     x = torch.zeros(1, 4, 8)
     with pytest.raises(RuntimeError, match="not implemented on the CPU"):
