@@ -664,6 +664,16 @@ extern "C" int dpft_conv2d_nhwc(const void* x, const void* w, const float* bias,
         return launch<128, 6, 3, 2>(ta, tb, td, tr, prm, s2);
     }
     const bool stream_bound = residual != nullptr && prm.kblocks <= 4;   // 1x1 expand convs: deep residual prefetch
+    // tuning hook (tools/conv_bench.py --variants): DPFT_CONV_STREAM_VARIANT picks another stage / residual-buffer split
+    static const int variant = [] { const char* e = getenv("DPFT_CONV_STREAM_VARIANT"); return e ? atoi(e) : 0; }();
+    if (stream_bound && variant == 1) {
+        if (bn == 256) return launch<256, 3, 2>(ta, tb, td, tr, prm, s);
+        if (bn == 128) return launch<128, 4, 3>(ta, tb, td, tr, prm, s);
+    }
+    if (stream_bound && variant == 2) {
+        if (bn == 256) return launch<256, 2, 3>(ta, tb, td, tr, prm, s);
+        if (bn == 128) return launch<128, 3, 5>(ta, tb, td, tr, prm, s);
+    }
     if (bn == 256) return stream_bound ? launch<256, 2, 5>(ta, tb, td, tr, prm, s) : launch<256, 3, 2>(ta, tb, td, tr, prm, s);
     if (bn == 128) return stream_bound ? launch<128, 2, 7>(ta, tb, td, tr, prm, s) : launch<128, 4, 3>(ta, tb, td, tr, prm, s);
     return stream_bound ? launch<64, 3, 7>(ta, tb, td, tr, prm, s) : launch<64, 6, 3>(ta, tb, td, tr, prm, s);

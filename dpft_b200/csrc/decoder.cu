@@ -264,20 +264,44 @@ decoder_layer_kernel(const LayerParams prm) {
     __syncthreads();                                      // s_k / s_v complete
 
     // ---- self-attention of head j over the N keys (online softmax) ---------------------------------------------
+    // two passes over the keys in shared memory (the scores are two FMAs): first the row maximum, then exp2 / sums.  No
+    // running-maximum branch and no rescaling in the loop, so four keys are in flight per trip instead of a dependent chain.
     float mx = -INFINITY, den = 0.0f, o0 = 0.0f, o1 = 0.0f;
-    for (int n = 0; n < N; ++n) {
-        const float2 kk = *reinterpret_cast<const float2*>(s_k + n * C + 2 * j);
-        const float2 vv = *reinterpret_cast<const float2*>(s_v + n * C + 2 * j);
-        const float s = fmaf(qa, kk.x, qb * kk.y);
-        if (s > mx) {
-            const float r = exp2f(mx - s);
-            den *= r; o0 *= r; o1 *= r;
-            mx = s;
+    {
+        const float2* kp = reinterpret_cast<const float2*>(s_k + 2 * j);
+        const float2* vp = reinterpret_cast<const float2*>(s_v + 2 * j);
+        float m0 = -INFINITY, m1 = -INFINITY, m2 = -INFINITY, m3 = -INFINITY;
+        int n = 0;
+        for (; n + 4 <= N; n += 4) {
+            const float2 k0 = kp[(n + 0) * (C / 2)], k1 = kp[(n + 1) * (C / 2)], k2 = kp[(n + 2) * (C / 2)], k3 = kp[(n + 3) * (C / 2)];
+            m0 = fmaxf(m0, fmaf(qa, k0.x, qb * k0.y));
+            m1 = fmaxf(m1, fmaf(qa, k1.x, qb * k1.y));
+            m2 = fmaxf(m2, fmaf(qa, k2.x, qb * k2.y));
+            m3 = fmaxf(m3, fmaf(qa, k3.x, qb * k3.y));
         }
-        const float p = exp2f(s - mx);
-        den += p;
-        o0 = fmaf(p, vv.x, o0);
-        o1 = fmaf(p, vv.y, o1);
+        for (; n < N; ++n) {
+            const float2 k0 = kp[n * (C / 2)];
+            m0 = fmaxf(m0, fmaf(qa, k0.x, qb * k0.y));
+        }
+        mx = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
+        float d0 = 0.0f, d1 = 0.0f, a0 = 0.0f, a1 = 0.0f, b0 = 0.0f, b1 = 0.0f;
+        n = 0;
+        for (; n + 2 <= N; n += 2) {
+            const float2 k0 = kp[n * (C / 2)], k1 = kp[(n + 1) * (C / 2)];
+            const float2 v0 = vp[n * (C / 2)], v1 = vp[(n + 1) * (C / 2)];
+            const float p0 = exp2f(fmaf(qa, k0.x, qb * k0.y) - mx);
+            const float p1 = exp2f(fmaf(qa, k1.x, qb * k1.y) - mx);
+            d0 += p0; d1 += p1;
+            a0 = fmaf(p0, v0.x, a0); a1 = fmaf(p0, v0.y, a1);
+            b0 = fmaf(p1, v1.x, b0); b1 = fmaf(p1, v1.y, b1);
+        }
+        for (; n < N; ++n) {
+            const float2 k0 = kp[n * (C / 2)], v0 = vp[n * (C / 2)];
+            const float p0 = exp2f(fmaf(qa, k0.x, qb * k0.y) - mx);
+            d0 += p0;
+            a0 = fmaf(p0, v0.x, a0); a1 = fmaf(p0, v0.y, a1);
+        }
+        den = d0 + d1; o0 = a0 + b0; o1 = a1 + b1;
     }
     {
         const float inv = 1.0f / den;

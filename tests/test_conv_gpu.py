@@ -58,6 +58,38 @@ def test_conv_matches_torch_fp32(shape, block_n, relu, with_res):
         assert err <= 2.0 ** -7 * scale, (cluster_mode, err, scale)    # only the bf16 output rounding should remain
 
 
+# the pointwise "expand" convs with a residual (conv3 of every Bottleneck: the stream-bound configuration of the kernel): several
+# waves of m-tiles per CTA, M tails, 1 / 2 / 4 n-tiles, grid smaller and larger than the SM count
+EXPAND_SHAPES = [(2, 45, 80, 256, 1024), (3, 30, 33, 128, 512), (2, 16, 24, 64, 256), (8, 45, 80, 256, 1024), (1, 5, 5, 192, 768),
+                 (4, 90, 160, 128, 512)]
+
+
+@pytest.mark.parametrize("shape", EXPAND_SHAPES)
+@pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16])
+@pytest.mark.parametrize("relu", [True, False])
+def test_expand_conv_with_residual_matches_torch_fp32(shape, dtype, relu):
+    from dpft_b200 import conv
+    B, H, W, Cin, Cout = shape
+    dev = "cuda:0"
+    g = torch.Generator(device=dev).manual_seed(Cin + Cout + H)
+    x = torch.randn(B, H, W, Cin, generator=g, device=dev).to(dtype)
+    w = (torch.randn(Cout, 1, 1, Cin, generator=g, device=dev) / Cin ** 0.5).to(dtype)
+    bias = torch.randn(Cout, generator=g, device=dev)
+    res = torch.randn(B, H, W, Cout, generator=g, device=dev).to(dtype)
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    want = _reference(x, w, bias, 1, 0, relu, res)
+    scale = want.abs().max().item()
+    got = conv.conv2d_nhwc(x, w, bias, 1, 0, relu, res, block_n=256, cluster_mode=1)
+    again = conv.conv2d_nhwc(x, w, bias, 1, 0, relu, res, block_n=256, cluster_mode=1)
+    torch.cuda.synchronize()
+    assert torch.equal(got, again)                                        # deterministic
+    err = (got.float() - want).abs().max().item()
+    assert err <= (2.0 ** -7 if dtype == torch.bfloat16 else 2.0 ** -10) * scale, (err, scale)   # output rounding only
+    auto = conv.conv2d_nhwc(x, w, bias, 1, 0, relu, res)                  # whatever tile the heuristic picks agrees
+    assert (auto.float() - got.float()).abs().max().item() <= 2.0 ** -7 * scale
+
+
 def test_folded_bottleneck_matches_torch_block():
     """conv+bn folding and the residual/ReLU epilogue reproduce a torchvision-style bottleneck in eval mode."""
     from dpft_b200 import conv
