@@ -8,10 +8,14 @@ BASELINE cfg-3 query grid: 300 queries) over one synthetic batch of B=8 frames p
 256x256 range-azimuth and 256x256 elevation-azimuth radar projections.  N > 1 runs one replica per GPU
 (launched by torch.distributed.run) on its own batch shard — weak scaling, no data-path collective.
 
-  value   frames/s with the batch already resident in HBM (CUDA events, max over ranks, L2 flushed between steps)
-  e2e     frames/s through the public call model(batch) with HOST (pinned) input buffers: H2D of the batch and
-          D2H of the four outputs inside the timed region
-  roofline     the deformable-attention forward kernel on the step's own tensors (HBM bound)
+  value   frames/s with the batches already resident in HBM, through DPRT.infer_stream with --depth forwards in flight
+          (each on its own stream, captured graph and memory pool): ONE device-timed region around exactly K forwards
+          (CUDA events, max over ranks); the loop alternates two input batches (227 MB of inputs > 126 MB L2)
+  e2e     the same loop with HOST (pinned) input buffers: H2D of every batch and D2H of its four outputs inside the
+          timed region
+  sequential   one forward at a time (model(batch)), per-step events, L2 flushed by a 256 MiB write between steps: the
+          latency view, and the number earlier rounds reported as `value`
+  roofline     the dominant kernel (tcgen05 convolution, every launch of one step) + the deformable-attention forward kernel
   cpu_baseline the CPU oracle port of the reference forward on the host cores (rank 0, N=1, bounded sample)
 
 --impl reference times the reference's CPU forward (the oracle port in oracle/dprt_oracle.py — the reference is
@@ -49,6 +53,8 @@ def parse():
     ap.add_argument("--small", action="store_true", help="debug: tiny inputs (NOT a valid bench number)")
     ap.add_argument("--mode", default="infer", choices=["infer", "train"],
                     help="infer: eval forward (headline).  train: fwd+bwd+gradient all-reduce+AdamW (BASELINE config 4)")
+    ap.add_argument("--depth", type=int, default=3,
+                    help="forwards in flight in the timed loop (DPRT.infer_stream); 1 = one forward at a time with an L2 flush between steps")
     ap.add_argument("--no-graph", action="store_true", help="train mode: issue the step eagerly instead of replaying one CUDA graph")
     ap.add_argument("--dtype", default="f16", choices=["f16", "bf16", "f32"],
                     help="activation type of the native backbone (f32 = fused decoder on torch fp32 features)")
@@ -416,14 +422,62 @@ def main():
             torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
         return float(t.item())
 
+    # second input set: the pipelined loop alternates between two batches (2 x 113.6 MB of inputs > 126 MB L2)
+    host2 = {k: v.pin_memory() for k, v in synthetic.synthetic_batch(cfg, B, seed=2000 + rank, sizes=sizes).items()}
+    resident2 = {k: v.to(dev) for k, v in host2.items()}
+
+    def timed_stream(feed, steps, warmup, d2h):
+        """K forwards through the public streaming call (DPRT.infer_stream, `depth` forwards in flight), timed as ONE region on
+        the device: event before the first launch, event after the last output is handed out (and copied to the host)."""
+        nonlocal out_host
+
+        def gen(n):
+            for i in range(n):
+                yield feed[i % len(feed)]
+
+        def drain(n):
+            nonlocal out_host
+            for out in model.infer_stream(gen(n), depth=args.depth):
+                if d2h:
+                    if out_host is None:
+                        out_host = {k: torch.empty(v.shape, dtype=v.dtype).pin_memory() for k, v in out.items()}
+                    for k, v in out.items():
+                        out_host[k].copy_(v, non_blocking=True)
+
+        drain(warmup)
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        drain(steps)
+        e1.record()
+        barrier()
+        t = torch.tensor([e0.elapsed_time(e1) * 1e-3], device=dev, dtype=torch.float64)
+        if world > 1:
+            torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
+        return float(t.item())
+
     sampler = ClockSampler(local)
-    if rank == 0:
+    pipelined = args.depth > 1
+    # one forward at a time, L2 flushed between steps (latency view; the headline when --depth 1)
+    if rank == 0 and not pipelined:
         sampler.start()
     l0 = native.launches()
-    t_res = timed(step_resident, args.steps, max(args.warmup, 3))
+    t_seq = timed(step_resident, args.steps, max(args.warmup, 3))
     launches = native.launches() - l0
-    clocks = sampler.stop() if rank == 0 else None
-    t_e2e = timed(step_e2e, args.steps, 2)
+    if rank == 0 and not pipelined:
+        clocks = sampler.stop()
+    t_seq_e2e = timed(step_e2e, args.steps, 2)
+    t_res, t_e2e = t_seq, t_seq_e2e
+    if pipelined:
+        if rank == 0:
+            sampler.start()
+        l0 = native.launches()
+        t_res = timed_stream([resident, resident2], args.steps, max(args.warmup, 3), d2h=False)
+        launches = native.launches() - l0
+        clocks = sampler.stop() if rank == 0 else None
+        t_e2e = timed_stream([host, host2], args.steps, max(args.warmup, 3), d2h=True)
+    elif rank != 0:
+        clocks = None
     d2h_bytes = sum(v.numel() * v.element_size() for v in out_host.values())
 
     frames = B * world * args.steps
@@ -444,13 +498,20 @@ def main():
                 "warmup": max(args.warmup, 3), "ms_per_step": 1e3 * t_res / args.steps, "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": args.dtype, "data": "synthetic",
                 "config": {"workload": WORKLOAD, "frames_per_gpu": B,
-                           "arithmetic": "backbone convs: %s operands, f32 accumulate (tcgen05); FPN/decoder f32" % args.dtype, "l2": "flushed between timed steps (256 MiB write)",
+                           "arithmetic": "backbone convs: %s operands, f32 accumulate (tcgen05); FPN/decoder f32" % args.dtype,
+                           "launch": ("DPRT.infer_stream, %d forwards in flight (one captured graph, memory pool and stream each)" % args.depth)
+                                     if pipelined else "one forward at a time (CUDA graph replay)",
+                           "l2": ("no flush inside the pipelined region: the loop alternates between two input batches (227 MB of inputs "
+                                  "> 126 MB L2) and every step streams > 2 GB of activations; `sequential` = one forward at a time with a "
+                                  "256 MiB L2-flushing write between steps") if pipelined else "flushed between timed steps (256 MiB write)",
                            "sizes": {k: list(v) for k, v in sizes.items()}, "parallelism": f"replicas x{world}",
                            "valid": not args.small},
                 "roofline": roof, "roofline_msda": roof_msda, "clocks": clocks,
                 "e2e": {"value": frames / t_e2e, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes,
                         "d2h_bytes_per_step": d2h_bytes, "ms_per_step": 1e3 * t_e2e / args.steps},
-                "gpu_launches": launches}
+                "gpu_launches": launches,
+                "sequential": {"value": frames / t_seq, "ms_per_step": 1e3 * t_seq / args.steps, "e2e_value": frames / t_seq_e2e,
+                               "note": "one forward at a time, per-step CUDA events, L2 flushed between steps"}}
         if world == 1 and not args.no_cpu_baseline:
             torch.set_num_threads(os.cpu_count())
             fps, secs = cpu_forward_fps(cfg, sizes, sd, args.cpu_sample, reps=3)

@@ -59,6 +59,7 @@ class FusedEngine:
         self._row_0001 = torch.tensor([0.0, 0.0, 0.0, 1.0], device=self.device)
         self._param_version = self._version(model)
         self._graphs: Dict[tuple, List["_CapturedForward"]] = {}
+        self._pipelines: Dict[tuple, List["_PipelineSlot"]] = {}
         self._seen: Dict[tuple, int] = {}
         self._slot = 0
         self._side_streams = [torch.cuda.Stream(device=self.device) for _ in range(max(0, len(model.inputs) - 1))]
@@ -234,6 +235,40 @@ class FusedEngine:
     def _to_device(self, batch: Dict[str, torch.Tensor]) -> Dict[str, torch.Tensor]:
         return {k: batch[k].to(self.device, non_blocking=True) for k in self._keys()}
 
+    # -- pipelined replay: consecutive forwards overlap on the GPU -------------------------------------------------------
+    def stream(self, batches, depth: int = 2):
+        """Generator over ``batches`` (same shapes) yielding their outputs in order, with up to ``depth`` forwards in flight:
+        forward k+1 is replayed on its own stream, from its own captured graph and memory pool, before the outputs of
+        forward k are handed out.  A single forward leaves SMs idle in the second wave of every 2-wave convolution (225
+        m-tiles on 148 SMs in stage 3), in the latency-bound decoder and while the stem ramps up; the neighbouring
+        forward's kernels fill those holes.  Batches may be device tensors or pinned host tensors (uploaded on the copy
+        stream).  Outputs are private copies, valid on the caller's current stream."""
+        from collections import deque
+        depth = max(1, int(depth))
+        pending = deque()
+        slots = None
+        index = 0
+        for batch in batches:
+            on_host = not batch[self.model.inputs[0]].is_cuda
+            if slots is None:
+                sig = ("stream", depth) + tuple((k, tuple(batch[k].shape), batch[k].dtype) for k in self._keys())
+                slots = self._pipelines.get(sig)
+                if slots is None:
+                    with torch.no_grad():
+                        dev_batch = self._to_device(batch) if on_host else batch
+                        self.forward_eager(dev_batch)                # fills the per-shape caches outside any capture
+                        slots = self._pipelines[sig] = [_PipelineSlot(self, dev_batch) for _ in range(depth)]
+                shapes = {k: tuple(batch[k].shape) for k in self._keys()}
+            elif {k: tuple(batch[k].shape) for k in self._keys()} != shapes:
+                raise RuntimeError("FusedEngine.stream: every batch of one stream must have the same shapes")
+            with torch.no_grad():
+                pending.append(slots[index % depth].launch(batch, self._copy_stream if on_host else None))
+            index += 1
+            if len(pending) >= depth:
+                yield _PipelineSlot.collect(pending.popleft(), self.device)
+        while pending:
+            yield _PipelineSlot.collect(pending.popleft(), self.device)
+
 
 class _CapturedForward:
     """One captured forward for one set of input shapes: static input buffers -> graph -> static outputs."""
@@ -274,3 +309,30 @@ class _CapturedForward:
         self.consumed.record(main)
         native.count_launch(self.n_launches)
         return OrderedDict((k, v.clone()) for k, v in self.static_out.items())
+
+
+class _PipelineSlot:
+    """A captured forward with a PRIVATE memory pool and its own stream, so that several can replay concurrently."""
+
+    def __init__(self, engine: FusedEngine, batch: Dict[str, torch.Tensor]):
+        self.captured = _CapturedForward(engine, batch, None)
+        self.stream = torch.cuda.Stream(device=engine.device)
+        self.device = engine.device
+
+    def launch(self, batch: Dict[str, torch.Tensor], copy_stream):
+        caller = torch.cuda.current_stream(self.device)
+        self.stream.wait_stream(caller)          # inputs made on the caller's stream; also orders after this slot's last hand-out
+        with torch.cuda.stream(self.stream):
+            outs = self.captured.replay(batch, copy_stream)
+            done = torch.cuda.Event()
+            done.record(self.stream)
+        return outs, done
+
+    @staticmethod
+    def collect(pending, device) -> "OrderedDict[str, torch.Tensor]":
+        outs, done = pending
+        caller = torch.cuda.current_stream(device)
+        caller.wait_event(done)
+        for v in outs.values():
+            v.record_stream(caller)
+        return outs

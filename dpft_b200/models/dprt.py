@@ -115,6 +115,30 @@ class DPRT(nn.Module):
                 return self._engine.forward(batch)
         return self.forward_composed(batch)
 
+    def infer_stream(self, batches, depth: int = 2):
+        """Inference over a sequence of equally shaped batches, yielding each batch's output dictionary in order.  On the
+        fused sm_100a pipeline up to ``depth`` forwards are in flight at once (``FusedEngine.stream``: one captured graph,
+        memory pool and stream per slot), which is how a serving / evaluation loop (reference
+        src/dprt/evaluation/evaluator.py:120-135) should drive the model; otherwise the batches run one after the other."""
+        from ..engine import FusedEngine
+        it = iter(batches)
+        try:
+            first = next(it)
+        except StopIteration:
+            return
+        import itertools
+        chain = itertools.chain([first], it)
+        if self.use_fused and not self.training and self.use_cuda_graph:
+            if self._engine is None:
+                self._engine = FusedEngine.try_create(self)
+            if self._engine is not None and self._engine.accepts(first):
+                yield from self._engine.stream(chain, depth)
+                return
+        for batch in chain:
+            with torch.no_grad():                    # (not held across the yield: grad mode is the caller's between items)
+                out = self(batch)
+            yield out
+
 
 def build_dprt(config: Dict[str, Any], *args, **kwargs) -> DPRT:
     return DPRT.from_config(config)

@@ -1,0 +1,66 @@
+"""DPRT.infer_stream (FusedEngine.stream): pipelined replay of consecutive forwards must give exactly what the one-at-a-time
+forward gives, in order, for device and pinned-host batches, any depth, and leave grad mode alone between items."""
+import pytest
+import torch
+
+from conftest import load_golden
+from helpers import case_setup
+from dpft_b200 import models, synthetic
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+def _setup():
+    rec = load_golden("fusion_small_300q")
+    cfg, _ = case_setup(rec)
+    model = models.build("dprt", cfg).eval()
+    model.load_state_dict(synthetic.seeded_state_dict(model.state_dict(), seed=rec["weight_seed"]), strict=True)
+    model = model.to(DEV)
+    batches = [synthetic.synthetic_batch(cfg, rec["case"]["batch"], seed=100 + i, sizes=rec["case"]["sizes"]) for i in range(5)]
+    return model, batches
+
+
+@pytest.mark.parametrize("depth", [1, 2, 3])
+@pytest.mark.parametrize("host", [False, True])
+def test_stream_equals_sequential_forward(depth, host):
+    model, batches = _setup()
+    dev_batches = [{k: v.to(DEV) for k, v in b.items()} for b in batches]
+    with torch.no_grad():
+        model.use_cuda_graph = False
+        want = [model(b) for b in dev_batches]
+        model.use_cuda_graph = True
+    feed = [{k: v.pin_memory() for k, v in b.items()} for b in batches] if host else dev_batches
+    order = [0, 1, 2, 3, 4, 2, 0, 4, 1]                         # more items than slots, repeats, both parities
+    got = []
+    for out in model.infer_stream((feed[i] for i in order), depth=depth):
+        assert torch.is_grad_enabled()                           # the generator does not leak no_grad into the caller
+        got.append({k: v.clone() for k, v in out.items()})
+    torch.cuda.synchronize()
+    assert len(got) == len(order)
+    for i, out in zip(order, got):
+        assert list(out) == ["center", "size", "angle", "class"]
+        for k in out:
+            assert torch.allclose(out[k], want[i][k], rtol=1e-5, atol=1e-5), (i, k)
+    assert len(model._engine._pipelines) == 1 and len(next(iter(model._engine._pipelines.values()))) == depth
+
+
+def test_stream_rejects_changing_shapes_and_handles_empty_input():
+    model, batches = _setup()
+    assert list(model.infer_stream(iter(()))) == []
+    b0 = {k: v.to(DEV) for k, v in batches[0].items()}
+    b1 = {k: v[:1].to(DEV) for k, v in batches[1].items()}
+    with pytest.raises(RuntimeError, match="same shapes"):
+        list(model.infer_stream([b0, b1]))
+
+
+def test_stream_falls_back_to_sequential_without_the_graph():
+    model, batches = _setup()
+    model.use_cuda_graph = False
+    dev_batches = [{k: v.to(DEV) for k, v in b.items()} for b in batches[:2]]
+    with torch.no_grad():
+        want = [model(b) for b in dev_batches]
+    got = list(model.infer_stream(dev_batches))
+    for a, b in zip(got, want):
+        for k in a:
+            assert torch.equal(a[k], b[k])
