@@ -8,15 +8,16 @@
 //   D[m, n] = act( sum_k A[m, k] * Wt[n, k] + bias[n] (+ residual[m, n]) )
 //   m = output pixel (b, p, q) linearised,  n = output channel,  k = (r, s, c) with c fastest.
 //
-// One persistent CTA per SM, 192 threads:
+// One persistent CTA per SM (or a CTA pair per 256-row tile, cta_group::2), 10 or 18 warps:
 //   warp 0   TMA producer   A tile (128 pixels x 64 channels of one filter tap) by an im2col-mode tensor map
 //                           (cp.async.bulk.tensor.4d...im2col; the tap (s, r) goes in the offset operands) or,
 //                           for 1x1/stride-1 layers, a plain 2-d tiled map over the [M, Cin] activation matrix;
 //                           B tile (BLOCK_N filters x 64) from the [Cout, R*S*Cin] weight matrix.  128B swizzle.
-//   warp 1   MMA issuer     one elected lane issues tcgen05.mma.cta_group::1.kind::f16 (M=128, N=BLOCK_N, K=16)
-//                           x4 per stage; tcgen05.commit releases the stage / publishes the accumulator.
-//   warps 2-5 epilogue      tcgen05.ld the fp32 accumulator (lane quadrant = warp_id % 4), + bias, + residual,
-//                           ReLU, pack to bf16, 16-byte global stores.
+//   warp 1   MMA issuer     one elected lane issues tcgen05.mma.kind::f16 (M=128 or 256, N=BLOCK_N, K=16) x4 per stage;
+//                           tcgen05.commit releases the stage / publishes the accumulator.
+//   warps 2+ epilogue       EG (2 or 4) warps per TMEM lane quadrant: tcgen05.ld the fp32 accumulator, + bias (smem copy of
+//                           the tile's bias), + residual (TMA-prefetched [32 x 64] sub-tiles), ReLU, cvt.satfinite pack into
+//                           a 128B-swizzled staging buffer, TMA store.
 // The accumulator is double-buffered in TMEM (2 x BLOCK_N columns) so the epilogue of tile i overlaps the
 // main loop of tile i+1.  Stages: a ring of STAGES {A 16 KB, B BLOCK_N*128 B} buffers with full/empty mbarriers.
 #include <cuda.h>
@@ -31,7 +32,8 @@ namespace {
 constexpr int BLOCK_M = 128;
 constexpr int BLOCK_K = 64;          // bf16 elements = 128 bytes = one swizzle row
 constexpr int UMMA_K = 16;
-constexpr int kNumThreads = 320;       // warp 0 TMA, warp 1 MMA, warps 2-9 epilogue (two per TMEM lane quadrant / scheduler)
+// warp 0 TMA, warp 1 MMA, then 4*EG epilogue warps: EG per TMEM lane quadrant (= per scheduler), each owning 64/EG of an item's columns
+constexpr int threads_for(int eg) { return (2 + 4 * eg) * 32; }
 
 enum ConvMode : int { kTiled2D = 0, kIm2col = 1 };
 
@@ -157,8 +159,8 @@ __device__ __forceinline__ void tmem_dealloc_2sm(uint32_t base, uint32_t cols) {
 }
 
 // ---- the kernel -------------------------------------------------------------------------------------------------
-template <int BLOCK_N, int STAGES, int EPI_RES_BUFS, int CG>
-__global__ void __launch_bounds__(kNumThreads, 1)
+template <int BLOCK_N, int STAGES, int EPI_RES_BUFS, int CG, int EG>
+__global__ void __launch_bounds__(threads_for(EG), 1)
 conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                  const __grid_constant__ CUtensorMap tmap_d, const __grid_constant__ CUtensorMap tmap_r,
                  const ConvParams prm) {
@@ -193,7 +195,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         }
         for (int i = 0; i < 2; ++i) {
             mbar_init(&tmem_full[i], 1);
-            mbar_init(&tmem_empty[i], 8 * CG);        // one arrive per epilogue warp (of both CTAs of a pair)
+            mbar_init(&tmem_empty[i], 4 * EG * CG);   // one arrive per epilogue warp (of both CTAs of a pair)
         }
         for (int i = 0; i < 4 * EPI_RES_BUFS; ++i) mbar_init(&res_bar[i], 1);
         fence_barrier_init();
@@ -307,7 +309,9 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         // are staged in shared memory (128-byte swizzle) and written by TMA; residual items are prefetched by TMA several
         // items ahead.  The pair synchronises with a 64-thread named barrier around the staging buffer.
         const int quad = warp & 3;
-        const int grp = (warp - 2) >> 2;              // 0 = A (issues the TMA traffic), 1 = B
+        const int grp = (warp - 2) >> 2;              // 0 .. EG-1: which 64/EG columns of an item; 0 issues the stores, 1 the residual loads
+        constexpr int WCOLS = EPI_COLS / EG;          // columns per warp and item (32 or 16)
+        constexpr int WCHUNKS = WCOLS / 8;            // 16-byte chunks per warp and row
         uint8_t* my_smem = smem_epi + quad * (EPI_RES_BUFS + EPI_OUT_BUFS) * EPI_BUF_BYTES;
         uint8_t* res_buf = my_smem;
         uint8_t* out_buf = my_smem + EPI_RES_BUFS * EPI_BUF_BYTES;
@@ -319,7 +323,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         const int total_items = my_tiles * kChunks;
         const bool issuer = grp == 0 && lane == 0;          // issues the TMA stores of the pair
         const bool loader = grp == 1 && lane == 0;          // issues the residual TMA loads of the pair
-        auto pair_sync = [&]() { asm volatile("bar.sync %0, 64;" ::"r"(2 + quad) : "memory"); };
+        auto pair_sync = [&]() { asm volatile("bar.sync %0, %1;" ::"r"(2 + quad), "n"(32 * EG) : "memory"); };
 
         auto prefetch_residual = [&](int item) {
             if (!has_res || item >= total_items) return;
@@ -346,7 +350,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
             const int n0 = n_tile * BLOCK_N;
             // this tile's bias -> the pair's shared-memory copy (the previous tile's readers are past their last pair_sync)
             float* bias_s = smem_bias + quad * BLOCK_N;
-            for (int i = (grp * 32 + lane) * 4; i < BLOCK_N; i += 64 * 4)
+            for (int i = (grp * 32 + lane) * 4; i < BLOCK_N; i += 32 * EG * 4)
                 *reinterpret_cast<float4*>(bias_s + i) = __ldg(reinterpret_cast<const float4*>(prm.bias + n0 + i));
             pair_sync();
             if (prm.out_f32) {
@@ -383,12 +387,13 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
             } else {
 #pragma unroll 1
                 for (int c = 0; c < kChunks; ++c, ++item) {
-                    uint32_t v[32];
+                    uint32_t v[WCOLS];
                     const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) +
-                                           (uint32_t)(acc * BLOCK_N + c * EPI_COLS + grp * 32);
-                    tmem_ld_32x32b_x32(taddr, v);
+                                           (uint32_t)(acc * BLOCK_N + c * EPI_COLS + grp * WCOLS);
+                    if constexpr (EG == 2) tmem_ld_32x32b_x32(taddr, v);
+                    else tmem_ld_32x32b_x16(taddr, v);
                     tmem_ld_wait();
-                    const float4* bias4 = reinterpret_cast<const float4*>(bias_s + c * EPI_COLS + grp * 32);
+                    const float4* bias4 = reinterpret_cast<const float4*>(bias_s + c * EPI_COLS + grp * WCOLS);
                     const uint8_t* rrow = res_buf + (item % EPI_RES_BUFS) * EPI_BUF_BYTES + lane * 128;
                     if (has_res) mbar_wait(&my_res_bar[item % EPI_RES_BUFS], (uint32_t)((item / EPI_RES_BUFS) & 1));
                     // the staging buffer of item-2 must have been read by its TMA store before it is overwritten
@@ -396,8 +401,8 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                     pair_sync();
                     uint8_t* orow = out_buf + (item % EPI_OUT_BUFS) * EPI_BUF_BYTES + lane * 128;
 #pragma unroll
-                    for (int jj = 0; jj < 4; ++jj) {               // 8 columns = one 16-byte chunk of the row
-                        const int j = grp * 4 + jj;                 // chunk index within the 128-byte row
+                    for (int jj = 0; jj < WCHUNKS; ++jj) {         // 8 columns = one 16-byte chunk of the row
+                        const int j = grp * WCHUNKS + jj;           // chunk index within the 128-byte row
                         float f[8];
                         const float4 b0 = bias4[2 * jj], b1 = bias4[2 * jj + 1];
                         f[0] = __uint_as_float(v[8 * jj]) + b0.x;     f[1] = __uint_as_float(v[8 * jj + 1]) + b0.y;
@@ -519,12 +524,12 @@ bool use_pdl() {
     return v != 0;
 }
 
-template <int BLOCK_N, int STAGES, int RES_BUFS, int CG = 1>
+template <int BLOCK_N, int STAGES, int RES_BUFS, int CG = 1, int EG = 2>
 int launch(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& td, const CUtensorMap& tr, const ConvParams& prm,
            cudaStream_t stream) {
     using L = SmemLayout<BLOCK_N, STAGES, RES_BUFS, CG>;
     static_assert(L::kTotal <= 232448, "shared memory budget of one CTA exceeded");
-    auto kern = conv_gemm_kernel<BLOCK_N, STAGES, RES_BUFS, CG>;
+    auto kern = conv_gemm_kernel<BLOCK_N, STAGES, RES_BUFS, CG, EG>;
     static bool configured = false;
     if (!configured) {
         int st = cuda_status(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -537,7 +542,7 @@ int launch(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& td, 
     const int grid = CG * (tiles < max_ctas ? tiles : max_ctas);
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3(grid);
-    cfg.blockDim = dim3(kNumThreads);
+    cfg.blockDim = dim3(threads_for(EG));
     cfg.dynamicSmemBytes = L::kTotal;
     cfg.stream = stream;
     cudaLaunchAttribute attr[2];
@@ -664,7 +669,7 @@ extern "C" int dpft_conv2d_nhwc(const void* x, const void* w, const float* bias,
         return launch<128, 6, 3, 2>(ta, tb, td, tr, prm, s2);
     }
     const bool stream_bound = residual != nullptr && prm.kblocks <= 4;   // 1x1 expand convs: deep residual prefetch
-    // tuning hook (tools/conv_bench.py --variants): DPFT_CONV_STREAM_VARIANT picks another stage / residual-buffer split
+    // tuning hook (with tools/conv_bench.py): DPFT_CONV_STREAM_VARIANT picks another stage / residual-buffer / epilogue-warp split
     static const int variant = [] { const char* e = getenv("DPFT_CONV_STREAM_VARIANT"); return e ? atoi(e) : 0; }();
     if (stream_bound && variant == 1) {
         if (bn == 256) return launch<256, 3, 2>(ta, tb, td, tr, prm, s);
@@ -674,7 +679,20 @@ extern "C" int dpft_conv2d_nhwc(const void* x, const void* w, const float* bias,
         if (bn == 256) return launch<256, 2, 3>(ta, tb, td, tr, prm, s);
         if (bn == 128) return launch<128, 3, 5>(ta, tb, td, tr, prm, s);
     }
-    if (bn == 256) return stream_bound ? launch<256, 2, 5>(ta, tb, td, tr, prm, s) : launch<256, 3, 2>(ta, tb, td, tr, prm, s);
-    if (bn == 128) return stream_bound ? launch<128, 2, 7>(ta, tb, td, tr, prm, s) : launch<128, 4, 3>(ta, tb, td, tr, prm, s);
-    return stream_bound ? launch<64, 3, 7>(ta, tb, td, tr, prm, s) : launch<64, 6, 3>(ta, tb, td, tr, prm, s);
+    if (stream_bound && variant == 3) {              // the two-warps-per-quadrant epilogue these layers used before
+        if (bn == 256) return launch<256, 2, 5>(ta, tb, td, tr, prm, s);
+        if (bn == 128) return launch<128, 2, 7>(ta, tb, td, tr, prm, s);
+        return launch<64, 3, 7>(ta, tb, td, tr, prm, s);
+    }
+    // Stream-bound layers run FOUR epilogue warps per TMEM lane quadrant (16 columns of an item each, 18 warps per CTA): the
+    // epilogue is a chain of dependent short operations (TMEM load, smem residual, pack, staging store), and four warps
+    // per scheduler hide its latency better than two (s1_conv3 97 -> 89 us = 0.91 of the HBM peak, whole step -1.7 %).
+    if (stream_bound) {
+        if (bn == 256) return launch<256, 2, 5, 1, 4>(ta, tb, td, tr, prm, s);
+        if (bn == 128) return launch<128, 2, 7, 1, 4>(ta, tb, td, tr, prm, s);
+        return launch<64, 3, 7, 1, 4>(ta, tb, td, tr, prm, s);
+    }
+    if (bn == 256) return launch<256, 3, 2>(ta, tb, td, tr, prm, s);
+    if (bn == 128) return launch<128, 4, 3>(ta, tb, td, tr, prm, s);
+    return launch<64, 6, 3>(ta, tb, td, tr, prm, s);
 }
