@@ -38,7 +38,7 @@ def launches(path, out_prefix):
         agg[name][1] += 1
     total = sum(v[0] for v in agg.values())
     with open(out_prefix + "_ncu_launches_eval_step.txt", "w") as f:
-        f.write("ncu --metrics gpu__time_duration.sum --clock-control none python tools/one_forward.py 2   (eager, serial streams; "
+        f.write("ncu --metrics gpu__time_duration.sum --clock-control none --profile-from-start off python tools/one_forward.py 2   (eager, serial streams; "
                 "cold-cache serialised launches: shares, not absolute times)\n")
         f.write(f"one eval forward of the bench workload: {len(step)} launches, {total / 1e3:.3f} ms summed\n\n")
         f.write(f"{'us':>10} {'share':>7} {'launches':>8}  kernel\n")
@@ -58,7 +58,7 @@ def conv_traffic(path, out_prefix):
         per_id[int(r["ID"])]["name"] = short(r["Kernel Name"])
         per_id[int(r["ID"])]["grid"] = r["Grid Size"]
     ids = sorted(per_id)
-    n = len(ids) // 2                         # two forwards were profiled; keep the second
+    n = len(ids) // 2 if len(ids) > 300 else 0    # two forwards profiled: keep the second; one (cudaProfilerStart range): keep all
     sel = [per_id[i] for i in ids[n:]]
 
     def to_bytes(v):
@@ -75,7 +75,7 @@ def conv_traffic(path, out_prefix):
     key = "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active"
     tw = sum(s[key][0] * to_us(s["gpu__time_duration.sum"]) for s in sel) / us
     summary = {"source": "ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum," + key +
-                         " --clock-control none -k regex:conv_gemm python tools/one_forward.py 2 (second forward)",
+                         " --clock-control none --profile-from-start off -k regex:conv_gemm python tools/one_forward.py (one eager forward, serial streams)",
                "launches": len(sel), "dram_read_bytes": rd, "dram_write_bytes": wr, "dram_bytes": rd + wr,
                "sum_duration_us_under_ncu": us, "tensor_pipe_active_pct_time_weighted": tw}
     with open(out_prefix + "_ncu_conv_traffic.json", "w") as f:
