@@ -569,12 +569,13 @@ int launch(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& td, 
 
 int pick_block_n(int Cout, int m_tiles, int want) {
     if (want == 64 || want == 128 || want == 256) return (Cout % want == 0) ? want : 64;
-    // largest tile that still leaves every SM a tile or so; small problems prefer more, smaller tiles
+    // largest tile that still gives three quarters of the SMs a tile (measured on the stage-4 layers, 58 m-tiles: 256-wide
+    // tiles on 116 CTAs beat 128-wide ones on 148; profiles/r01_conv_layers_v7_sweep.jsonl); small problems prefer more, smaller tiles
     const int cands[3] = {256, 128, 64};
     for (int i = 0; i < 3; ++i) {
         const int bn = cands[i];
         if (Cout % bn) continue;
-        if ((long long)m_tiles * (Cout / bn) >= (long long)g_sm_count || bn == 64) return bn;
+        if ((long long)m_tiles * (Cout / bn) * 4 >= (long long)g_sm_count * 3 || bn == 64) return bn;
     }
     return 64;
 }

@@ -323,6 +323,7 @@ fpn_output_tc_kernel(const FpnOutParams prm) {
     uint64_t* bars = reinterpret_cast<uint64_t*>(s_b + TC_B_BYTES);
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + TC_TH);
     float* s_lat = reinterpret_cast<float*>(tmem_slot + 4);          // [16][CIN] + [16]
+    float* s_py = s_lat + FC * 6 + FC;                                // [TC_TH][16]: pos_y rows of this tile (+ bias)
     const int b = blockIdx.z;
     const int p0 = blockIdx.y * TC_TH, q0 = blockIdx.x * TC_TW;
     const int tid = threadIdx.x, warp = tid >> 5;
@@ -335,6 +336,10 @@ fpn_output_tc_kernel(const FpnOutParams prm) {
         tc::fence_barrier_init();
     }
     for (int i = tid; i < TC_B_BYTES / 16; i += TC_THREADS) reinterpret_cast<uint4*>(s_b)[i] = __ldg(prm.w_packed + i);
+    if (tid < TC_TH * FC) {                      // pos_y[p] + bias for the tile's rows: the epilogue reads them from shared memory
+        const int r = tid / FC, c = tid - r * FC;
+        s_py[tid] = (p0 + r < H ? __ldg(prm.pos_y + (long long)(p0 + r) * FC + c) : 0.0f) + __ldg(prm.bias + c);
+    }
     if (CIN > 0) {
         for (int i = tid; i < FC * CIN; i += TC_THREADS) s_lat[i] = __ldg(prm.lat_w + i);
         if (tid < FC) s_lat[FC * CIN + tid] = __ldg(prm.lat_b + tid);
@@ -423,31 +428,32 @@ fpn_output_tc_kernel(const FpnOutParams prm) {
         }
     }
     __syncwarp();
-    // epilogue: thread t <-> pixel q0 + t <-> TMEM lane t
-    const int q = q0 + tid;
-    float4 px4[4], bias4[4];
+    // epilogue: all eight warps; warps w and w+4 share TMEM lane quadrant w%4 (pixels q0 + 32*(w%4) + lane) and take the
+    // first / second half of the tile's rows
+    const int lane_px = (warp & 3) * 32 + (tid & 31);
+    const int q = q0 + lane_px;
+    float4 px4[4];
 #pragma unroll
-    for (int c4 = 0; c4 < 4; ++c4) {
-        px4[c4] = (q < W && warp < 4) ? __ldg(reinterpret_cast<const float4*>(prm.pos_x + (long long)q * FC) + c4) : make_float4(0, 0, 0, 0);
-        bias4[c4] = __ldg(reinterpret_cast<const float4*>(prm.bias) + c4);
-    }
-    for (int r = 0; r < TC_TH && warp < 4; ++r) {
+    for (int c4 = 0; c4 < 4; ++c4)
+        px4[c4] = q < W ? __ldg(reinterpret_cast<const float4*>(prm.pos_x + (long long)q * FC) + c4) : make_float4(0, 0, 0, 0);
+    const int r_begin = (warp >> 2) * (TC_TH / 2);
+    for (int r = r_begin; r < r_begin + TC_TH / 2; ++r) {
         tc::mbar_wait(&bars[r], 0);
         tc::tcgen05_fence_after();
         uint32_t v[16];
-        tc::tmem_ld_32x32b_x16(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(r * 16), v);
+        tc::tmem_ld_32x32b_x16(tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(r * 16), v);
         tc::tmem_ld_wait();
         const int p = p0 + r;
         if (p < H && q < W) {
-            const float4* py = reinterpret_cast<const float4*>(prm.pos_y + (long long)p * FC);
+            const float4* py = reinterpret_cast<const float4*>(s_py + r * FC);     // pos_y + bias
             float outv[FC];
 #pragma unroll
             for (int c4 = 0; c4 < 4; ++c4) {
-                const float4 c = __ldg(py + c4);
-                outv[4 * c4] = ((__uint_as_float(v[4 * c4]) + bias4[c4].x) + px4[c4].x) + c.x;
-                outv[4 * c4 + 1] = ((__uint_as_float(v[4 * c4 + 1]) + bias4[c4].y) + px4[c4].y) + c.y;
-                outv[4 * c4 + 2] = ((__uint_as_float(v[4 * c4 + 2]) + bias4[c4].z) + px4[c4].z) + c.z;
-                outv[4 * c4 + 3] = ((__uint_as_float(v[4 * c4 + 3]) + bias4[c4].w) + px4[c4].w) + c.w;
+                const float4 c = py[c4];
+                outv[4 * c4] = (__uint_as_float(v[4 * c4]) + c.x) + px4[c4].x;
+                outv[4 * c4 + 1] = (__uint_as_float(v[4 * c4 + 1]) + c.y) + px4[c4].y;
+                outv[4 * c4 + 2] = (__uint_as_float(v[4 * c4 + 2]) + c.z) + px4[c4].z;
+                outv[4 * c4 + 3] = (__uint_as_float(v[4 * c4 + 3]) + c.w) + px4[c4].w;
             }
             store_pyramid_row(prm.pyramid, (long long)b * prm.S + prm.start + (long long)p * W + q, outv, prm.pyramid_f16 != 0);
         }
@@ -500,6 +506,7 @@ stem_tc_kernel(const float* __restrict__ x, const uint4* __restrict__ w_packed, 
     uint8_t* s_b = tsm + ST_A_BYTES;
     uint64_t* bars = reinterpret_cast<uint64_t*>(s_b + ST_B_BYTES);
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + ST_TH);
+    float* s_bias = reinterpret_cast<float*>(tmem_slot + 4);         // [64]
     const int b = blockIdx.z;
     const int p0 = blockIdx.y * ST_TH, q0 = blockIdx.x * ST_TW;
     const int tid = threadIdx.x, warp = tid >> 5;
@@ -512,6 +519,7 @@ stem_tc_kernel(const float* __restrict__ x, const uint4* __restrict__ w_packed, 
     }
     // weights: the pre-packed f16 UMMA image
     for (int i = tid; i < ST_B_BYTES / 16; i += ST_THREADS) reinterpret_cast<uint4*>(s_b)[i] = __ldg(w_packed + i);
+    if (tid < STEM_COUT) s_bias[tid] = __ldg(bias + tid);
     // input tile: rows 2*p0-3 .. 2*p0-3+ST_ROWS-1, columns 2*q0-3 .. (+2*ST_PLANE_ENTRIES-1), even/odd planes
     const int h_base = 2 * p0 - 3, w_base = 2 * q0 - 3;
     // (batches of ST_BATCH entries per thread: all global loads of a batch are issued before any is converted)
@@ -566,23 +574,25 @@ stem_tc_kernel(const float* __restrict__ x, const uint4* __restrict__ w_packed, 
         }
     }
     __syncwarp();
-    const int q = q0 + tid;
-    for (int pr = 0; pr < ST_TH && warp < 4; ++pr) {
+    // epilogue: all eight warps; warps w and w+4 share TMEM lane quadrant w%4 and take the first / second half of the rows
+    const int q = q0 + (warp & 3) * 32 + (tid & 31);
+    const int pr_begin = (warp >> 2) * (ST_TH / 2);
+    for (int pr = pr_begin; pr < pr_begin + ST_TH / 2; ++pr) {
         tc::mbar_wait(&bars[pr], 0);
         tc::tcgen05_fence_after();
         const int p = p0 + pr;
 #pragma unroll
         for (int half = 0; half < 2; ++half) {
             uint32_t v[32];
-            tc::tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(pr * 64 + half * 32), v);
+            tc::tmem_ld_32x32b_x32(tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(pr * 64 + half * 32), v);
             tc::tmem_ld_wait();
             if (p < P && q < Q) {
                 OT* o = y + (((long long)b * P + p) * Q + q) * STEM_COUT + half * 32;
 #pragma unroll
                 for (int o8 = 0; o8 < 4; ++o8) {
                     uint4 pk;
-                    const float4 b0v = __ldg(reinterpret_cast<const float4*>(bias + half * 32 + o8 * 8));
-                    const float4 b1v = __ldg(reinterpret_cast<const float4*>(bias + half * 32 + o8 * 8 + 4));
+                    const float4 b0v = *reinterpret_cast<const float4*>(s_bias + half * 32 + o8 * 8);
+                    const float4 b1v = *reinterpret_cast<const float4*>(s_bias + half * 32 + o8 * 8 + 4);
                     const float bb[8] = {b0v.x, b0v.y, b0v.z, b0v.w, b1v.x, b1v.y, b1v.z, b1v.w};
 #pragma unroll
                     for (int t = 0; t < 4; ++t) {
@@ -610,7 +620,7 @@ template <int CIN, typename OT>
 static int launch_stem_tc(const float* x, const void* w_packed, const float* bias, void* y, int B, int H, int W, int P, int Q,
                           float lo, cudaStream_t s) {
     auto kern = stem_tc_kernel<CIN, OT>;
-    const size_t smem = ST_A_BYTES + ST_B_BYTES + ST_TH * 8 + 16;
+    const size_t smem = ST_A_BYTES + ST_B_BYTES + ST_TH * 8 + 16 + STEM_COUT * sizeof(float);
     static bool configured = false;
     if (!configured) {
         int st = cuda_status(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "stem tc attr");
@@ -731,7 +741,7 @@ extern "C" int dpft_fpn_output_forward(const float* inner, const float* raw, int
     DPFT_REQUIRE(impl != 2 || w_packed, "fpn_output: the tensor-core kernel needs the packed weights (dpft_fpn_pack_weights)");
     if (impl == 2 || (impl == 0 && W >= 96 && w_packed)) {          // wide levels: 128-pixel row strips on the tensor cores
         const dim3 tgrid((W + TC_TW - 1) / TC_TW, (H + TC_TH - 1) / TC_TH, B);
-        const size_t smem = TC_A_BYTES + TC_B_BYTES + TC_TH * 8 + 16 + sizeof(float) * (FC * 6 + FC);
+        const size_t smem = TC_A_BYTES + TC_B_BYTES + TC_TH * 8 + 16 + sizeof(float) * (FC * 6 + FC + TC_TH * FC);
         static bool configured = false;
         if (!configured) {
             int st = cuda_status(cudaFuncSetAttribute(fpn_output_tc_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "fpn tc attr");
