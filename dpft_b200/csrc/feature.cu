@@ -505,7 +505,7 @@ stem_tc_kernel(const float* __restrict__ x, const uint4* __restrict__ w_packed, 
     uint8_t* s_a = tsm;
     uint8_t* s_b = tsm + ST_A_BYTES;
     uint64_t* bars = reinterpret_cast<uint64_t*>(s_b + ST_B_BYTES);
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + ST_TH);
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + ST_TH + 2);   // (+2 keeps s_bias 16-byte aligned)
     float* s_bias = reinterpret_cast<float*>(tmem_slot + 4);         // [64]
     const int b = blockIdx.z;
     const int p0 = blockIdx.y * ST_TH, q0 = blockIdx.x * ST_TW;
@@ -514,11 +514,14 @@ stem_tc_kernel(const float* __restrict__ x, const uint4* __restrict__ w_packed, 
     if (warp == 0) {
         tc::tmem_alloc(tmem_slot, ST_TH * 64);
     } else if (tid == 32) {
-        for (int r = 0; r < ST_TH; ++r) tc::mbar_init(&bars[r], 1);
+        for (int r = 0; r <= ST_TH; ++r) tc::mbar_init(&bars[r], 1);
         tc::fence_barrier_init();
+        // weights: the pre-packed f16 UMMA image, one bulk async copy (57 KB) that lands while the threads build the input tile
+        tc::mbar_expect_tx(&bars[ST_TH], ST_B_BYTES);
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(tc::smem_u32(s_b)),
+                     "l"(w_packed), "r"((uint32_t)ST_B_BYTES), "r"(tc::smem_u32(&bars[ST_TH]))
+                     : "memory");
     }
-    // weights: the pre-packed f16 UMMA image
-    for (int i = tid; i < ST_B_BYTES / 16; i += ST_THREADS) reinterpret_cast<uint4*>(s_b)[i] = __ldg(w_packed + i);
     if (tid < STEM_COUT) s_bias[tid] = __ldg(bias + tid);
     // input tile: rows 2*p0-3 .. 2*p0-3+ST_ROWS-1, columns 2*q0-3 .. (+2*ST_PLANE_ENTRIES-1), even/odd planes
     const int h_base = 2 * p0 - 3, w_base = 2 * q0 - 3;
@@ -558,6 +561,7 @@ stem_tc_kernel(const float* __restrict__ x, const uint4* __restrict__ w_packed, 
     const uint32_t tmem_base = *tmem_slot;
 
     if (tid == 0) {
+        tc::mbar_wait(&bars[ST_TH], 0);              // the weight image has landed (async proxy -> async proxy: no fence needed)
         constexpr uint32_t idesc = tc::umma_idesc_16bit(128, 64, true);
         const uint32_t a0 = tc::smem_u32(s_a), b0 = tc::smem_u32(s_b);
         for (int pr = 0; pr < ST_TH; ++pr) {
@@ -620,7 +624,7 @@ template <int CIN, typename OT>
 static int launch_stem_tc(const float* x, const void* w_packed, const float* bias, void* y, int B, int H, int W, int P, int Q,
                           float lo, cudaStream_t s) {
     auto kern = stem_tc_kernel<CIN, OT>;
-    const size_t smem = ST_A_BYTES + ST_B_BYTES + ST_TH * 8 + 16 + STEM_COUT * sizeof(float);
+    const size_t smem = ST_A_BYTES + ST_B_BYTES + (ST_TH + 2) * 8 + 16 + STEM_COUT * sizeof(float);
     static bool configured = false;
     if (!configured) {
         int st = cuda_status(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "stem tc attr");
