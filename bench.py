@@ -55,6 +55,7 @@ def parse():
                     help="infer: eval forward (headline).  train: fwd+bwd+gradient all-reduce+AdamW (BASELINE config 4)")
     ap.add_argument("--depth", type=int, default=3,
                     help="forwards in flight in the timed loop (DPRT.infer_stream); 1 = one forward at a time with an L2 flush between steps")
+    ap.add_argument("--side-priority", action="store_true", help="A/B: the radar views on high-priority streams")
     ap.add_argument("--no-graph", action="store_true", help="train mode: issue the step eagerly instead of replaying one CUDA graph")
     ap.add_argument("--dtype", default="f16", choices=["f16", "bf16", "f32"],
                     help="activation type of the native backbone (f32 = fused decoder on torch fp32 features)")
@@ -370,6 +371,7 @@ def main():
     sd = synthetic.seeded_state_dict(model.state_dict(), seed=1)
     model.load_state_dict(sd)
     model = model.to(dev)
+    model.side_view_priority = args.side_priority
     if args.dtype == "f32":
         model.native_features = False
     else:

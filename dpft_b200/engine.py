@@ -63,6 +63,7 @@ class FusedEngine:
         self._seen: Dict[tuple, int] = {}
         self._slot = 0
         self._side_streams = [torch.cuda.Stream(device=self.device) for _ in range(max(0, len(model.inputs) - 1))]
+        self._side_streams_hp = [torch.cuda.Stream(device=self.device, priority=-1) for _ in range(max(0, len(model.inputs) - 1))]
         self._copy_stream = torch.cuda.Stream(device=self.device)
 
     # -- construction ---------------------------------------------------------------------------------------------
@@ -132,7 +133,10 @@ class FusedEngine:
                 if k == 0:
                     flat, shapes = self.views[i].pyramid(batch[name])
                 else:
-                    side = self._side_streams[k - 1]
+                    # model.side_view_priority: the small (radar) views on HIGH-priority streams get SMs as soon as any
+                    # frees up and are out of the way early; on normal streams they interleave with the first view's kernels
+                    hp = getattr(model, "side_view_priority", False)
+                    side = (self._side_streams_hp if hp else self._side_streams)[k - 1]
                     side.wait_event(fork)
                     with torch.cuda.stream(side):
                         flat, shapes = self.views[i].pyramid(batch[name])

@@ -61,6 +61,7 @@ class DPRT(nn.Module):
         self.pyramid_dtype = torch.float16    # storage of the native (B, S, 16) feature pyramid: float16 or float32
         self.use_cuda_graph = True     # fused pipeline: replay a captured graph once an input shape repeats
         self.parallel_views = True     # fused pipeline: run the per-view feature extractors on forked streams
+        self.side_view_priority = False     # ... the other views on high-priority streams (measured: no gain)
         self.native_train = True       # train() on CUDA: ResNet stages through the sm_100a training kernels (16-bit
                                        # activations, dpft_b200/train_backbone.py); False = torch/cuDNN autograd in fp32
         self.train_dtype = torch.float16
