@@ -13,6 +13,11 @@ namespace dpft {
 void set_error(const char* fmt, ...);
 int cuda_status(cudaError_t e, const char* what);  // 0 on success, else records + returns (int)e
 
+// conv3x3_halo.cu: the 64 -> 64 channel 3x3 convolution over a shared-memory halo tile (dispatched from dpft_conv2d_nhwc)
+bool conv3x3_halo_eligible(int H, int W, int Cin, int Cout, int R, int S, int stride, int pad, bool has_residual);
+int conv3x3_halo_launch(const void* x, const void* w, const float* bias, void* y, int B, int H, int W, int relu, bool is_f16,
+                        cudaStream_t stream);
+
 #define DPFT_REQUIRE(cond, ...)                      \
     do {                                             \
         if (!(cond)) {                               \

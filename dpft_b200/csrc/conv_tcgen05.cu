@@ -622,6 +622,9 @@ extern "C" int dpft_conv2d_nhwc(const void* x, const void* w, const float* bias,
     if (st) return st;
     const int P = (H + 2 * pad - R) / stride + 1, Q = (W + 2 * pad - S) / stride + 1;
     DPFT_REQUIRE(P > 0 && Q > 0, "conv2d: empty output");
+    // 64 -> 64 channel 3x3 layers on wide maps: halo-tile kernel (input staged once instead of once per tap)
+    if (block_n == 0 && cluster_mode == 0 && conv3x3_halo_eligible(H, W, Cin, Cout, R, S, stride, pad, residual != nullptr))
+        return conv3x3_halo_launch(x, w, bias, y, B, H, W, relu, is_f16, (cudaStream_t)stream);
     ConvParams prm{};
     prm.M = B * P * Q; prm.N = Cout; prm.P = P; prm.Q = Q; prm.taps_s = S; prm.cblocks = Cin / 64;
     prm.kblocks = R * S * prm.cblocks; prm.stride = stride; prm.pad = pad; prm.relu = relu; prm.is_f16 = is_f16;

@@ -90,6 +90,36 @@ def test_expand_conv_with_residual_matches_torch_fp32(shape, dtype, relu):
     assert (auto.float() - got.float()).abs().max().item() <= 2.0 ** -7 * scale
 
 
+# 64 -> 64 channel 3x3 layers on wide maps go through the halo-tile kernel (conv3x3_halo.cu): width / height tails, a width that
+# is not a multiple of the 128-column tile, odd heights (last tile has one row), several images, more tiles than SMs
+HALO_SHAPES = [(1, 2, 128), (2, 7, 130), (1, 9, 96), (3, 33, 200), (2, 16, 320), (8, 45, 257), (1, 181, 131)]
+
+
+@pytest.mark.parametrize("shape", HALO_SHAPES)
+@pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16])
+@pytest.mark.parametrize("relu", [True, False])
+def test_halo_conv3x3_matches_torch_fp32(shape, dtype, relu):
+    from dpft_b200 import conv
+    B, H, W = shape
+    dev = "cuda:0"
+    g = torch.Generator(device=dev).manual_seed(H * 1000 + W)
+    x = torch.randn(B, H, W, 64, generator=g, device=dev).to(dtype)
+    w = (torch.randn(64, 3, 3, 64, generator=g, device=dev) / 24.0).to(dtype)
+    bias = torch.randn(64, generator=g, device=dev)
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    want = _reference(x, w, bias, 1, 1, relu, None)
+    scale = want.abs().max().item()
+    got = conv.conv2d_nhwc(x, w, bias, 1, 1, relu)                       # heuristic path = halo kernel for these shapes
+    generic = conv.conv2d_nhwc(x, w, bias, 1, 1, relu, block_n=64)       # forcing a tile keeps the im2col kernel
+    torch.cuda.synchronize()
+    assert got.shape == (B, H, W, 64) and got.dtype == dtype
+    err = (got.float() - want).abs().max().item()
+    assert err <= (2.0 ** -7 if dtype == torch.bfloat16 else 2.0 ** -10) * scale, (err, scale)   # output rounding only
+    # both kernels accumulate the same 576 products in fp32 (in a different order): at most one 16-bit ulp apart
+    assert (got.float() - generic.float()).abs().max().item() <= 2.0 ** -7 * scale
+
+
 def test_folded_bottleneck_matches_torch_block():
     """conv+bn folding and the residual/ReLU epilogue reproduce a torchvision-style bottleneck in eval mode."""
     from dpft_b200 import conv
