@@ -203,10 +203,10 @@ def conv_roofline(model, resident, dev, tf_peak, peak_src):
             with open(os.path.join(ROOT, "profiles", name)) as f:
                 t = json.load(f)
             traffic, traffic_src = t["dram_bytes"], f"profiles/{name}: dram__bytes_read.sum + dram__bytes_write.sum over " \
-                f"{t['launches']} conv_gemm_kernel launches of one step (ncu, bs 8 bench workload); tensor pipe active " \
+                f"{t['launches']} tcgen05 convolution launches of one step (ncu, bs 8 bench workload); tensor pipe active " \
                 f"{t['tensor_pipe_active_pct_time_weighted']:.1f} % time-weighted"
             break
-    return {"kernel": "conv_gemm_kernel (all %d backbone conv launches of one step)" % len(prof), "bound": "tensor",
+    return {"kernel": "conv_gemm_kernel / conv3x3_halo_kernel (all %d backbone conv launches of one step)" % len(prof), "bound": "tensor",
             "achieved": achieved, "peak": tf_peak, "unit": "TFLOP/s", "frac": achieved / tf_peak, "traffic": traffic,
             "traffic_source": traffic_src,
             "peak_source": peak_src + ", bf16_tflops_sustained (kernel timed inside a long step)",

@@ -667,14 +667,15 @@ extern "C" int dpft_conv2d_nhwc(const void* x, const void* w, const float* bias,
     st = encode_2d(&tr, residual ? residual : y, (uint64_t)Cout, (uint64_t)prm.M, (uint64_t)Cout * 2, EPI_COLS, 32, is_f16);
     if (st) return st;
     cudaStream_t s = (cudaStream_t)stream;
+    // tuning hook (with tools/conv_bench.py): DPFT_CONV_STREAM_VARIANT picks another stage / residual-buffer / epilogue-warp split
+    static const int variant = [] { const char* e = getenv("DPFT_CONV_STREAM_VARIANT"); return e ? atoi(e) : 0; }();
     if (pairs) {
         cudaStream_t s2 = (cudaStream_t)stream;
+        // (four epilogue warps per lane quadrant were tried here as well: no gain, 37.9 -> 38.9 us on s3_conv2)
         if (bn == 256) return launch<256, 4, 3, 2>(ta, tb, td, tr, prm, s2);
         return launch<128, 6, 3, 2>(ta, tb, td, tr, prm, s2);
     }
     const bool stream_bound = residual != nullptr && prm.kblocks <= 4;   // 1x1 expand convs: deep residual prefetch
-    // tuning hook (with tools/conv_bench.py): DPFT_CONV_STREAM_VARIANT picks another stage / residual-buffer / epilogue-warp split
-    static const int variant = [] { const char* e = getenv("DPFT_CONV_STREAM_VARIANT"); return e ? atoi(e) : 0; }();
     if (stream_bound && variant == 1) {
         if (bn == 256) return launch<256, 3, 2>(ta, tb, td, tr, prm, s);
         if (bn == 128) return launch<128, 4, 3>(ta, tb, td, tr, prm, s);
