@@ -11,7 +11,7 @@ r=json.loads(sys.stdin.read()); print('ms', r['ms_per_step'], 'fps', r['value'],
 tail -2 gpurun_out/bench.err
 timeout 600 python bench.py --mode train --steps 10 --warmup 3 > gpurun_out/bench_train.json 2> gpurun_out/bench_train.err
 tail -1 gpurun_out/bench_train.json | cut -c1-160
-timeout 600 python tools/stage_times.py > gpurun_out/stage_times.json 2> gpurun_out/stage_times.err; cat gpurun_out/stage_times.json
+timeout 300 python tools/stage_times.py > gpurun_out/stage_times.json 2> gpurun_out/stage_times.err; cat gpurun_out/stage_times.json
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none --profile-from-start off --csv --log-file gpurun_out/launches_eval_step.csv python tools/one_forward.py 2 > gpurun_out/ncu_launches.log 2>&1
 timeout 900 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum,sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active --clock-control none --profile-from-start off -k 'regex:conv_gemm|conv3x3_halo' --csv --log-file gpurun_out/conv_traffic.csv python tools/one_forward.py 1 > gpurun_out/ncu_conv_traffic.log 2>&1
 wc -l gpurun_out/launches_eval_step.csv gpurun_out/conv_traffic.csv
