@@ -16,6 +16,8 @@
 // All three are HBM-bound (N = 16 output channels, tiny K): coalesced 16-byte accesses, halo tiles in shared memory.
 #include <type_traits>
 
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "tcgen05.cuh"
 
@@ -620,9 +622,213 @@ stem_tc_kernel(const float* __restrict__ x, const uint4* __restrict__ w_packed, 
     }
 }
 
+// ---- the same stem as a ROW-STREAMING pipeline --------------------------------------------------------------------------
+// stem_tc_kernel builds 13 input rows to produce 4 output rows (3.25 input rows per output row instead of 2) and runs its
+// phases — weights, tile build, multiply, drain — one after the other in a short-lived CTA.  Here a CTA owns (image, 128-column
+// strip, chunk of ~P / chunks output rows) and its warps specialise:
+//   warps 4-7  builders: warp w converts input rows i = w, w + 4, ... (fp32 -> f16, even / odd column planes) into a ring of
+//              12 rows; every input row of the chunk is built once
+//   warp 8     the 57 KB weight image by one bulk async copy, then per output row 7 x 4 tcgen05.mma (M=128, N=64, K=16) on
+//              ring rows 2j .. 2j+6 into one of four TMEM accumulators; the commit releases rows 2j and 2j+1
+//   warps 0-3  drain (TMEM lane quadrant = 32 output columns): + bias, clamp, 16-bit pack, 128 contiguous bytes per pixel
+// Two CTAs fit per SM (110 KB of shared memory, 256 TMEM columns each).
+constexpr int SS_RING = 12;
+constexpr int SS_ACCS = 4;
+constexpr int SS_THREADS = 288;
+constexpr int SS_SMEM = ST_B_BYTES + SS_RING * ST_ROWB + STEM_COUT * 4 + (2 * SS_RING + 1 + 2 * SS_ACCS) * 8 + 16;
+
+template <int CIN, typename OT>
+__global__ void __launch_bounds__(SS_THREADS)
+stem_stream_kernel(const float* __restrict__ x, const uint4* __restrict__ w_packed, const float* __restrict__ bias,
+                   OT* __restrict__ y, int H, int W, int P, int Q, float lo, int strips, int chunks, int chunk_rows) {
+    extern __shared__ __align__(128) uint8_t tsm[];
+    uint8_t* s_b = tsm;
+    uint8_t* s_a = tsm + ST_B_BYTES;
+    float* s_bias = reinterpret_cast<float*>(s_a + SS_RING * ST_ROWB);
+    uint64_t* row_full = reinterpret_cast<uint64_t*>(s_bias + STEM_COUT);
+    uint64_t* row_empty = row_full + SS_RING;
+    uint64_t* w_bar = row_empty + SS_RING;
+    uint64_t* tmem_full = w_bar + 1;
+    uint64_t* tmem_empty = tmem_full + SS_ACCS;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + SS_ACCS);
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int unit = blockIdx.x;
+    const int chunk = unit % chunks;
+    const int strip = (unit / chunks) % strips;
+    const int b = unit / (chunks * strips);
+    const int p_begin = chunk * chunk_rows, q0 = strip * ST_TW;
+    const int n_out = min(chunk_rows, P - p_begin);          // output rows of this CTA (>= 1)
+    const int n_in = 2 * n_out + 5;                            // input rows 2*p_begin - 3 .. 2*(p_begin + n_out - 1) + 3
+    const int h_base = 2 * p_begin - 3, w_base = 2 * q0 - 3;
+
+    if (warp == 8) {
+        tc::tmem_alloc(tmem_slot, SS_ACCS * 64);
+    } else if (tid == 0) {
+        for (int i = 0; i < SS_RING; ++i) {
+            tc::mbar_init(&row_full[i], 1);
+            tc::mbar_init(&row_empty[i], 1);
+        }
+        for (int i = 0; i < SS_ACCS; ++i) {
+            tc::mbar_init(&tmem_full[i], 1);
+            tc::mbar_init(&tmem_empty[i], 4);
+        }
+        tc::mbar_init(w_bar, 1);
+        tc::fence_barrier_init();
+    }
+    if (tid < STEM_COUT) s_bias[tid] = __ldg(bias + tid);
+    tc::tcgen05_fence_before();
+    __syncthreads();
+    tc::tcgen05_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp >= 4 && warp < 8) {
+        // ================================ builders: one input row per warp and turn ================================
+        constexpr int ENTRIES = 2 * ST_PLANE_ENTRIES;        // 272 column entries per row (even + odd plane)
+        constexpr int PER_LANE = (ENTRIES + 31) / 32;        // 9
+        for (int i = warp - 4; i < n_in; i += 4) {
+            const int slot = i % SS_RING;
+            tc::mbar_wait(&row_empty[slot], ((i / SS_RING) & 1) ^ 1);
+            const int hh = h_base + i;
+            const bool row_ok = hh >= 0 && hh < H;
+            const float* xrow = x + ((long long)b * H + (row_ok ? hh : 0)) * W * CIN;
+            float v[PER_LANE][CIN];
+#pragma unroll
+            for (int u = 0; u < PER_LANE; ++u) {             // all global loads of the row first
+                const int xl = lane + u * 32;
+                const int ww = w_base + xl;
+                const bool ok = row_ok && xl < ENTRIES && ww >= 0 && ww < W;
+                const float* xp = xrow + (long long)(ok ? ww : 0) * CIN;
+#pragma unroll
+                for (int c = 0; c < CIN; ++c) v[u][c] = ok ? __ldg(xp + c) : 0.0f;
+            }
+            uint8_t* dst = s_a + slot * ST_ROWB;
+#pragma unroll
+            for (int u = 0; u < PER_LANE; ++u) {
+                const int xl = lane + u * 32;
+                if (xl < ENTRIES) {
+                    __align__(16) __half hv[8];
+#pragma unroll
+                    for (int c = 0; c < 8; ++c) hv[c] = __float2half_rn(c < CIN ? v[u][c < CIN ? c : 0] : 0.0f);
+                    *reinterpret_cast<uint4*>(dst + (xl & 1) * ST_PLANE + (xl >> 1) * 16) = *reinterpret_cast<uint4*>(hv);
+                }
+            }
+            tc::fence_proxy_async();                          // generic-proxy writes -> visible to the tensor core
+            __syncwarp();
+            if (lane == 0) tc::mbar_arrive(&row_full[slot]);
+        }
+    } else if (warp == 8) {
+        // ====================================== weights + MMA issuer ======================================
+        if (lane == 0) {
+            tc::mbar_expect_tx(w_bar, ST_B_BYTES);
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(tc::smem_u32(s_b)),
+                         "l"(w_packed), "r"((uint32_t)ST_B_BYTES), "r"(tc::smem_u32(w_bar))
+                         : "memory");
+        }
+        tc::mbar_wait(w_bar, 0);
+        constexpr uint32_t idesc = tc::umma_idesc_16bit(128, 64, true);
+        const uint32_t a0 = tc::smem_u32(s_a), b0 = tc::smem_u32(s_b);
+        for (int j = 0; j < n_out; ++j) {
+            const int acc = j % SS_ACCS;
+            tc::mbar_wait(&tmem_empty[acc], ((j / SS_ACCS) & 1) ^ 1);
+            for (int r = (j == 0 ? 0 : 5); r < 7; ++r) {     // rows 2j .. 2j+4 were awaited by the previous output row
+                const int i = 2 * j + r;
+                tc::mbar_wait(&row_full[i % SS_RING], (i / SS_RING) & 1);
+            }
+            tc::tcgen05_fence_after();
+            if (tc::elect_one()) {
+#pragma unroll 1
+                for (int r = 0; r < 7; ++r) {
+                    const uint32_t row = a0 + ((2 * j + r) % SS_RING) * ST_ROWB;
+#pragma unroll
+                    for (int t = 0; t < 4; ++t) {
+                        const uint64_t adesc = tc::umma_desc_noswizzle(row + t * 16, ST_PLANE, 128);
+                        const uint64_t bdesc = tc::umma_desc_noswizzle(b0 + (r * 4 + t) * 2048, 1024, 128);
+                        tc::umma_bf16(tmem_base + acc * 64, adesc, bdesc, idesc, (r | t) ? 1u : 0u);
+                    }
+                }
+                tc::umma_commit(&tmem_full[acc]);
+                tc::umma_commit(&row_empty[(2 * j) % SS_RING]);       // input rows 2j and 2j+1 are not read again
+                tc::umma_commit(&row_empty[(2 * j + 1) % SS_RING]);
+            }
+            __syncwarp();
+        }
+    } else {
+        // =========================================== drain ===========================================
+        const int q = q0 + warp * 32 + lane;
+        for (int j = 0; j < n_out; ++j) {
+            const int acc = j % SS_ACCS;
+            const int p = p_begin + j;
+            tc::mbar_wait(&tmem_full[acc], (j / SS_ACCS) & 1);
+            tc::tcgen05_fence_after();
+#pragma unroll
+            for (int half = 0; half < 2; ++half) {
+                uint32_t v[32];
+                tc::tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(acc * 64 + half * 32), v);
+                tc::tmem_ld_wait();
+                if (q < Q) {
+                    OT* o = y + (((long long)b * P + p) * Q + q) * STEM_COUT + half * 32;
+#pragma unroll
+                    for (int o8 = 0; o8 < 4; ++o8) {
+                        uint4 pk;
+                        const float4 b0v = *reinterpret_cast<const float4*>(s_bias + half * 32 + o8 * 8);
+                        const float4 b1v = *reinterpret_cast<const float4*>(s_bias + half * 32 + o8 * 8 + 4);
+                        const float bb[8] = {b0v.x, b0v.y, b0v.z, b0v.w, b1v.x, b1v.y, b1v.z, b1v.w};
+#pragma unroll
+                        for (int t = 0; t < 4; ++t) {
+                            const float a0f = fmaxf(__uint_as_float(v[8 * o8 + 2 * t]) + bb[2 * t], lo);      // lo = 0: ReLU
+                            const float a1f = fmaxf(__uint_as_float(v[8 * o8 + 2 * t + 1]) + bb[2 * t + 1], lo);
+                            if constexpr (std::is_same<OT, __half>::value)
+                                reinterpret_cast<__half2*>(&pk)[t] = __floats2half2_rn(fminf(a0f, 65504.0f), fminf(a1f, 65504.0f));
+                            else
+                                reinterpret_cast<__nv_bfloat162*>(&pk)[t] = __floats2bfloat162_rn(a0f, a1f);
+                        }
+                        reinterpret_cast<uint4*>(o)[o8] = pk;
+                    }
+                }
+            }
+            tc::tcgen05_fence_before();
+            __syncwarp();
+            if (lane == 0) tc::mbar_arrive(&tmem_empty[acc]);
+        }
+    }
+    tc::tcgen05_fence_before();
+    __syncthreads();
+    if (warp == 8) {
+        tc::tcgen05_fence_after();
+        tc::tmem_dealloc(tmem_base, SS_ACCS * 64);
+    }
+}
+
+template <int CIN, typename OT>
+static int launch_stem_stream(const float* x, const void* w_packed, const float* bias, void* y, int B, int H, int W, int P, int Q,
+                              float lo, cudaStream_t s) {
+    auto kern = stem_stream_kernel<CIN, OT>;
+    static bool configured = false;
+    if (!configured) {
+        int st = cuda_status(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SS_SMEM), "stem stream attr");
+        if (st) return st;
+        configured = true;
+    }
+    // work units = (image, 128-column strip, row chunk): about two per SM (two CTAs are resident per SM)
+    int sms = 148, dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const int strips = (Q + ST_TW - 1) / ST_TW;
+    int chunks = (2 * sms + B * strips / 2) / (B * strips);
+    if (chunks < 1) chunks = 1;
+    if (chunks > P) chunks = P;
+    const int chunk_rows = (P + chunks - 1) / chunks;
+    chunks = (P + chunk_rows - 1) / chunk_rows;
+    kern<<<B * strips * chunks, SS_THREADS, SS_SMEM, s>>>(x, (const uint4*)w_packed, bias, (OT*)y, H, W, P, Q, lo, strips, chunks, chunk_rows);
+    return 0;
+}
+
 template <int CIN, typename OT>
 static int launch_stem_tc(const float* x, const void* w_packed, const float* bias, void* y, int B, int H, int W, int P, int Q,
                           float lo, cudaStream_t s) {
+    static const int stream_mode = [] { const char* e = getenv("DPFT_STEM_STREAM"); return (e && e[0] == '0') ? 0 : 1; }();
+    if (stream_mode) return launch_stem_stream<CIN, OT>(x, w_packed, bias, y, B, H, W, P, Q, lo, s);
     auto kern = stem_tc_kernel<CIN, OT>;
     const size_t smem = ST_A_BYTES + ST_B_BYTES + (ST_TH + 2) * 8 + 16 + STEM_COUT * sizeof(float);
     static bool configured = false;
