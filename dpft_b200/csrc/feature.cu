@@ -499,6 +499,23 @@ __global__ void stem_pack_weights_kernel(const float* __restrict__ w, __half* __
     packed[i] = __float2half_rn(v);
 }
 
+// 4-channels-per-tap image of the streaming kernel (Cin <= 4): a 16-byte K chunk holds TWO taps of the same column parity,
+// [tap sa: ch 0..3 | tap sb: ch 0..3] with (sa, sb) = (0,2), (1,3), (4,6), (5,-) for chunks 0..3 of a filter row, so a K = 16
+// MMA covers four taps and a filter row takes two MMAs instead of four.  Layout [(r*2 + t)][khalf][o/8][o%8][8 elems].
+constexpr int ST_B4_BYTES = 7 * 2 * 2048;            // 28,672
+template <int CIN>
+__global__ void stem_pack_weights4_kernel(const float* __restrict__ w, __half* __restrict__ packed) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;      // one packed element
+    if (i >= ST_B4_BYTES / 2) return;
+    const int k = i & 7, orow = (i >> 3) & 7, og = (i >> 6) & 7, kh = (i >> 9) & 1, rt = i >> 10;
+    const int r = rt >> 1, chunk = (rt & 1) * 2 + kh, o = og * 8 + orow;
+    const int sa = chunk == 0 ? 0 : chunk == 1 ? 1 : chunk == 2 ? 4 : 5;
+    const int tap = k < 4 ? sa : sa + 2, c = k & 3;
+    float v = 0.0f;
+    if (tap < 7 && c < CIN) v = w[((r * 7 + tap) * CIN + c) * 64 + o];
+    packed[i] = __float2half_rn(v);
+}
+
 template <int CIN, typename OT>
 __global__ void __launch_bounds__(ST_THREADS)
 stem_tc_kernel(const float* __restrict__ x, const uint4* __restrict__ w_packed, const float* __restrict__ bias,
@@ -636,6 +653,8 @@ constexpr int SS_RING = 12;
 constexpr int SS_ACCS = 4;
 constexpr int SS_THREADS = 288;
 constexpr int SS_SMEM = ST_B_BYTES + SS_RING * ST_ROWB + STEM_COUT * 4 + (2 * SS_RING + 1 + 2 * SS_ACCS) * 8 + 16;
+// Cin == 3 uses the 4-channels-per-tap operands (stem_pack_weights4_kernel): an A entry is [pixel x: 4 ch | pixel x + 2: 4 ch],
+// i.e. every pixel is written into two entries of its parity plane; the MMA count per output row drops from 28 to 14.
 
 template <int CIN, typename OT>
 __global__ void __launch_bounds__(SS_THREADS)
@@ -652,6 +671,9 @@ stem_stream_kernel(const float* __restrict__ x, const uint4* __restrict__ w_pack
     uint64_t* tmem_empty = tmem_full + SS_ACCS;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + SS_ACCS);
 
+    constexpr bool PACK4 = CIN <= 4;
+    constexpr int W_BYTES = PACK4 ? ST_B4_BYTES : ST_B_BYTES;
+    constexpr int MMAS_PER_ROW = PACK4 ? 2 : 4;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int unit = blockIdx.x;
     const int chunk = unit % chunks;
@@ -707,10 +729,19 @@ stem_stream_kernel(const float* __restrict__ x, const uint4* __restrict__ w_pack
             for (int u = 0; u < PER_LANE; ++u) {
                 const int xl = lane + u * 32;
                 if (xl < ENTRIES) {
-                    __align__(16) __half hv[8];
+                    if constexpr (PACK4) {
+                        __align__(8) __half hv[4];
 #pragma unroll
-                    for (int c = 0; c < 8; ++c) hv[c] = __float2half_rn(c < CIN ? v[u][c < CIN ? c : 0] : 0.0f);
-                    *reinterpret_cast<uint4*>(dst + (xl & 1) * ST_PLANE + (xl >> 1) * 16) = *reinterpret_cast<uint4*>(hv);
+                        for (int c = 0; c < 4; ++c) hv[c] = __float2half_rn(c < CIN ? v[u][c < CIN ? c : 0] : 0.0f);
+                        uint8_t* e = dst + (xl & 1) * ST_PLANE + (xl >> 1) * 16;
+                        *reinterpret_cast<uint2*>(e) = *reinterpret_cast<uint2*>(hv);                 // first tap of entry xl >> 1
+                        if (xl >= 2) *reinterpret_cast<uint2*>(e - 8) = *reinterpret_cast<uint2*>(hv); // second tap of the entry before
+                    } else {
+                        __align__(16) __half hv[8];
+#pragma unroll
+                        for (int c = 0; c < 8; ++c) hv[c] = __float2half_rn(c < CIN ? v[u][c < CIN ? c : 0] : 0.0f);
+                        *reinterpret_cast<uint4*>(dst + (xl & 1) * ST_PLANE + (xl >> 1) * 16) = *reinterpret_cast<uint4*>(hv);
+                    }
                 }
             }
             tc::fence_proxy_async();                          // generic-proxy writes -> visible to the tensor core
@@ -720,9 +751,11 @@ stem_stream_kernel(const float* __restrict__ x, const uint4* __restrict__ w_pack
     } else if (warp == 8) {
         // ====================================== weights + MMA issuer ======================================
         if (lane == 0) {
-            tc::mbar_expect_tx(w_bar, ST_B_BYTES);
+            // the 4-channel image follows the 8-channel one in the packed buffer
+            const uint8_t* wsrc = reinterpret_cast<const uint8_t*>(w_packed) + (PACK4 ? ST_B_BYTES : 0);
+            tc::mbar_expect_tx(w_bar, W_BYTES);
             asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(tc::smem_u32(s_b)),
-                         "l"(w_packed), "r"((uint32_t)ST_B_BYTES), "r"(tc::smem_u32(w_bar))
+                         "l"(wsrc), "r"((uint32_t)W_BYTES), "r"(tc::smem_u32(w_bar))
                          : "memory");
         }
         tc::mbar_wait(w_bar, 0);
@@ -741,9 +774,11 @@ stem_stream_kernel(const float* __restrict__ x, const uint4* __restrict__ w_pack
                 for (int r = 0; r < 7; ++r) {
                     const uint32_t row = a0 + ((2 * j + r) % SS_RING) * ST_ROWB;
 #pragma unroll
-                    for (int t = 0; t < 4; ++t) {
-                        const uint64_t adesc = tc::umma_desc_noswizzle(row + t * 16, ST_PLANE, 128);
-                        const uint64_t bdesc = tc::umma_desc_noswizzle(b0 + (r * 4 + t) * 2048, 1024, 128);
+                    for (int t = 0; t < MMAS_PER_ROW; ++t) {
+                        // 8-channel entries: taps (2t, 2t+1) start t entries in; 4-channel entries: taps (0,2 | 1,3) start at
+                        // entry 0 and taps (4,6 | 5,-) two entries in
+                        const uint64_t adesc = tc::umma_desc_noswizzle(row + (PACK4 ? 2 * t : t) * 16, ST_PLANE, 128);
+                        const uint64_t bdesc = tc::umma_desc_noswizzle(b0 + (r * MMAS_PER_ROW + t) * 2048, 1024, 128);
                         tc::umma_bf16(tmem_base + acc * 64, adesc, bdesc, idesc, (r | t) ? 1u : 0u);
                     }
                 }
@@ -865,8 +900,13 @@ extern "C" int dpft_stem_pack_weights(const float* w, void* packed, int Cin, voi
     DPFT_REQUIRE(w && packed, "stem_pack_weights: null pointer");
     DPFT_REQUIRE(Cin == 3 || Cin == 6, "stem_pack_weights: Cin=%d (3 or 6 supported)", Cin);
     const int n = ST_B_BYTES / 2;
-    if (Cin == 3) stem_pack_weights_kernel<3><<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(w, (__half*)packed);
-    else stem_pack_weights_kernel<6><<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(w, (__half*)packed);
+    if (Cin == 3) {
+        stem_pack_weights_kernel<3><<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(w, (__half*)packed);
+        stem_pack_weights4_kernel<3><<<(ST_B4_BYTES / 2 + 255) / 256, 256, 0, (cudaStream_t)stream>>>(
+            w, reinterpret_cast<__half*>(reinterpret_cast<uint8_t*>(packed) + ST_B_BYTES));
+    } else {
+        stem_pack_weights_kernel<6><<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(w, (__half*)packed);
+    }
     DPFT_LAUNCH_CHECK("stem_pack_weights_kernel");
     return DPFT_OK;
 }

@@ -29,8 +29,9 @@ def _lib():
 
 
 def stem_pack_weights(w: torch.Tensor) -> torch.Tensor:
-    """[7][7][Cin][64] fp32 -> the f16 operand image of the tcgen05 stem kernel (57344 bytes)."""
-    packed = torch.empty(57344, dtype=torch.uint8, device=w.device)
+    """[7][7][Cin][64] fp32 -> the f16 operand images of the tcgen05 stem kernels: 57344 bytes in the 8-channels-per-tap
+    layout, followed (Cin == 3) by 28672 bytes in the 4-channels-per-tap layout of the streaming kernel."""
+    packed = torch.empty(57344 + 28672, dtype=torch.uint8, device=w.device)
     st = _lib().dpft_stem_pack_weights(native.ptr(w), native.ptr(packed), w.shape[2], native.stream_ptr(w.device))
     native.check(st, "dpft_stem_pack_weights")
     return packed

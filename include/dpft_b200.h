@@ -110,7 +110,10 @@ DPFT_API int dpft_stem_conv7x7_forward(const float* x, const float* w, const voi
 /* Same with the ReLU optional (relu = 0: y = conv + bias, the pre-BatchNorm activation the training path stores). */
 DPFT_API int dpft_stem_conv7x7_forward_ex(const float* x, const float* w, const void* w_packed, const float* bias, void* y,
                                           int B, int H, int W, int Cin, int dtype, int impl, int relu, void* stream);
-/* w [7][7][Cin][64] f32 -> the 57344-byte f16 operand image the tcgen05 stem kernel stages (done once per model). */
+/* w [7][7][Cin][64] f32 -> the f16 operand images the tcgen05 stem kernels stage (done once per model): `packed` must hold
+ * DPFT_STEM_PACKED_BYTES = 86016 bytes (57344 in the 8-channels-per-tap layout, then, for Cin = 3, 28672 in the
+ * 4-channels-per-tap layout of the row-streaming kernel). */
+#define DPFT_STEM_PACKED_BYTES 86016
 DPFT_API int dpft_stem_pack_weights(const float* w, void* packed, int Cin, void* stream);
 
 /* torchvision ResNet maxpool (kernel 3, stride 2, padding 1), NHWC bf16, C % 8 == 0.  y (B, (H-1)/2+1, (W-1)/2+1, C). */
