@@ -100,3 +100,14 @@ def test_plugin_registration():
     assert MSDA.ms_deform_attn_forward is msda.ms_deform_attn_forward
     assert MSDA.ms_deform_attn_backward is msda.ms_deform_attn_backward
     del sys.modules["MultiScaleDeformableAttention"]
+
+
+def test_packed_stem_buffer_size_matches_the_header():
+    """dpft_b200/features.py allocates what include/dpft_b200.h says dpft_stem_pack_weights writes."""
+    import inspect
+    import re
+    from dpft_b200 import features, native
+    header = open(native.HEADER_PATH).read()
+    declared = int(re.search(r"#define\s+DPFT_STEM_PACKED_BYTES\s+(\d+)", header).group(1))
+    sizes = [int(a) + int(b) for a, b in re.findall(r"torch\.empty\((\d+) \+ (\d+), dtype=torch\.uint8", inspect.getsource(features.stem_pack_weights))]
+    assert sizes == [declared]
