@@ -143,3 +143,4 @@ def test_fpn_output_tensor_core_matches_cuda_core(cin, H, W):
     torch.cuda.synchronize()
     assert float(b[:, :7].abs().max()) == 0.0                      # nothing written before `start`
     assert _rel(b, a) < 2e-3, _rel(b, a)
+
