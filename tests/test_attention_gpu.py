@@ -134,6 +134,27 @@ def test_decoder_self_attention_matches_the_oracle_restatement():
     assert float((got - want).abs().max()) < 1e-5
 
 
+@pytest.mark.gpu
+def test_decoder_self_attention_matches_the_reference_golden():
+    """The same sub-layer through the tcgen05 kernel against the outputs of the UNMODIFIED reference (fixture
+    tests/golden/mlfusion_self_attn.pt: 8 heads x 2 channels at 400 queries, 4 heads x 16 channels at 257 queries)."""
+    from conftest import load_golden
+    from dpft_b200 import native
+    from dpft_b200.models.fuser import MLFusion
+    torch.backends.cuda.matmul.allow_tf32 = False
+    rec = load_golden("mlfusion_self_attn")
+    for case in rec["cases"]:
+        d, h = case["d_model"], case["n_heads"]
+        layer = MLFusion(d_model=d, d_ffn=2 * d, n_levels=1, n_heads=h, n_points=4, norm=True, dropout=0.1, activation="Mish").eval()
+        layer.load_state_dict(case["state_dict"], strict=False)
+        layer = layer.to(DEV)
+        with torch.no_grad():
+            l0 = native.launches()
+            got = layer.forward_self_attn(case["x"].to(DEV), case["pos"].to(DEV)).cpu()
+            assert native.launches() == l0 + 1                       # the attention core ran in the native kernel
+        assert float((got - case["out"]).abs().max()) < 2e-5, float((got - case["out"]).abs().max())
+
+
 def test_rejects_cpu_tensors_and_wide_heads():
     x = torch.zeros(1, 4, 8)
     with pytest.raises(RuntimeError, match="not implemented on the CPU"):

@@ -62,3 +62,25 @@ def test_default_initialisation_of_msdeformattn_follows_the_reference_scheme():
     b = m.sampling_offsets.bias.view(8, 5, 4, 2)
     assert torch.allclose(b[0, 0, :, 0], torch.tensor([1.0, 2.0, 3.0, 4.0])) and b[0, :, :, 1].abs().max() < 1e-6
     assert torch.allclose(b[2, 3, 1], torch.tensor([0.0, 2.0]), atol=1e-6)
+
+
+def test_self_attention_sublayer_matches_reference_golden():
+    """The decoder's self-attention sub-layer (reference MLFusion.forward_self_attn, mpfusion.py:122-148; fixture from
+    tools/make_golden_selfattn.py): the oracle restatement and the product's host logic (torch path on the CPU) against the
+    outputs of the unmodified reference."""
+    import torch.nn.functional as F
+    from oracle import dprt_oracle
+    from dpft_b200.models.fuser import MLFusion
+    rec = load_golden("mlfusion_self_attn")
+    for case in rec["cases"]:
+        d, h = case["d_model"], case["n_heads"]
+        sd = {"l." + k: v for k, v in case["state_dict"].items()}
+        with torch.no_grad():
+            got = case["x"] + dprt_oracle.self_attention(sd, "l.self_attn", case["x"], case["pos"], h)
+            got = F.layer_norm(got, (d,), sd["l.norm1.weight"], sd["l.norm1.bias"], 1e-5)
+        assert float((got - case["out"]).abs().max()) < 2e-6
+        layer = MLFusion(d_model=d, d_ffn=2 * d, n_levels=1, n_heads=h, n_points=4, norm=True, dropout=0.1, activation="Mish").eval()
+        layer.load_state_dict(case["state_dict"], strict=False)
+        with torch.no_grad():
+            mine = layer.forward_self_attn(case["x"], case["pos"])
+        assert float((mine - case["out"]).abs().max()) < 2e-6
