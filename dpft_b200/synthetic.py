@@ -37,8 +37,8 @@ def load_config(name_or_path: str) -> dict:
 
 
 def offline_config(cfg: dict, n_queries: Optional[Tuple[int, int, int]] = None, dropout: Optional[float] = None,
-                   multi_scale: Optional[int] = None) -> dict:
-    """Config edits SURVEY.md §8d lists: no ImageNet download, optional query-grid / level-count change."""
+                   multi_scale: Optional[int] = None, d_model: Optional[int] = None) -> dict:
+    """Config edits SURVEY.md §8d lists: no ImageNet download, optional query-grid / level-count / width change."""
     cfg = copy.deepcopy(cfg)
     m = cfg["model"]
     for b in m["backbones"].values():
@@ -56,6 +56,12 @@ def offline_config(cfg: dict, n_queries: Optional[Tuple[int, int, int]] = None, 
             m["necks"][name]["in_channels_list"] = [first] + chans
             m["embeddings"][name]["n_levels"] = multi_scale + 1
         m["fuser"]["n_levels"] = [multi_scale + 1] * m["fuser"]["m_views"]
+    if d_model is not None:                                # SURVEY §8d cfg 5 sweeps d_model in {16, 64, 256}
+        for name in m["inputs"]:
+            m["necks"][name]["out_channels"] = d_model
+            m["embeddings"][name]["num_feats"] = d_model
+        m["fuser"]["d_model"], m["fuser"]["d_ffn"] = d_model, 2 * d_model
+        m["head"]["in_channels"] = d_model
     return cfg
 
 

@@ -9,7 +9,8 @@ from dpft_b200 import configs, synthetic
 def case_setup(rec):
     """(cfg, batch) of a golden record, rebuilt from seeds."""
     case = rec["case"]
-    cfg = synthetic.offline_config(configs.make_config(case["config"]), n_queries=case["n_queries"])
+    cfg = synthetic.offline_config(configs.make_config(case["config"]), n_queries=case["n_queries"],
+                                   multi_scale=case.get("multi_scale"), d_model=case.get("d_model"))
     batch = synthetic.synthetic_batch(cfg, case["batch"], seed=rec["input_seed"], sizes=case["sizes"])
     return cfg, batch
 

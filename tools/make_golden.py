@@ -31,14 +31,22 @@ CASES = [
          n_queries=(20, 15, 1)),
     dict(name="fusion_native_1", config="kradar", batch=1,
          sizes={"camera_mono": (128, 228, 3)}, n_queries=None),
+    # BASELINE config 5's structure: 900 queries, 4 levels (raw + 3 stages), d_model 64 (8 heads of 8 channels)
+    dict(name="stress_4level_d64_900q", config="kradar", batch=1,
+         sizes={"camera_mono": (96, 160, 3), "radar_bev": (64, 48, 6), "radar_front": (37, 48, 6)},
+         n_queries=(30, 30, 1), multi_scale=3, d_model=64),
 ]
 
 
-def main():
+def main(only=None):
+    """``python tools/make_golden.py [case ...]``: all fixtures, or only the named model cases."""
     ref = reference_shim.import_reference_models()
     os.makedirs(GOLDEN, exist_ok=True)
     for i, case in enumerate(CASES):
-        cfg = synthetic.offline_config(configs.make_config(case["config"]), n_queries=case["n_queries"])
+        if only and case["name"] not in only:
+            continue
+        cfg = synthetic.offline_config(configs.make_config(case["config"]), n_queries=case["n_queries"],
+                                       multi_scale=case.get("multi_scale"), d_model=case.get("d_model"))
         model = ref.build("dprt", cfg).eval()
         wseed, iseed = 100 + i, 200 + i
         sd = synthetic.seeded_state_dict(model.state_dict(), seed=wseed)
@@ -53,6 +61,8 @@ def main():
         torch.save(rec, os.path.join(GOLDEN, case["name"] + ".pt"))
         print(case["name"], {k: (tuple(v.shape), float(v.abs().max())) for k, v in out.items()})
 
+    if only:
+        return
     # module-level fixture: the reference's MSDeformAttn (its Python arithmetic around the op)
     from dprt.models.layers import MSDeformAttn
     torch.manual_seed(7)
@@ -75,4 +85,4 @@ def main():
 
 
 if __name__ == "__main__":
-    main()
+    main(sys.argv[1:] or None)
