@@ -469,6 +469,203 @@ fpn_output_tc_kernel(const FpnOutParams prm) {
 }
 
 
+// ----------------------------------------------------------- FPN output, raw level: column-owning tile builder (v2)
+// EXPERIMENTAL (DPFT_FPN_BUILD=2 / impl 3; parity-checked on the CPU against an emulation of the index maps only — the
+// default stays fpn_output_tc_kernel until it is validated on a B200).  Same GEMM, same shared-memory operand image and
+// the same epilogue as fpn_output_tc_kernel<CIN>; only the construction of the inner halo tile differs.  ncu on the
+// 8x720x1280 camera level (gpurun_out/fpn_out_cam.raw.csv): 102.7 M warp instructions, issue slots 39 % active, two CTAs
+// per SM (96 registers) -> 243 us for 324 MB, i.e. the kernel is bound by the builders' instruction stream (~230 per halo
+// entry), not by HBM (50 us).  Here
+//   * a thread owns one tile COLUMN and walks five of the tile's ten rows: no per-entry division, the column's validity,
+//     coarse column and raw pointer are computed once;
+//   * the top-down term is staged once per CTA: the (<= FB_CR x FB_CC) patch of the coarser inner map the tile touches,
+//     with the lateral bias already added, goes to shared memory with coalesced loads; a thread re-reads its 16 values only
+//     when the nearest-neighbour source row changes (every fourth row) and they START the FMA chain
+//     (v = w2*x2 + (w1*x1 + (w0*x0 + (coarse + bias)))), so the 16 adds and 4 global loads per entry disappear;
+//   * three CTAs per SM (launch bound), 58 KB of shared memory each.
+constexpr int FB_CR = 5, FB_CC = 36;                 // rows / columns of the staged coarse patch (host checks the spans)
+constexpr int FB_ROWS = (TC_TH + 2) / 2;             // rows per column-owning thread
+static_assert(TC_THREADS == 2 * TC_TW && (TC_TH + 2) % 2 == 0, "two row groups of TC_TW column threads");
+
+__device__ __forceinline__ int nearest_src_scaled(int dst, float scale, int in_size) {
+    const int s = (int)floorf((float)dst * scale);   // same arithmetic as nearest_src (scale = float(in) / float(out))
+    return s < in_size - 1 ? s : in_size - 1;
+}
+
+template <int CIN, int ROWS>
+__device__ __forceinline__ void fpn_build_column(const FpnOutParams& prm, uint8_t* s_a, const float* s_lat, const float* s_cb,
+                                                 int b, int p0, int q0, int px, int rr0, float scale_h, float scale_w,
+                                                 int hc0, int wc0) {
+    const int H = prm.H, W = prm.W;
+    const int ww = q0 - 1 + px;
+    const bool col_ok = ww >= 0 && ww < W;
+    const int ws = col_ok ? ww : 0;
+    const int wcl = nearest_src_scaled(ws, scale_w, prm.Wc) - wc0;
+    float xin[ROWS][CIN];
+    bool ok[ROWS];
+#pragma unroll
+    for (int u = 0; u < ROWS; ++u) {                 // every raw load of the column is issued before any is consumed
+        const int hh = p0 - 1 + rr0 + u;
+        ok[u] = col_ok && hh >= 0 && hh < H;
+        const float* xp = prm.raw + (((long long)b * H + (ok[u] ? hh : 0)) * W + ws) * CIN;
+#pragma unroll
+        for (int c = 0; c < CIN; ++c) xin[u][c] = ok[u] ? __ldg(xp + c) : 0.0f;
+    }
+    float cb[FC];
+#pragma unroll
+    for (int o = 0; o < FC; ++o) cb[o] = 0.0f;
+    int cur = -1;
+#pragma unroll
+    for (int u = 0; u < ROWS; ++u) {
+        const int rr = rr0 + u;
+        uint4 pk[2] = {make_uint4(0u, 0u, 0u, 0u), make_uint4(0u, 0u, 0u, 0u)};      // zero outside the image (conv padding)
+        if (ok[u]) {
+            const int hcl = nearest_src_scaled(p0 - 1 + rr, scale_h, prm.Hc) - hc0;
+            if (hcl != cur) {                        // coarse + lateral bias of this (coarse row, coarse column)
+                const float4* cp = reinterpret_cast<const float4*>(s_cb + (hcl * FB_CC + wcl) * FC);
+#pragma unroll
+                for (int c4 = 0; c4 < 4; ++c4) {
+                    const float4 f = cp[c4];
+                    cb[4 * c4] = f.x; cb[4 * c4 + 1] = f.y; cb[4 * c4 + 2] = f.z; cb[4 * c4 + 3] = f.w;
+                }
+                cur = hcl;
+            }
+            float v[FC];
+#pragma unroll
+            for (int o = 0; o < FC; ++o) {
+                float a = cb[o];
+#pragma unroll
+                for (int c = 0; c < CIN; ++c) a = fmaf(s_lat[o * CIN + c], xin[u][c], a);
+                v[o] = a;
+            }
+            uint32_t* pw = reinterpret_cast<uint32_t*>(pk);
+#pragma unroll
+            for (int t = 0; t < 8; ++t) asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(pw[t]) : "f"(v[2 * t + 1]), "f"(v[2 * t]));
+        }
+        *reinterpret_cast<uint4*>(s_a + rr * TC_ROWB + px * 16) = pk[0];
+        *reinterpret_cast<uint4*>(s_a + rr * TC_ROWB + TC_PLANE + px * 16) = pk[1];
+    }
+}
+
+template <int CIN>
+__global__ void __launch_bounds__(TC_THREADS, 3)
+fpn_output_tc2_kernel(const FpnOutParams prm) {
+    static_assert(CIN > 0, "the column builder is for the raw level");
+    extern __shared__ __align__(128) uint8_t tsm[];
+    uint8_t* s_a = tsm;
+    uint8_t* s_b = tsm + TC_A_BYTES;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(s_b + TC_B_BYTES);
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + TC_TH);
+    float* s_lat = reinterpret_cast<float*>(tmem_slot + 4);          // [16][CIN]
+    float* s_py = s_lat + FC * 6 + FC;                                // [TC_TH][16]: pos_y rows of this tile (+ bias)
+    float* s_cb = s_py + TC_TH * FC;                                  // [FB_CR][FB_CC][16]: coarse patch + lateral bias
+    const int b = blockIdx.z;
+    const int p0 = blockIdx.y * TC_TH, q0 = blockIdx.x * TC_TW;
+    const int tid = threadIdx.x, warp = tid >> 5;
+    const int H = prm.H, W = prm.W;
+
+    if (warp == 0) {
+        tc::tmem_alloc(tmem_slot, 128);
+    } else if (tid == 32) {
+        for (int r = 0; r < TC_TH; ++r) tc::mbar_init(&bars[r], 1);
+        tc::fence_barrier_init();
+    }
+    for (int i = tid; i < TC_B_BYTES / 16; i += TC_THREADS) reinterpret_cast<uint4*>(s_b)[i] = __ldg(prm.w_packed + i);
+    if (tid < TC_TH * FC) {
+        const int r = tid / FC, c = tid - r * FC;
+        s_py[tid] = (p0 + r < H ? __ldg(prm.pos_y + (long long)(p0 + r) * FC + c) : 0.0f) + __ldg(prm.bias + c);
+    }
+    for (int i = tid; i < FC * CIN; i += TC_THREADS) s_lat[i] = __ldg(prm.lat_w + i);
+    // the patch of the coarser inner map under this tile (nearest-neighbour sources of rows p0-1 .. p0+TC_TH and columns
+    // q0-1 .. q0+TC_TW, clamped to the image), lateral bias added
+    const float scale_h = (float)prm.Hc / (float)H, scale_w = (float)prm.Wc / (float)W;
+    const int hc0 = nearest_src_scaled(p0 > 0 ? p0 - 1 : 0, scale_h, prm.Hc);
+    const int wc0 = nearest_src_scaled(q0 > 0 ? q0 - 1 : 0, scale_w, prm.Wc);
+    for (int i = tid; i < FB_CR * FB_CC * 4; i += TC_THREADS) {
+        const int cell = i >> 2, c4 = i & 3;
+        const int cr = cell / FB_CC, cc = cell - cr * FB_CC;
+        const int hc = hc0 + cr < prm.Hc ? hc0 + cr : prm.Hc - 1;
+        const int wc = wc0 + cc < prm.Wc ? wc0 + cc : prm.Wc - 1;
+        float4 f = __ldg(reinterpret_cast<const float4*>(prm.coarse + (((long long)b * prm.Hc + hc) * prm.Wc + wc) * FC) + c4);
+        const float4 lb = __ldg(reinterpret_cast<const float4*>(prm.lat_b) + c4);
+        f.x += lb.x; f.y += lb.y; f.z += lb.z; f.w += lb.w;
+        reinterpret_cast<float4*>(s_cb)[i] = f;
+    }
+    __syncthreads();
+    // inner halo tile, f16: thread (group g, column c) builds rows g*FB_ROWS .. of column c; the two right halo columns
+    // (TC_TW, TC_TW + 1) are one more entry for the first 2 * (TC_TH + 2) threads.  Entries beyond TC_TW + 1 are never read
+    // by the MMAs (tap ds reads entries ds .. ds + 127).
+    fpn_build_column<CIN, FB_ROWS>(prm, s_a, s_lat, s_cb, b, p0, q0, tid & (TC_TW - 1), (tid >> 7) * FB_ROWS, scale_h, scale_w, hc0, wc0);
+    if (tid < 2 * (TC_TH + 2))
+        fpn_build_column<CIN, 1>(prm, s_a, s_lat, s_cb, b, p0, q0, TC_TW + (tid & 1), tid >> 1, scale_h, scale_w, hc0, wc0);
+    tc::fence_proxy_async();                 // generic-proxy smem writes -> visible to the tensor core (async proxy)
+    tc::tcgen05_fence_before();
+    __syncthreads();
+    tc::tcgen05_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (tid == 0) {
+        constexpr uint32_t idesc = tc::umma_idesc_16bit(128, 16, true);
+        const uint32_t a0 = tc::smem_u32(s_a), b0 = tc::smem_u32(s_b);
+        for (int r = 0; r < TC_TH; ++r) {
+#pragma unroll
+            for (int tap = 0; tap < 9; ++tap) {
+                const int dr = tap / 3, ds = tap % 3;
+                const uint64_t adesc = tc::umma_desc_noswizzle(a0 + (r + dr) * TC_ROWB + ds * 16, TC_PLANE, 128);
+                const uint64_t bdesc = tc::umma_desc_noswizzle(b0 + tap * 512, 256, 128);
+                tc::umma_bf16(tmem_base + r * 16, adesc, bdesc, idesc, tap ? 1u : 0u);
+            }
+            tc::umma_commit(&bars[r]);
+        }
+    }
+    __syncwarp();
+    // epilogue: as fpn_output_tc_kernel
+    const int lane_px = (warp & 3) * 32 + (tid & 31);
+    const int q = q0 + lane_px;
+    float4 px4[4];
+#pragma unroll
+    for (int c4 = 0; c4 < 4; ++c4)
+        px4[c4] = q < W ? __ldg(reinterpret_cast<const float4*>(prm.pos_x + (long long)q * FC) + c4) : make_float4(0, 0, 0, 0);
+    const int r_begin = (warp >> 2) * (TC_TH / 2);
+    for (int r = r_begin; r < r_begin + TC_TH / 2; ++r) {
+        tc::mbar_wait(&bars[r], 0);
+        tc::tcgen05_fence_after();
+        uint32_t v[16];
+        tc::tmem_ld_32x32b_x16(tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(r * 16), v);
+        tc::tmem_ld_wait();
+        const int p = p0 + r;
+        if (p < H && q < W) {
+            const float4* py = reinterpret_cast<const float4*>(s_py + r * FC);     // pos_y + bias
+            float outv[FC];
+#pragma unroll
+            for (int c4 = 0; c4 < 4; ++c4) {
+                const float4 c = py[c4];
+                outv[4 * c4] = (__uint_as_float(v[4 * c4]) + c.x) + px4[c4].x;
+                outv[4 * c4 + 1] = (__uint_as_float(v[4 * c4 + 1]) + c.y) + px4[c4].y;
+                outv[4 * c4 + 2] = (__uint_as_float(v[4 * c4 + 2]) + c.z) + px4[c4].z;
+                outv[4 * c4 + 3] = (__uint_as_float(v[4 * c4 + 3]) + c.w) + px4[c4].w;
+            }
+            store_pyramid_row(prm.pyramid, (long long)b * prm.S + prm.start + (long long)p * W + q, outv, prm.pyramid_f16 != 0);
+        }
+    }
+    tc::tcgen05_fence_before();
+    __syncthreads();
+    if (warp == 0) {
+        tc::tcgen05_fence_after();
+        tc::tmem_dealloc(tmem_base, 128);
+    }
+}
+
+// Worst-case extent of the coarse patch under one tile: `n` consecutive fine positions map to at most floor((n-1)*in/out)+2
+// consecutive coarse positions (nearest-neighbour indices are floor(dst * in/out), clamped); one more for the float
+// rounding of dst * scale at inexact ratios.
+inline bool fpn_column_builder_eligible(int H, int W, int Hc, int Wc, bool has_coarse) {
+    if (!has_coarse || Hc <= 0 || Wc <= 0 || Hc > H || Wc > W) return false;
+    const long long span_r = ((long long)(TC_TH + 1) * Hc) / H + 3, span_c = ((long long)(TC_TW + 1) * Wc) / W + 3;
+    return span_r <= FB_CR && span_c <= FB_CC;
+}
+
+
 // --------------------------------------------------------------------------------------- stem on the tensor cores
 // conv 7x7 / stride 2 as an implicit GEMM per output row: M = 128 output pixels, N = 64 channels, K = 7 filter rows x
 // 8 taps (7 + one zero tap) x 8 channels (Cin + zero padding).  The stride-2 window is made contiguous by splitting
@@ -982,13 +1179,36 @@ extern "C" int dpft_fpn_output_forward(const float* inner, const float* raw, int
     FpnOutParams prm{inner, raw, lat_w, lat_b, coarse, w, (const uint4*)w_packed, bias, pos_y, pos_x, pyramid, pyramid_dtype == DPFT_F16 ? 1 : 0,
                      S, start, H, W, Hc, Wc};
     cudaStream_t s = (cudaStream_t)stream;
-    DPFT_REQUIRE(impl >= 0 && impl <= 2, "fpn_output: impl must be 0 (auto), 1 (CUDA cores) or 2 (tensor cores)");
+    DPFT_REQUIRE(impl >= 0 && impl <= 3, "fpn_output: impl must be 0 (auto), 1 (CUDA cores), 2 (tensor cores) or 3 (tensor cores, "
+                 "column-owning tile builder: experimental)");
     if (!inner) {
         DPFT_REQUIRE(lat_w && lat_b, "fpn_output: lateral weights needed for the raw level");
         DPFT_REQUIRE(coarse == nullptr || (Hc > 0 && Wc > 0), "fpn_output: bad coarse size");
         DPFT_REQUIRE(raw_channels == 3 || raw_channels == 6, "fpn_output: raw_channels=%d (3 or 6 supported)", raw_channels);
     }
-    DPFT_REQUIRE(impl != 2 || w_packed, "fpn_output: the tensor-core kernel needs the packed weights (dpft_fpn_pack_weights)");
+    DPFT_REQUIRE(impl < 2 || w_packed, "fpn_output: the tensor-core kernel needs the packed weights (dpft_fpn_pack_weights)");
+    // EXPERIMENTAL raw-level tile builder (fpn_output_tc2_kernel): impl 3, or DPFT_FPN_BUILD=2 in the environment for the
+    // automatic choice; off by default until validated on a B200
+    static const int build_mode = [] { const char* e = getenv("DPFT_FPN_BUILD"); return e ? atoi(e) : 1; }();
+    const bool column_builder = !inner && fpn_column_builder_eligible(H, W, Hc, Wc, coarse != nullptr) && ((uintptr_t)lat_b & 15) == 0 &&
+                                (impl == 3 || (impl == 0 && build_mode == 2 && W >= 96 && w_packed));
+    DPFT_REQUIRE(impl != 3 || column_builder, "fpn_output: impl 3 needs the raw level with a coarser map of <= 1/%d x the size",
+                 (TC_TH + 1) / (FB_CR - 3));
+    if (column_builder) {
+        const dim3 tgrid((W + TC_TW - 1) / TC_TW, (H + TC_TH - 1) / TC_TH, B);
+        const size_t smem = TC_A_BYTES + TC_B_BYTES + TC_TH * 8 + 16 + sizeof(float) * (FC * 6 + FC + TC_TH * FC + FB_CR * FB_CC * FC);
+        static bool configured2 = false;
+        if (!configured2) {
+            int st = cuda_status(cudaFuncSetAttribute(fpn_output_tc2_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "fpn tc2 attr");
+            if (!st) st = cuda_status(cudaFuncSetAttribute(fpn_output_tc2_kernel<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "fpn tc2 attr");
+            if (st) return st;
+            configured2 = true;
+        }
+        if (raw_channels == 3) fpn_output_tc2_kernel<3><<<tgrid, TC_THREADS, smem, s>>>(prm);
+        else fpn_output_tc2_kernel<6><<<tgrid, TC_THREADS, smem, s>>>(prm);
+        DPFT_LAUNCH_CHECK("fpn_output_tc2_kernel");
+        return DPFT_OK;
+    }
     if (impl == 2 || (impl == 0 && W >= 96 && w_packed)) {          // wide levels: 128-pixel row strips on the tensor cores
         const dim3 tgrid((W + TC_TW - 1) / TC_TW, (H + TC_TH - 1) / TC_TH, B);
         const size_t smem = TC_A_BYTES + TC_B_BYTES + TC_TH * 8 + 16 + sizeof(float) * (FC * 6 + FC + TC_TH * FC);

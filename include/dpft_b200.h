@@ -140,7 +140,9 @@ DPFT_API int dpft_fpn_lateral_forward(const void* x, const void* w, const float*
  *   w [3][3][16 out][16 in] f32;  bias [16];  pos_y (H, 16), pos_x (W, 16) f32
  * w_packed: output of dpft_fpn_pack_weights or NULL.
  * impl: 0 = choose (tcgen05 row-strip kernel with an f16 inner tile for W >= 96 when w_packed is given, else the fp32
- * CUDA-core kernel), 1 / 2 = force.
+ * CUDA-core kernel), 1 / 2 = force.  3 = EXPERIMENTAL variant of 2 for the raw level (needs `coarse`, at most a quarter of the
+ * size): column-owning tile builder with the coarse patch staged in shared memory; not yet validated on a B200, never chosen by
+ * impl 0 unless DPFT_FPN_BUILD=2 is set in the environment.
  */
 DPFT_API int dpft_fpn_output_forward(const float* inner, const float* raw, int raw_channels, const float* lat_w,
                                      const float* lat_b, const float* coarse, int Hc, int Wc, const float* w,

@@ -144,3 +144,35 @@ def test_fpn_output_tensor_core_matches_cuda_core(cin, H, W):
     assert float(b[:, :7].abs().max()) == 0.0                      # nothing written before `start`
     assert _rel(b, a) < 2e-3, _rel(b, a)
 
+
+
+EXPERIMENTAL = __import__("os").environ.get("DPFT_EXPERIMENTAL") == "1"
+
+
+@pytest.mark.skipif(not EXPERIMENTAL, reason="kernel written without GPU access (no budget left in round 1): opt in with "
+                                             "DPFT_EXPERIMENTAL=1 until it has been validated on a B200")
+@pytest.mark.parametrize("cin,H,W", [(3, 45, 300), (6, 17, 129), (6, 37, 107), (3, 90, 160), (6, 64, 256)])
+def test_fpn_output_column_builder_matches_cuda_core(cin, H, W):
+    """impl 3 (fpn_output_tc2_kernel: column-owning tile builder, staged coarse patch) against the fp32 CUDA-core kernel
+    and the validated tensor-core kernel on the same inputs."""
+    from dpft_b200 import features
+    g = torch.Generator(device=DEV).manual_seed(cin + H)
+    B = 2
+    w = torch.randn(3, 3, 16, 16, generator=g, device=DEV) * 0.1
+    bias = torch.randn(16, generator=g, device=DEV)
+    py = torch.randn(H, 16, generator=g, device=DEV)
+    px = torch.randn(W, 16, generator=g, device=DEV)
+    coarse = torch.randn(B, (H + 3) // 4, (W + 3) // 4, 16, generator=g, device=DEV)
+    kw = dict(raw=torch.rand(B, H, W, cin, generator=g, device=DEV) * 255, coarse=coarse,
+              lat_w=torch.randn(16, cin, generator=g, device=DEV) * 0.01, lat_b=torch.randn(16, generator=g, device=DEV))
+    S = H * W + 7
+    outs = []
+    for impl in (1, 2, 3):
+        o = torch.zeros(B, S, 16, device=DEV)
+        features.fpn_output_forward(o, 7, H, W, w, bias, py, px, impl=impl, **kw)
+        outs.append(o)
+    torch.cuda.synchronize()
+    a, b, c = outs
+    assert float(c[:, :7].abs().max()) == 0.0                      # nothing written before `start`
+    assert _rel(c, a) < 2e-3, _rel(c, a)
+    assert _rel(c, b) < 1e-3, _rel(c, b)                           # same operand image up to the rounding of the FMA chain
