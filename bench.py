@@ -157,11 +157,13 @@ def run_reference(args):
                 times.append(time.perf_counter() - t)
     total = sum(times)
     fps = frames * len(times) / total
-    sample = f"{frames} frame(s) per step of the same workload (full sizes), {len(times)} timed steps"
+    sample = (f"{frames} frame(s) per step of the same workload ({'REDUCED sizes: --small' if args.small else 'full sizes'}), "
+              f"{len(times)} timed steps")
     line = {"impl": "reference", "metric": METRIC, "value": fps, "unit": UNIT, "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / len(times),
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "frames_per_step": frames},
+            "config": {"workload": WORKLOAD, "frames_per_step": frames, "sizes": {k: list(v) for k, v in sizes.items()},
+                       "valid": not args.small},
             "cpu_baseline": {"value": fps, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
                              "sample": sample, "host_cpus": os.cpu_count()},
             "e2e": {"value": fps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
