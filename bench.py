@@ -197,7 +197,7 @@ def conv_roofline(model, resident, dev, tf_peak, peak_src):
     tensor_bound = [p for p in prof if p[0] / (tf_peak * 1e12) >= p[1] / (hbm_peak * 1e9)]
     tb_secs = sum(p[2].elapsed_time(p[3]) for p in tensor_bound) * 1e-3
     tb_flops = sum(p[0] for p in tensor_bound)
-    # DRAM traffic of the same launches from the committed ncu pass (tools/gpu_round23.sh -> tools/ncu_summaries.py); it is
+    # DRAM traffic of the same launches from the committed ncu pass (tools/gpu_calls/gpu_round23.sh -> tools/ncu_summaries.py); it is
     # evidence captured under the profiler, reported beside the live numbers, never a timing
     traffic, traffic_src = None, None
     for name in sorted(os.listdir(os.path.join(ROOT, "profiles")), reverse=True):

@@ -1,4 +1,4 @@
-"""Turns the raw ncu CSV logs of tools/gpu_round23.sh into the summaries committed under profiles/:
+"""Turns the raw ncu CSV logs of tools/gpu_calls/gpu_round23.sh into the summaries committed under profiles/:
   launches: per-kernel share of ONE eval forward (the last forward in the log), from gpu__time_duration.sum
   conv traffic: DRAM bytes / duration / tensor-pipe activity summed over the conv_gemm_kernel launches of one forward
 usage: python tools/ncu_summaries.py gpurun_out/launches_eval_step.csv gpurun_out/conv_traffic.csv profiles/r01"""
