@@ -189,7 +189,8 @@ def deformable_attention(sd, p: str, query, ref_points, flat, shapes: Sequence[T
     return F.linear(out, sd[p + ".output_proj.weight"], sd[p + ".output_proj.bias"])      # :215
 
 
-def ml_fusion(sd, p: str, fcfg: dict, view: int, query, pos, levels: "OrderedDict[str, torch.Tensor]", ref):
+def ml_fusion(sd, p: str, fcfg: dict, view: int, query, pos, levels: "OrderedDict[str, torch.Tensor]", ref,
+              taps: dict = None, tap_key: str = ""):
     """MLFusion.forward (mpfusion.py:231-263), eval mode (dropouts are identities), norm optional."""
     n_heads, n_points = fcfg["n_heads"][view], fcfg["n_points"][view]
     norm = fcfg.get("norm", False)
@@ -199,7 +200,10 @@ def ml_fusion(sd, p: str, fcfg: dict, view: int, query, pos, levels: "OrderedDic
     shapes = [(int(l.shape[1]), int(l.shape[2])) for l in levels.values()]  # :172-176
     flat = torch.cat([l.flatten(1, 2) for l in levels.values()], dim=1)    # :179
     refs = ref.unsqueeze(2).repeat(1, 1, len(shapes), 1)                   # :190
-    x = x + deformable_attention(sd, p + ".ms_deform_attn", x + pos, refs, flat, shapes, n_heads, n_points)
+    cross = deformable_attention(sd, p + ".ms_deform_attn", x + pos, refs, flat, shapes, n_heads, n_points)
+    if taps is not None:
+        taps[tap_key] = cross.clone()
+    x = x + cross
     if norm:
         x = _layer_norm(sd, p + ".norm2", x)                               # :202-206
     act = getattr(torch.nn, fcfg.get("activation", "ReLU"))()
@@ -246,7 +250,7 @@ def fuser(sd, cfg: dict, feats: List["OrderedDict[str, torch.Tensor]"], shapes_h
         per_view = []
         for v in range(V):                                                 # :496-509
             p = f"fuser.mpfusion.fusion{it}.ml_fusion_layers.ms_deform_attn{v}"
-            per_view.append(ml_fusion(sd, p, fcfg, v, query, pos, feats[v], refs[v]))
+            per_view.append(ml_fusion(sd, p, fcfg, v, query, pos, feats[v], refs[v], taps, f"msda_out_{it}_{v}"))
         stacked = torch.stack(per_view, dim=-1)                            # (B,N,C,V)
         red = fcfg.get("reduction", "mean")
         if red == "linear":                                                # :438: view(B,N,C*V), channel-major
