@@ -1,0 +1,18 @@
+#!/bin/bash
+# First gpurun call of round 2: validate what was written after round 1's GPU budget ran out (all of it is off by default).
+#   gpurun --timeout 900 -- 'bash tools/gpu_calls/r02_first_call.sh > gpurun_out/r02_first_call.log 2>&1'
+# 1. experimental tests (column-owning FPN raw-level builder = dpft_fpn_output_forward impl 3; golden taps / gradient digests
+#    of the reference on the GPU paths)
+export DPFT_EXPERIMENTAL=1
+timeout 120 python -m pytest tests/test_features_gpu.py -m gpu -q -x --timeout 60 -k "column_builder" 2>&1 | tail -5
+timeout 300 python -m pytest tests/test_golden_taps_gpu.py -m gpu -q --timeout 120 2>&1 | tail -8
+unset DPFT_EXPERIMENTAL
+# 2. the whole model with the experimental builder chosen by the automatic path, then the A/B on the bench workload
+DPFT_FPN_BUILD=2 timeout 300 python -m pytest tests/test_features_gpu.py tests/test_model_gpu.py -m gpu -q -x --timeout 120 2>&1 | tail -3
+for v in 1 2; do
+DPFT_FPN_BUILD=$v timeout 200 python bench.py --steps 20 --warmup 4 --no-cpu-baseline 2>/dev/null | tail -1 | python -c "
+import sys,json
+r=json.loads(sys.stdin.read()); print('fpn_build=$v', 'ms', r['ms_per_step'], 'fps', r['value'], 'e2e', r['e2e']['value'], 'seq', r['sequential']['ms_per_step'])"
+done
+# 3. per-stage times with the experimental builder (camera_mono.pyramid_total - camera_mono.backbone = the FPN part)
+DPFT_FPN_BUILD=2 timeout 200 python tools/stage_times.py 2>/dev/null | tail -1
