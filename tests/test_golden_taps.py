@@ -71,3 +71,21 @@ def test_product_host_logic_gradients_match_reference_digest():
         v = model.state_dict()[k].double()
         assert abs(float(v.norm()) - norm) < 1e-5 * max(norm, 1e-6) + 1e-7, k
         assert abs(float(v.sum()) - total) < 1e-4 * max(abs(total), 1.0), k
+
+
+def test_reference_point_edge_cases_match_the_reference():
+    """Every branch of the reference-point projection (mpfusion.py:617-696, transformations.py:71-120; fixture
+    refpoints_edge_cases.pt): r = 0 after the rigid transform, points on the axes, w = 0 and w < 0 in the perspective division,
+    clipping, 3x4 and 4x4 projections, the zero transformation of the camera views — oracle and product host logic."""
+    from dpft_b200.models.fuser import IMPFusion
+    rec = load_golden("refpoints_edge_cases")
+    for c in rec["cases"]:
+        want = c["out"]
+        got_oracle = dprt_oracle.reference_points(c["query"].clone(), c["t"], c["p"], c["shape"])
+        got_mine = IMPFusion.get_reference_points(c["query"].clone(), c["t"], c["p"], c["shape"])
+        assert got_oracle.shape == want.shape == got_mine.shape
+        assert float((got_oracle - want).abs().max()) < 1e-6, c["name"]
+        assert float((got_mine - want).abs().max()) < 1e-6, c["name"]
+        assert float(want.min()) >= 0.0 and float(want.max()) <= 1.0
+    cam = rec["cases"][2]["out"]
+    assert float(cam[0, 2].abs().max()) == 0.0            # w = 0: no division, (u, v) = (-700, -700) / size clipped to 0

@@ -63,5 +63,43 @@ def main():
     print("grads", len(grads["names"]), "parameters with,", len(grads["none"]), "without gradient;", os.path.getsize(path), "bytes")
 
 
+def edge_case_inputs():
+    """Reference-point inputs that hit every branch of mpfusion.py:617-696 / transformations.py:71-120: r = 0 after the
+    rigid transform (elevation forced to 0), points on the axes (azimuth +-90 / 180 degrees, elevation +-90), w = 0 and
+    w < 0 in the perspective division, results outside [0, 1] (clipped), 3x4 and 4x4 projections, zero transformation."""
+    t = torch.eye(4).repeat(2, 1, 1)
+    t[0, :3, 3] = torch.tensor([0.5, -0.25, 0.125])
+    t[1, :3, 3] = torch.tensor([-1.0, 2.0, 0.0])
+    pts = torch.tensor([[-0.5, 0.25, -0.125], [9.5, 0.25, -0.125], [-10.5, 0.25, -0.125], [-0.5, 7.25, -0.125],
+                        [-0.5, -6.75, -0.125], [-0.5, 0.25, 3.875], [-0.5, 0.25, -4.125], [30.0, 10.0, 2.0],
+                        [70.0, -40.0, -1.0], [4.0, 4.0, 4.0], [1e-6, 1e-6, 1e-6], [118.0, 0.0, 0.0]])
+    radar_pts = torch.stack((pts, pts - t[1, :3, 3] + t[0, :3, 3]))          # sample 1 hits r = 0 as well
+    H, W = 256, 107
+    p_bev = torch.tensor([[0.0, -1.0, 0.0, (W - 1) / 2.0], [H / 118.037, 0.0, 0.0, 0.0], [0.0, 0.0, 0.0, 1.0]]).repeat(2, 1, 1)
+    p_front = torch.tensor([[0.0, -1.0, 0.0, 53.0], [0.0, 0.0, 1.0, 18.0], [0.0, 0.0, 0.0, 1.0]]).repeat(2, 1, 1)
+    cam_pts = torch.tensor([[10.0, 0.0, 0.0], [10.0, 3.0, -1.0], [0.0, 1.0, 1.0], [-5.0, 1.0, 1.0], [2.0, 30.0, 0.0],
+                            [2.0, -30.0, 5.0], [50.0, -6.0, 2.0], [1e-3, 0.0, 0.0], [0.0, 0.0, 0.0], [72.0, 6.4, 6.0],
+                            [4.0, -6.4, -2.0], [20.0, 0.5, 0.25]]).repeat(2, 1, 1)
+    f, cx, cy = 700.0, 640.0, 360.0
+    p_cam = torch.tensor([[cx, -f, 0.0, 0.0], [cy, 0.0, -f, 0.0], [1.0, 0.0, 0.0, 0.0], [0.0, 0.0, 0.0, 1.0]]).repeat(2, 1, 1)
+    return [dict(name="radar_bev", query=radar_pts, t=t, p=p_bev, shape=torch.tensor([[H, W]] * 2)),
+            dict(name="radar_front", query=radar_pts, t=t, p=p_front, shape=torch.tensor([[37, 107]] * 2)),
+            dict(name="camera", query=cam_pts, t=torch.zeros(2, 4, 4), p=p_cam, shape=torch.tensor([[720, 1280]] * 2))]
+
+
+def reference_point_edge_cases():
+    reference_shim.import_reference_models()
+    from dprt.models.fusers.mpfusion import IMPFusion
+    cases = edge_case_inputs()
+    for c in cases:
+        c["out"] = IMPFusion.get_reference_points(None, c["query"].clone(), c["t"].clone(), c["p"].clone(), c["shape"].clone())
+        print(c["name"], c["out"][0, :4].tolist())
+    path = os.path.join(GOLDEN, "refpoints_edge_cases.pt")
+    torch.save({"cases": cases, "torch_version": torch.__version__}, path)
+    print("refpoints", os.path.getsize(path), "bytes")
+
+
 if __name__ == "__main__":
-    main()
+    if "--refpoints-only" not in sys.argv:
+        main()
+    reference_point_edge_cases()
