@@ -24,6 +24,8 @@
 // the 16-channel feature row (64 B, two sectors) of each corner straight from the FPN pyramid and projects after
 // the reduce; the dense value_proj / torch.cat passes over all S positions that the reference makes in every
 // layer (ms_deform_attn.py:172, mpfusion.py:179) disappear.
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace dpft {
@@ -542,6 +544,91 @@ decoder_head_kernel(const HeadParams prm) {
     }
 }
 
+// EXPERIMENTAL (reduction | DPFT_HEAD_LANES16, or DPFT_HEAD_LANES=16 in the environment; off by default until it has run on a
+// B200): the same reduction + head with SIXTEEN lanes per query instead of one thread per query.  decoder_head_kernel is a
+// serial chain of ~3000 instructions per thread on 19 CTAs (B*N = 2400 threads) at the end of every decoder iteration:
+// 19 us of pure latency, four times per forward.  Here lane o of a query owns output channel o of every layer (one dot16
+// per layer instead of sixteen), the 16-vectors go through a padded shared-memory row exactly as in decoder_layer_kernel,
+// and B*N/16 CTAs cover the GPU.  Every output is accumulated in the same order as in decoder_head_kernel (fmaf chains from
+// zero, views outer / channels inner in the reduction), so the results are bit-identical.
+constexpr int HQ = 16;                                 // queries per CTA (16 lanes each)
+
+__global__ void __launch_bounds__(HQ * C)
+decoder_head16_kernel(const HeadParams prm) {
+    extern __shared__ __align__(16) float smem[];
+    float* s_x = smem + ((prm.weight_floats + 3) & ~3);    // [HQ][ROW] exchange rows
+    for (int i = threadIdx.x; i < prm.weight_floats; i += blockDim.x) smem[i] = __ldg(prm.weights + i);
+    __syncthreads();
+    const int o = threadIdx.x & (C - 1);                   // output channel owned by this lane
+    const int ql = threadIdx.x >> 4;
+    const long long total = (long long)prm.B * prm.N;
+    long long idx = (long long)blockIdx.x * HQ + ql;
+    const bool ok = idx < total;
+    if (!ok) idx = total - 1;                              // keep the lanes alive for the warp-level exchanges; they never store
+    const int n = (int)(idx % prm.N);
+    const int b = (int)(idx / prm.N);
+    const int V = prm.V;
+    float* row = s_x + ql * ROW;
+    float vec[C];
+
+    float x;
+    if (prm.reduction == 0) {
+        const float* red = smem;
+        x = 0.0f;
+        for (int v = 0; v < V; ++v) {
+            const float4* src = reinterpret_cast<const float4*>(prm.views + (((long long)b * V + v) * prm.N + n) * C);
+#pragma unroll
+            for (int c4 = 0; c4 < 4; ++c4) {
+                const float4 f = __ldg(src + c4);
+                vec[4 * c4] = f.x; vec[4 * c4 + 1] = f.y; vec[4 * c4 + 2] = f.z; vec[4 * c4 + 3] = f.w;
+            }
+#pragma unroll
+            for (int c = 0; c < C; ++c) x = fmaf(red[o * (V * C) + c * V + v], vec[c], x);
+        }
+    } else {
+        x = prm.reduction == 1 ? 0.0f : -INFINITY;
+        for (int v = 0; v < V; ++v) {
+            const float* src = prm.views + (((long long)b * V + v) * prm.N + n) * C;
+            x = prm.reduction == 1 ? x + __ldg(src + o) / (float)V : fmaxf(x, __ldg(src + o));
+        }
+    }
+    if (ok) prm.query_out[idx * C + o] = x;
+
+    auto exchange = [&](float mine) {                      // every lane of the query gets the full 16-vector
+        row[o] = mine;
+        __syncwarp();
+#pragma unroll
+        for (int c = 0; c < C; ++c) vec[c] = row[c];
+        __syncwarp();
+    };
+    float xin[C];
+    exchange(x);
+#pragma unroll
+    for (int c = 0; c < C; ++c) xin[c] = vec[c];
+    // one branch: Linear(16,16) -> ReLU -> Linear(16,16) -> ReLU -> Linear(16,k); lane o < k returns output o
+    auto mlp = [&](const float* w, int k) -> float {
+        exchange(fmaxf(dot16(w + o * C, xin), 0.0f));
+        exchange(fmaxf(dot16(w + C * C + o * C, vec), 0.0f));
+        return o < k ? dot16(w + 2 * C * C + o * C, vec) : 0.0f;
+    };
+    const float* hw = smem + (prm.reduction == 0 ? C * V * C : 0);
+    const int branch = 2 * C * C;
+    float r = mlp(hw, 3);                                  // centre: Identity, + previous centre
+    if (ok && o < 3)
+        prm.center_out[idx * 3 + o] = r + __ldg(prm.center_in + (long long)b * prm.center_batch_stride + (long long)n * 3 + o);
+    if (prm.size_out) {
+        hw += branch + 3 * C;
+        r = mlp(hw, 3);                                    // size: ReLU
+        if (ok && o < 3) prm.size_out[idx * 3 + o] = fmaxf(r, 0.0f);
+        hw += branch + 3 * C;
+        r = mlp(hw, 2);                                    // angle: Tanh
+        if (ok && o < 2) prm.angle_out[idx * 2 + o] = tanhf(r);
+        hw += branch + 2 * C;
+        r = mlp(hw, prm.n_cls);                            // class: Identity (logits)
+        if (ok && o < prm.n_cls) prm.class_out[idx * prm.n_cls + o] = r;
+    }
+}
+
 template <int L, int P, typename PT>
 int launch_layer(const LayerParams& prm, cudaStream_t stream) {
     const size_t smem = sizeof(float) * (((prm.weight_floats + 3) & ~3) + (size_t)prm.N * C * 2 + TQ * ROW + TQ * (prm.d_ffn + 1));
@@ -612,6 +699,11 @@ extern "C" int dpft_decoder_head_forward(const float* views, const float* weight
                                          long long center_batch_stride, float* query_out, float* center_out, float* size_out,
                                          float* angle_out, float* class_out, int B, int V, int N, int n_cls, int reduction,
                                          int weight_floats, void* stream) {
+    // EXPERIMENTAL kernel selection: reduction | DPFT_HEAD_LANES16 (tests) or DPFT_HEAD_LANES=16 in the environment
+    static const int env_lanes = [] { const char* e = getenv("DPFT_HEAD_LANES"); return e ? atoi(e) : 1; }();
+    const bool lanes16 = (reduction & DPFT_HEAD_LANES16) != 0 || env_lanes == 16;
+    reduction &= ~DPFT_HEAD_LANES16;
+    DPFT_REQUIRE(reduction >= 0 && reduction <= 2, "decoder_head: reduction=%d (0 linear, 1 mean, 2 max)", reduction);
     DPFT_REQUIRE(views && weights && center_in && query_out && center_out, "decoder_head: null pointer");
     DPFT_REQUIRE(!size_out == !angle_out && !size_out == !class_out, "decoder_head: size/angle/class outputs go together");
     DPFT_REQUIRE(n_cls >= 1 && n_cls <= 8, "decoder_head: n_cls=%d (1..8 supported)", n_cls);
@@ -627,6 +719,19 @@ extern "C" int dpft_decoder_head_forward(const float* views, const float* weight
         configured = smem;
     }
     const long long total = (long long)B * N;
+    if (lanes16) {
+        const size_t smem16 = (size_t)((weight_floats + 3) & ~3) * 4 + HQ * ROW * 4;
+        static size_t configured16 = 0;
+        if (smem16 > configured16) {
+            int st = cuda_status(cudaFuncSetAttribute(decoder_head16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem16),
+                                 "cudaFuncSetAttribute(decoder_head16_kernel)");
+            if (st) return st;
+            configured16 = smem16;
+        }
+        decoder_head16_kernel<<<(unsigned)((total + HQ - 1) / HQ), HQ * C, smem16, (cudaStream_t)stream>>>(prm);
+        DPFT_LAUNCH_CHECK("decoder_head16_kernel");
+        return DPFT_OK;
+    }
     decoder_head_kernel<<<(unsigned)((total + 127) / 128), 128, smem, (cudaStream_t)stream>>>(prm);
     DPFT_LAUNCH_CHECK("decoder_head_kernel");
     return DPFT_OK;

@@ -67,6 +67,9 @@ def pack_layer(layer) -> torch.Tensor:
     return img
 
 
+HEAD_LANES16 = 0x100      # include/dpft_b200.h: DPFT_HEAD_LANES16
+
+
 def pack_head(reduction_layer, head, reduction: str) -> torch.Tensor:
     """Reduction weight (16, V*16) then the centre / size / angle / class branches (3 Linear weights each)."""
     f = lambda t: t.detach().float().reshape(-1).cpu()
@@ -110,8 +113,11 @@ def layer_forward(views: Sequence[DecoderView], query: torch.Tensor, pos: torch.
 
 def head_forward(views: torch.Tensor, weights: torch.Tensor, center_in: torch.Tensor, query_out: torch.Tensor,
                  center_out: torch.Tensor, size_out, angle_out, class_out, B: int, V: int, N: int, n_cls: int,
-                 reduction: int) -> None:
+                 reduction: int, lanes16: bool = False) -> None:
+    """``lanes16``: the experimental sixteen-lanes-per-query kernel (DPFT_HEAD_LANES16 in include/dpft_b200.h)."""
     lib = native.load_library()
+    if lanes16:
+        reduction |= HEAD_LANES16
     cs = 0 if center_in.dim() == 2 else N * 3
     st = lib.dpft_decoder_head_forward(native.ptr(views), native.ptr(weights), native.ptr(center_in), cs,
                                        native.ptr(query_out), native.ptr(center_out), native.ptr(size_out),

@@ -6,6 +6,7 @@
 export DPFT_EXPERIMENTAL=1
 timeout 120 python -m pytest tests/test_features_gpu.py -m gpu -q -x --timeout 60 -k "column_builder" 2>&1 | tail -5
 timeout 300 python -m pytest tests/test_golden_taps_gpu.py -m gpu -q --timeout 120 2>&1 | tail -8
+timeout 120 python -m pytest tests/test_decoder_head16_gpu.py -m gpu -q -x --timeout 60 2>&1 | tail -5
 unset DPFT_EXPERIMENTAL
 # 2. the whole model with the experimental builder chosen by the automatic path, then the A/B on the bench workload
 DPFT_FPN_BUILD=2 timeout 300 python -m pytest tests/test_features_gpu.py tests/test_model_gpu.py -m gpu -q -x --timeout 120 2>&1 | tail -3
@@ -13,6 +14,13 @@ for v in 1 2; do
 DPFT_FPN_BUILD=$v timeout 200 python bench.py --steps 20 --warmup 4 --no-cpu-baseline 2>/dev/null | tail -1 | python -c "
 import sys,json
 r=json.loads(sys.stdin.read()); print('fpn_build=$v', 'ms', r['ms_per_step'], 'fps', r['value'], 'e2e', r['e2e']['value'], 'seq', r['sequential']['ms_per_step'])"
+done
+# 2b. sixteen-lanes-per-query head kernel (bit-identical by construction): whole-model tests, then the A/B
+DPFT_HEAD_LANES=16 timeout 300 python -m pytest tests/test_model_gpu.py -m gpu -q -x --timeout 120 2>&1 | tail -3
+for v in 1 16; do
+DPFT_HEAD_LANES=$v timeout 200 python bench.py --steps 20 --warmup 4 --no-cpu-baseline --depth 1 2>/dev/null | tail -1 | python -c "
+import sys,json
+r=json.loads(sys.stdin.read()); print('head_lanes=$v', 'sequential ms', r['ms_per_step'])"
 done
 # 3. per-stage times with the experimental builder (camera_mono.pyramid_total - camera_mono.backbone = the FPN part)
 DPFT_FPN_BUILD=2 timeout 200 python tools/stage_times.py 2>/dev/null | tail -1
