@@ -34,3 +34,38 @@ def import_reference_models():
         sys.path.insert(0, REFERENCE_SRC)
     import dprt.models as ref_models  # noqa: E402
     return ref_models
+
+
+def import_reference_dataset():
+    """``dprt.datasets.kradar.dataset`` of the unmodified reference.  Its package __init__ also imports the offline
+    pre-processing module, whose point-cloud dependency (pypcd) is not installed here: an empty stand-in module satisfies
+    that import; nothing of it is used."""
+    import_reference_models()
+    if "pypcd" not in sys.modules:
+        try:
+            import pypcd  # noqa: F401
+        except ImportError:
+            stub = types.ModuleType("pypcd")
+            stub.pypcd = types.ModuleType("pypcd.pypcd")
+            sys.modules["pypcd"] = stub
+            sys.modules["pypcd.pypcd"] = stub.pypcd
+    import dprt.datasets.kradar.dataset as ds
+    return ds
+
+
+def reference_sample_pipeline(ds_module, raw_sample, image_size, scale=True):
+    """The per-sample steps of KRadarDataset.__getitem__ (dataset.py:143-169) that follow load_sample_data, on one decoded
+    sample, through the reference's own methods (the instance is made without a dataset directory)."""
+    d = object.__new__(ds_module.KRadarDataset)
+    d.camera = "M" if "camera_mono" in raw_sample else ""
+    d.radar = ("B" if "radar_bev" in raw_sample else "") + ("F" if "radar_front" in raw_sample else "")
+    d.scale, d.image_size, d.dtype = scale, image_size, "float32"
+    sample = {k: v.clone() for k, v in raw_sample.items()}
+    if d.scale:
+        sample = d.scale_radar_data(sample)
+    sample = d._add_transformations(sample)
+    sample = d._add_projections(sample)
+    sample = d._add_shape(sample)
+    if d.image_size is not None:
+        sample = d.resize_image(sample)
+    return sample
