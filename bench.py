@@ -57,6 +57,8 @@ def parse():
                     help="forwards in flight in the timed loop (DPRT.infer_stream); 1 = one forward at a time with an L2 flush between steps")
     ap.add_argument("--side-priority", action="store_true", help="A/B: the radar views on high-priority streams")
     ap.add_argument("--no-graph", action="store_true", help="train mode: issue the step eagerly instead of replaying one CUDA graph")
+    ap.add_argument("--feeder", action="store_true",
+                    help="also time the e2e loop fed through dpft_b200.feeder (uint8 camera frames; experimental)")
     ap.add_argument("--dtype", default="f16", choices=["f16", "bf16", "f32"],
                     help="activation type of the native backbone (f32 = fused decoder on torch fp32 features)")
     return ap.parse_args()
@@ -430,7 +432,7 @@ def main():
     host2 = {k: v.pin_memory() for k, v in synthetic.synthetic_batch(cfg, B, seed=2000 + rank, sizes=sizes).items()}
     resident2 = {k: v.to(dev) for k, v in host2.items()}
 
-    def timed_stream(feed, steps, warmup, d2h):
+    def timed_stream(feed, steps, warmup, d2h, wrap=None):
         """K forwards through the public streaming call (DPRT.infer_stream, `depth` forwards in flight), timed as ONE region on
         the device: event before the first launch, event after the last output is handed out (and copied to the host)."""
         nonlocal out_host
@@ -441,7 +443,7 @@ def main():
 
         def drain(n):
             nonlocal out_host
-            for out in model.infer_stream(gen(n), depth=args.depth):
+            for out in model.infer_stream(wrap(gen(n)) if wrap else gen(n), depth=args.depth):
                 if d2h:
                     if out_host is None:
                         out_host = {k: torch.empty(v.shape, dtype=v.dtype).pin_memory() for k, v in out.items()}
@@ -482,6 +484,18 @@ def main():
         t_e2e = timed_stream([host, host2], args.steps, max(args.warmup, 3), d2h=True)
     elif rank != 0:
         clocks = None
+    e2e_feeder = None
+    if args.feeder and pipelined:
+        # EXPERIMENTAL (not yet validated on a B200, hence opt-in): the e2e loop fed with DECODER-side data through
+        # dpft_b200.feeder — uint8 camera frames and radar power cubes from pinned host memory, radar scaling / projections /
+        # shapes formed on the GPU — instead of the ready-made fp32 tensors of the reference's dataset contract
+        from dpft_b200 import feeder as fd
+        feed = fd.BatchFeeder(cfg["model"]["inputs"], image_size=None, scale=True, device=dev)
+        raws = [fd.synthetic_raw_batch(cfg["model"]["inputs"], B, seed=3000 + 10 * i + rank, sizes=sizes, pin=True) for i in range(2)]
+        t_feed = timed_stream(raws, args.steps, max(args.warmup, 3), d2h=True, wrap=feed.stream)
+        e2e_feeder = {"value": B * world * args.steps / t_feed, "unit": UNIT, "ms_per_step": 1e3 * t_feed / args.steps,
+                      "h2d_bytes_per_step": sum(v.numel() * v.element_size() for v in raws[0].values()),
+                      "note": "uint8 camera frames + f32 radar power cubes uploaded, dataset arithmetic on the GPU (dpft_b200/feeder.py)"}
     d2h_bytes = sum(v.numel() * v.element_size() for v in out_host.values())
 
     frames = B * world * args.steps
@@ -513,7 +527,7 @@ def main():
                 "roofline": roof, "roofline_msda": roof_msda, "clocks": clocks,
                 "e2e": {"value": frames / t_e2e, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes,
                         "d2h_bytes_per_step": d2h_bytes, "ms_per_step": 1e3 * t_e2e / args.steps},
-                "gpu_launches": launches,
+                "gpu_launches": launches, "e2e_feeder": e2e_feeder,
                 "sequential": {"value": frames / t_seq, "ms_per_step": 1e3 * t_seq / args.steps, "e2e_value": frames / t_seq_e2e,
                                "note": "one forward at a time, per-step CUDA events, L2 flushed between steps"}}
         if world == 1 and not args.no_cpu_baseline:

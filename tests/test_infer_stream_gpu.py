@@ -64,3 +64,33 @@ def test_stream_falls_back_to_sequential_without_the_graph():
     for a, b in zip(got, want):
         for k in a:
             assert torch.equal(a[k], b[k])
+
+
+@pytest.mark.skipif(__import__("os").environ.get("DPFT_EXPERIMENTAL") != "1", reason="not yet validated on a B200: DPFT_EXPERIMENTAL=1")
+def test_feeder_on_the_gpu_matches_the_cpu_and_feeds_the_stream():
+    """dpft_b200.feeder on cuda (uint8 frames uploaded on the copy stream, arithmetic on the GPU) against the same feeder on
+    the CPU (bit-exact against the reference dataset methods, tests/test_feeder.py), then DPRT.infer_stream fed by it."""
+    from dpft_b200 import configs, feeder
+    cfg = synthetic.offline_config(configs.make_config("kradar"), n_queries=(20, 15, 1))
+    sizes = {"camera_mono": (96, 160, 3), "radar_bev": (64, 48, 6), "radar_front": (37, 48, 6)}
+    inputs = cfg["model"]["inputs"]
+    raws = [feeder.synthetic_raw_batch(inputs, 2, seed=50 + i, sizes=sizes, pin=True) for i in range(3)]
+    cpu = feeder.BatchFeeder(inputs, image_size=64, device="cpu")
+    gpu = feeder.BatchFeeder(inputs, image_size=64, device="cuda:0")
+    for raw, got in zip(raws, gpu.stream(iter(raws))):
+        want = cpu.prepare(raw)
+        for k, w in want.items():
+            assert got[k].shape == w.shape and got[k].dtype == w.dtype, k
+            tol = 1e-3 if k == "camera_mono" else 0.0          # the library resize differs in rounding between CPU and CUDA
+            assert float((got[k].cpu().double() - w.double()).abs().max()) <= tol * 255, k
+    model = models.build("dprt", cfg).eval()
+    model.load_state_dict(synthetic.seeded_state_dict(model.state_dict(), seed=3))
+    model = model.to("cuda:0")
+    plain = feeder.BatchFeeder(inputs, image_size=None, device="cuda:0")
+    with torch.no_grad():
+        want = [model(plain.prepare(r)) for r in raws]
+        got = list(model.infer_stream(plain.stream(iter(raws)), depth=2))
+    assert len(got) == 3
+    for g, w in zip(got, want):
+        for k in w:
+            assert torch.allclose(g[k], w[k], rtol=1e-5, atol=1e-5), k

@@ -7,6 +7,7 @@ export DPFT_EXPERIMENTAL=1
 timeout 120 python -m pytest tests/test_features_gpu.py -m gpu -q -x --timeout 60 -k "column_builder" 2>&1 | tail -5
 timeout 300 python -m pytest tests/test_golden_taps_gpu.py -m gpu -q --timeout 120 2>&1 | tail -8
 timeout 120 python -m pytest tests/test_decoder_head16_gpu.py -m gpu -q -x --timeout 60 2>&1 | tail -5
+timeout 120 python -m pytest tests/test_infer_stream_gpu.py -m gpu -q -x --timeout 60 -k feeder 2>&1 | tail -5
 unset DPFT_EXPERIMENTAL
 # 2. the whole model with the experimental builder chosen by the automatic path, then the A/B on the bench workload
 DPFT_FPN_BUILD=2 timeout 300 python -m pytest tests/test_features_gpu.py tests/test_model_gpu.py -m gpu -q -x --timeout 120 2>&1 | tail -3
@@ -24,3 +25,7 @@ r=json.loads(sys.stdin.read()); print('head_lanes=$v', 'sequential ms', r['ms_pe
 done
 # 3. per-stage times with the experimental builder (camera_mono.pyramid_total - camera_mono.backbone = the FPN part)
 DPFT_FPN_BUILD=2 timeout 200 python tools/stage_times.py 2>/dev/null | tail -1
+# 4. e2e through the batch feeder (uint8 camera frames uploaded, dataset arithmetic on the GPU): compare e2e_feeder with e2e
+timeout 200 python bench.py --steps 20 --warmup 4 --no-cpu-baseline --feeder 2>/dev/null | tail -1 | python -c "
+import sys,json
+r=json.loads(sys.stdin.read()); print('e2e', r['e2e'], 'e2e_feeder', r['e2e_feeder'])"
