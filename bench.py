@@ -57,6 +57,9 @@ def parse():
                     help="forwards in flight in the timed loop (DPRT.infer_stream); 1 = one forward at a time with an L2 flush between steps")
     ap.add_argument("--side-priority", action="store_true", help="A/B: the radar views on high-priority streams")
     ap.add_argument("--no-graph", action="store_true", help="train mode: issue the step eagerly instead of replaying one CUDA graph")
+    ap.add_argument("--criterion", action="store_true",
+                    help="train mode: the reference's criterion (Hungarian assigner + focal / L1 set criterion, dpft_b200/criterion.py) on "
+                         "synthetic labels instead of the fixed scalar loss; issues the step eagerly (the assignment is solved on the host)")
     ap.add_argument("--feeder", action="store_true",
                     help="also time the e2e loop fed through dpft_b200.feeder (uint8 camera frames; experimental)")
     ap.add_argument("--dtype", default="f16", choices=["f16", "bf16", "f32"],
@@ -280,7 +283,7 @@ def run_train(args, cfg, sizes, rank, world, dev):
     weights, module-by-module path with the native deformable-attention fwd/bwd; fixed scalar loss sum_k mean(out_k^2)
     because the reference loss needs pytorch3d (absent)."""
     import torch.distributed as dist
-    from dpft_b200 import ddp, models, native, synthetic
+    from dpft_b200 import configs, ddp, models, native, synthetic
     torch.manual_seed(42)
     cfg_t = synthetic.offline_config(cfg, n_queries=N_QUERIES)
     model = models.build("dprt", cfg_t)
@@ -292,13 +295,34 @@ def run_train(args, cfg, sizes, rank, world, dev):
         ddp.broadcast_parameters(model, src=0)
     from dpft_b200.train_step import GraphedTrainStep
     bucket = ddp.GradientBucket(model, n_chunks=6)
-    graphed = not args.no_graph
+    graphed = not args.no_graph and not args.criterion
     opt = torch.optim.AdamW(bucket.params, lr=1e-4, capturable=graphed)
     B = args.batch
     batch = synthetic.synthetic_batch(cfg_t, B, seed=42 + rank, sizes=sizes, device=dev)
+    loss_name = "sum_k mean(out_k^2)"
+    loss_fn = lambda out, _b: sum((v ** 2).mean() for v in out.values())
+    if args.criterion:
+        # EXPERIMENTAL (written without GPU access): SURVEY §8d config 4's "real loss" variant — 1..8 boxes per sample inside the
+        # field of view of config/kradar.json:25-30, one-hot classes of width 2, (sin, cos) angles
+        from dpft_b200 import criterion as crit
+        g = torch.Generator().manual_seed(4242 + rank)
+        labels = []
+        for _ in range(B):
+            m = int(torch.randint(1, 9, (1,), generator=g))
+            a = torch.rand(m, generator=g) * 6.2831853
+            lo, hi = torch.tensor([0.0, -6.4, -2.0]), torch.tensor([72.0, 6.4, 6.0])
+            labels.append({k: v.to(dev) for k, v in {
+                "gt_class": torch.nn.functional.one_hot(torch.randint(0, 2, (m,), generator=g), 2).float(),
+                "gt_center": lo + torch.rand(m, 3, generator=g) * (hi - lo),
+                "gt_size": torch.rand(m, 3, generator=g) * torch.tensor([3.0, 1.0, 1.0]) + torch.tensor([3.0, 1.5, 1.2]),
+                "gt_angle": torch.stack((torch.sin(a), torch.cos(a)), -1)}.items()})
+        criterion = crit.build_loss(configs.make_config("kradar")["train"] | {
+            "anassigner": "HungarianAnassigner", "criterion": "SetCriterion",
+            "loss_weights": {"total_class": 1.0, "object_class": 0.0, "center": 1.0, "size": 1.0, "angle": 1.0}})
+        loss_fn = lambda out, _b: criterion(out, labels)[0]
+        loss_name = "reference criterion (HungarianAnassigner + SetCriterion: focal + L1; dpft_b200/criterion.py), synthetic labels"
     # the whole step (zero -> fwd -> loss -> bwd + all-reduce -> AdamW) is one CUDA graph, replayed per step
-    train_step = GraphedTrainStep(model, bucket, opt, lambda out, _b: sum((v ** 2).mean() for v in out.values()),
-                                  graph=graphed, warmup=3)
+    train_step = GraphedTrainStep(model, bucket, opt, loss_fn, graph=graphed, warmup=3)
 
     def step():
         return train_step(batch)
@@ -331,7 +355,7 @@ def run_train(args, cfg, sizes, rank, world, dev):
                                    else "f32 (torch TF32 convs allowed, as the reference's default)",
                           "data": "synthetic",
                           "config": {"workload": WORKLOAD.replace("eval forward", "training step (fwd+bwd+all-reduce+AdamW)"),
-                                     "frames_per_gpu": B, "parallelism": f"dp{world}", "loss": "sum_k mean(out_k^2)",
+                                     "frames_per_gpu": B, "parallelism": f"dp{world}", "loss": loss_name,
                                      "gradient_bucket_bytes": bucket.bytes(), "bucket_chunks": bucket.n_chunks,
                                      "launch": "one CUDA graph per step" if graphed else "eager"},
                           "gpu_launches": (train_step.native_launches_per_step * args.steps if graphed

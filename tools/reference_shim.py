@@ -69,3 +69,23 @@ def reference_sample_pipeline(ds_module, raw_sample, image_size, scale=True):
     if d.image_size is not None:
         sample = d.resize_image(sample)
     return sample
+
+
+def import_reference_loss(box3d_overlap):
+    """``dprt.training.loss`` (+ assigner, utils.iou / bbox) of the unmodified reference, without running the package
+    __init__ of dprt.training (it pulls in the trainer -> tensorboard / deepspeed, absent here).  ``pytorch3d`` is not
+    installed: ``box3d_overlap`` (dpft_b200.criterion.box3d_overlap) is registered as ``pytorch3d.ops.box3d_overlap`` — the
+    reference's own loss / assigner / GIoU code then runs unmodified around that one function."""
+    import importlib
+    import_reference_models()
+    p3d, ops = types.ModuleType("pytorch3d"), types.ModuleType("pytorch3d.ops")
+    ops.box3d_overlap = box3d_overlap
+    p3d.ops = ops
+    sys.modules["pytorch3d"], sys.modules["pytorch3d.ops"] = p3d, ops
+    if "dprt.training" not in sys.modules:
+        pkg = types.ModuleType("dprt.training")
+        pkg.__path__ = [os.path.join(REFERENCE_SRC, "dprt", "training")]
+        sys.modules["dprt.training"] = pkg
+    for name in ("dprt.utils.iou", "dprt.training.assigner", "dprt.training.loss"):
+        sys.modules.pop(name, None)
+    return importlib.import_module("dprt.training.loss")
