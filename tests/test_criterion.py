@@ -155,6 +155,6 @@ def test_criterion_drives_a_model_training_step():
         total.backward()
     assert torch.isfinite(total) and float(total) > 0
     grads = {k: p.grad for k, p in model.named_parameters()}
-    for key in ("fuser.heads.3.layers.class_head.0.weight", "fuser.heads.3.layers.size_head.6.weight", "fuser.query",
+    for key in ("fuser.heads.3.layers.class_head.0.weight", "fuser.heads.3.layers.center_head.6.weight", "fuser.query",
                 "backbones.radar_bev.body.conv1.weight"):
         assert grads[key] is not None and torch.isfinite(grads[key]).all() and float(grads[key].abs().max()) > 0, key
