@@ -2,7 +2,6 @@
 SURVEY.md §8c's golden-vector list — per-level FPN + embedding features, reference points per view and iteration, fused
 queries, per-iteration centres, MSDeformAttn outputs, and the gradients of the fixed scalar loss sum_k mean(out_k^2).
 The oracle restatement and the product's host logic (CUDA op swapped for the oracle op) are both checked on the CPU."""
-import pytest
 import torch
 
 import model_taps
