@@ -89,3 +89,17 @@ def import_reference_loss(box3d_overlap):
     for name in ("dprt.utils.iou", "dprt.training.assigner", "dprt.training.loss"):
         sys.modules.pop(name, None)
     return importlib.import_module("dprt.training.loss")
+
+
+def import_reference_metric(box3d_overlap):
+    """``dprt.evaluation.metric`` of the unmodified reference, without running the package __init__ of dprt.evaluation (the
+    evaluator needs deepspeed, absent here) and with ``box3d_overlap`` standing in for the absent pytorch3d op (as in
+    import_reference_loss)."""
+    import importlib
+    import_reference_loss(box3d_overlap)
+    if "dprt.evaluation" not in sys.modules:
+        pkg = types.ModuleType("dprt.evaluation")
+        pkg.__path__ = [os.path.join(REFERENCE_SRC, "dprt", "evaluation")]
+        sys.modules["dprt.evaluation"] = pkg
+    sys.modules.pop("dprt.evaluation.metric", None)
+    return importlib.import_module("dprt.evaluation.metric")
