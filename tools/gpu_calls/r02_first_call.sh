@@ -8,6 +8,7 @@ timeout 120 python -m pytest tests/test_features_gpu.py -m gpu -q -x --timeout 6
 timeout 300 python -m pytest tests/test_golden_taps_gpu.py -m gpu -q --timeout 120 2>&1 | tail -8
 timeout 120 python -m pytest tests/test_decoder_head16_gpu.py -m gpu -q -x --timeout 60 2>&1 | tail -5
 timeout 120 python -m pytest tests/test_infer_stream_gpu.py -m gpu -q -x --timeout 60 -k feeder 2>&1 | tail -5
+timeout 120 python -m pytest tests/test_criterion_metrics_gpu.py -m gpu -q --timeout 60 2>&1 | tail -5
 unset DPFT_EXPERIMENTAL
 # 2. the whole model with the experimental builder chosen by the automatic path, then the A/B on the bench workload
 DPFT_FPN_BUILD=2 timeout 300 python -m pytest tests/test_features_gpu.py tests/test_model_gpu.py -m gpu -q -x --timeout 120 2>&1 | tail -3
@@ -29,3 +30,6 @@ DPFT_FPN_BUILD=2 timeout 200 python tools/stage_times.py 2>/dev/null | tail -1
 timeout 200 python bench.py --steps 20 --warmup 4 --no-cpu-baseline --feeder 2>/dev/null | tail -1 | python -c "
 import sys,json
 r=json.loads(sys.stdin.read()); print('e2e', r['e2e'], 'e2e_feeder', r['e2e_feeder'])"
+# 5. training step with the reference criterion (eager: the assignment is a host solve) next to the fixed scalar loss
+timeout 300 python bench.py --mode train --steps 10 --warmup 3 --criterion 2>/dev/null | tail -1
+timeout 300 python bench.py --mode train --steps 10 --warmup 3 --no-graph 2>/dev/null | tail -1
