@@ -197,19 +197,55 @@ def pad_targets(targets: Sequence[Dict[str, torch.Tensor]], device, dtype) -> Tu
     return out, mask
 
 
+def order_like_scipy(col4row: torch.Tensor, counts: torch.Tensor, N: int):
+    """(B, Mmax) prediction matched to each target (-1 in padded slots), (B,) valid targets -> (index_i, index_j, mask) in the
+    order scipy.optimize.linear_sum_assignment returns for an (N x M) cost matrix: pairs sorted by prediction index.
+    Tensor ops only (no host synchronisation)."""
+    B, Mmax = col4row.shape
+    slot = torch.arange(Mmax, device=col4row.device)
+    valid = slot[None, :] < counts[:, None]
+    key = torch.where(valid, col4row, N + slot[None, :].expand(B, -1))          # padded slots sort behind every prediction
+    index_i, index_j = torch.sort(key, dim=1)
+    return torch.where(valid, index_i, torch.zeros_like(index_i)), torch.where(valid, index_j, torch.zeros_like(index_j)), valid
+
+
+def lsap_device(cost: torch.Tensor, counts: torch.Tensor) -> torch.Tensor:
+    """``dpft_lsap_forward`` (csrc/lsap.cu): cost (B, N, Mmax) float32 cuda, counts (B,) int32 cuda -> (B, Mmax) int64, the
+    prediction matched to each ground-truth box.  EXPERIMENTAL (not yet validated on a B200)."""
+    from . import native
+    native.require_cuda(cost, counts)
+    if cost.dtype != torch.float32 or counts.dtype != torch.int32:
+        raise RuntimeError("lsap_device: cost must be float32 and counts int32")
+    cost = cost.contiguous()
+    B, N, Mmax = cost.shape
+    out = torch.empty((B, Mmax), dtype=torch.int64, device=cost.device)
+    with torch.cuda.device(cost.device):
+        st = native.load_library().dpft_lsap_forward(native.ptr(cost), native.ptr(counts), native.ptr(out), B, N, Mmax,
+                                                     native.stream_ptr(cost.device))
+    native.check(st, "dpft_lsap_forward")
+    native.count_launch()
+    return out
+
+
 class HungarianAnassigner(nn.Module):
     """assigner.py:26-143 for a whole batch: one cost tensor (B, N, Mmax) on the device, ONE copy to the host, one scipy
     linear_sum_assignment per sample.  Returns (index_i, index_j, mask), each (B, Mmax): matched prediction / target indices
-    in the LSAP's order (ascending prediction index), padded slots masked out."""
+    in the LSAP's order (ascending prediction index), padded slots masked out.
 
-    def __init__(self, loss_weights: Dict[str, float] = None, giou_weight: float = 1.0, **kwargs):
+    ``solver="device"`` (EXPERIMENTAL, CUDA tensors only): the assignment is solved by ``dpft_lsap_forward`` on the GPU
+    instead — no host synchronisation at all in the criterion."""
+
+    def __init__(self, loss_weights: Dict[str, float] = None, giou_weight: float = 1.0, solver: str = "host", **kwargs):
         super().__init__()
         self.loss_weights = loss_weights
         self.giou_weight = giou_weight
+        if solver not in ("host", "device"):
+            raise ValueError("solver must be 'host' (scipy, one device->host copy per step) or 'device' (dpft_lsap_forward)")
+        self.solver = solver
 
     @classmethod
     def from_config(cls, config: Dict[str, Any]) -> "HungarianAnassigner":
-        return cls(loss_weights=config.get("loss_weights"))
+        return cls(loss_weights=config.get("loss_weights"), solver=config.get("lsap_solver", "host"))
 
     @torch.no_grad()
     def cost(self, outputs: Dict[str, torch.Tensor], tgt: Dict[str, torch.Tensor], mask: torch.Tensor) -> torch.Tensor:
@@ -228,6 +264,10 @@ class HungarianAnassigner(nn.Module):
 
     @torch.no_grad()
     def forward(self, outputs: Dict[str, torch.Tensor], tgt: Dict[str, torch.Tensor], mask: torch.Tensor):
+        if self.solver == "device":
+            cost = self.cost(outputs, tgt, mask).float()
+            counts = mask.sum(1).to(torch.int32)
+            return order_like_scipy(lsap_device(cost, counts), counts, cost.shape[1])
         from scipy.optimize import linear_sum_assignment
         C = self.cost(outputs, tgt, mask).cpu()                                                # the step's one device sync
         counts = mask.sum(1).tolist()

@@ -292,6 +292,16 @@ DPFT_API int dpft_pack_conv_weights(const void* table, int n_layers, long long t
  * gradient (Cout, Cin, R, S) which is ADDED to. */
 DPFT_API int dpft_unpack_conv_wgrads(const void* table, int n_layers, long long total, void* stream);
 
+/*
+ * Hungarian assignment of the training criterion on the device (EXPERIMENTAL: written without GPU access).  Replaces the
+ * per-sample `C.cpu()` + scipy.optimize.linear_sum_assignment of HungarianAnassigner.forward
+ * (src/dprt/training/assigner.py:134-141): one warp per sample solves the rectangular linear-sum-assignment problem by
+ * shortest augmenting paths (dpft_b200/csrc/lsap_core.h; the same source, built for the host, is checked against scipy).
+ *   cost (B, N, Mmax) f32: cost[b][n][m] of matching prediction n to ground-truth box m;  counts (B) int32: valid boxes of
+ *   each sample (<= Mmax <= 64 <= N);  col4row (B, Mmax) int64 out: the prediction matched to each box, -1 for padded slots.
+ */
+DPFT_API int dpft_lsap_forward(const float* cost, const int* counts, long long* col4row, int B, int N, int Mmax, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
