@@ -60,6 +60,9 @@ def parse():
     ap.add_argument("--criterion", action="store_true",
                     help="train mode: the reference's criterion (Hungarian assigner + focal / L1 set criterion, dpft_b200/criterion.py) on "
                          "synthetic labels instead of the fixed scalar loss; issues the step eagerly (the assignment is solved on the host)")
+    ap.add_argument("--lsap", default="host", choices=["host", "device"],
+                    help="--criterion: where the Hungarian assignment is solved (host = scipy, eager step; device = dpft_lsap_forward, "
+                         "no host synchronisation, step captured as one CUDA graph)")
     ap.add_argument("--feeder", action="store_true",
                     help="also time the e2e loop fed through dpft_b200.feeder (uint8 camera frames; experimental)")
     ap.add_argument("--dtype", default="f16", choices=["f16", "bf16", "f32"],
@@ -295,7 +298,7 @@ def run_train(args, cfg, sizes, rank, world, dev):
         ddp.broadcast_parameters(model, src=0)
     from dpft_b200.train_step import GraphedTrainStep
     bucket = ddp.GradientBucket(model, n_chunks=6)
-    graphed = not args.no_graph and not args.criterion
+    graphed = not args.no_graph and not (args.criterion and args.lsap == "host")
     opt = torch.optim.AdamW(bucket.params, lr=1e-4, capturable=graphed)
     B = args.batch
     batch = synthetic.synthetic_batch(cfg_t, B, seed=42 + rank, sizes=sizes, device=dev)
@@ -317,9 +320,10 @@ def run_train(args, cfg, sizes, rank, world, dev):
                 "gt_size": torch.rand(m, 3, generator=g) * torch.tensor([3.0, 1.0, 1.0]) + torch.tensor([3.0, 1.5, 1.2]),
                 "gt_angle": torch.stack((torch.sin(a), torch.cos(a)), -1)}.items()})
         criterion = crit.build_loss(configs.make_config("kradar")["train"] | {
-            "anassigner": "HungarianAnassigner", "criterion": "SetCriterion",
+            "anassigner": "HungarianAnassigner", "criterion": "SetCriterion", "lsap_solver": args.lsap,
             "loss_weights": {"total_class": 1.0, "object_class": 0.0, "center": 1.0, "size": 1.0, "angle": 1.0}})
-        loss_fn = lambda out, _b: criterion(out, labels)[0]
+        tgt, tgt_mask = crit.pad_targets(labels, dev, torch.float32)        # static inputs of the (possibly captured) step
+        loss_fn = lambda out, _b: criterion.forward_padded(out, tgt, tgt_mask)[0]
         loss_name = "reference criterion (HungarianAnassigner + SetCriterion: focal + L1; dpft_b200/criterion.py), synthetic labels"
     # the whole step (zero -> fwd -> loss -> bwd + all-reduce -> AdamW) is one CUDA graph, replayed per step
     train_step = GraphedTrainStep(model, bucket, opt, loss_fn, graph=graphed, warmup=3)

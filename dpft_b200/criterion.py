@@ -346,6 +346,12 @@ class Loss(nn.Module):
     def forward(self, inputs: Dict[str, torch.Tensor], targets: List[Dict[str, torch.Tensor]]):
         ref = inputs["class"]
         tgt, mask = pad_targets(targets, ref.device, ref.dtype)
+        return self.forward_padded(inputs, tgt, mask)
+
+    def forward_padded(self, inputs: Dict[str, torch.Tensor], tgt: Dict[str, torch.Tensor], mask: torch.Tensor):
+        """The same on targets already padded by ``pad_targets`` (device tensors).  With ``lsap_solver: "device"`` nothing
+        in here touches the host, so it can sit inside a captured CUDA graph (dpft_b200/train_step.py) with ``tgt`` / ``mask``
+        as static inputs."""
         indices = self.anassigner({k: v.detach() for k, v in inputs.items()}, tgt, mask)
         per_sample = self.criterion(inputs, tgt, indices)
         losses = {k: per_sample[k] * w for k, w in self.loss_weights.items()}

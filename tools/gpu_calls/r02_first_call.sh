@@ -32,4 +32,5 @@ import sys,json
 r=json.loads(sys.stdin.read()); print('e2e', r['e2e'], 'e2e_feeder', r['e2e_feeder'])"
 # 5. training step with the reference criterion (eager: the assignment is a host solve) next to the fixed scalar loss
 timeout 300 python bench.py --mode train --steps 10 --warmup 3 --criterion 2>/dev/null | tail -1
+timeout 300 python bench.py --mode train --steps 10 --warmup 3 --criterion --lsap device 2>/dev/null | tail -1   # one graph per step
 timeout 300 python bench.py --mode train --steps 10 --warmup 3 --no-graph 2>/dev/null | tail -1
