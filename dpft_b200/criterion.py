@@ -31,13 +31,26 @@ import torch.nn.functional as F
 from torch import nn
 
 
+_CONSTANTS: Dict[Tuple[str, str, torch.dtype], torch.Tensor] = {}
+
+
+def _const(name: str, values, device, dtype: torch.dtype) -> torch.Tensor:
+    """Small constant tables, created once per (device, dtype): a host->device copy of a fresh tensor is not allowed while a
+    CUDA graph is being captured, a cached device tensor is (the warm-up steps before the capture fill the cache)."""
+    key = (name, str(device), dtype)
+    t = _CONSTANTS.get(key)
+    if t is None:
+        t = _CONSTANTS[key] = torch.tensor(values, device=device, dtype=dtype)
+    return t
+
+
 # ------------------------------------------------------------------------------------------------------------ boxes
 def get_box_corners(center: torch.Tensor, size: torch.Tensor, angle: torch.Tensor) -> torch.Tensor:
     """(…, 3), (…, 3) = (l, w, h), (…) yaw in radians -> (…, 8, 3) corners, bottom face 0-3 counter-clockwise, top face 4-7
     (bbox.py:4-80)."""
-    sx = torch.tensor([-1, 1, 1, -1, -1, 1, 1, -1], device=center.device, dtype=center.dtype)
-    sy = torch.tensor([-1, -1, 1, 1, -1, -1, 1, 1], device=center.device, dtype=center.dtype)
-    sz = torch.tensor([-1, -1, -1, -1, 1, 1, 1, 1], device=center.device, dtype=center.dtype)
+    sx = _const("sx", [-1, 1, 1, -1, -1, 1, 1, -1], center.device, center.dtype)
+    sy = _const("sy", [-1, -1, 1, 1, -1, -1, 1, 1], center.device, center.dtype)
+    sz = _const("sz", [-1, -1, -1, -1, 1, 1, 1, 1], center.device, center.dtype)
     x = (size[..., 0] / 2)[..., None] * sx
     y = (size[..., 1] / 2)[..., None] * sy
     z = (size[..., 2] / 2)[..., None] * sz
@@ -129,10 +142,10 @@ def valid_boxes(boxes: torch.Tensor, eps: float = 1e-4) -> torch.Tensor:
     """(K, 8, 3) -> (K,) bool: the two checks the reference applies before the overlap (iou.py:9-70): every face triangle has
     an area above eps, and the summed out-of-plane distance of each face's fourth vertex is below eps."""
     K = boxes.shape[0]
-    tri = torch.tensor(_TRIANGLES, dtype=torch.int64, device=boxes.device)
+    tri = _const("triangles", _TRIANGLES, boxes.device, torch.int64)
     v0, v1, v2 = boxes.index_select(1, tri.view(-1)).reshape(K, len(_TRIANGLES), 3, 3).unbind(2)
     nonzero = ((torch.cross(v1 - v0, v2 - v0, dim=-1).norm(dim=-1) / 2) > eps).all(dim=1)
-    pl = torch.tensor(_PLANES, dtype=torch.int64, device=boxes.device)
+    pl = _const("planes", _PLANES, boxes.device, torch.int64)
     p0, p1, p2, p3 = boxes.index_select(1, pl.view(-1)).reshape(K, len(_PLANES), 4, 3).unbind(2)
     normal = F.normalize(torch.cross(F.normalize(p1 - p0, dim=-1), F.normalize(p2 - p0, dim=-1), dim=-1), dim=-1)
     coplanar = ((p3 - p0) * normal).sum((-1, -2)).abs() < eps
