@@ -23,10 +23,16 @@ def lsap_host(tmp_path_factory):
     lib.lsap_host.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_void_p]
     lib.lsap_host.restype = ctypes.c_int
 
-    def solve(cost, m):                      # cost (N, Mmax) float32, first m columns valid -> prediction per target
+    lib.lsap_host_lanes.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_void_p]
+    lib.lsap_host_lanes.restype = ctypes.c_int
+
+    def solve(cost, m, lanes=None):          # cost (N, Mmax) float32, first m columns valid -> prediction per target
         cost = np.ascontiguousarray(cost, dtype=np.float32)
         out = np.full(cost.shape[1], -7, dtype=np.int64)
-        st = lib.lsap_host(cost.ctypes.data, cost.shape[1], m, cost.shape[0], out.ctypes.data)
+        if lanes is None:
+            st = lib.lsap_host(cost.ctypes.data, cost.shape[1], m, cost.shape[0], out.ctypes.data)
+        else:
+            st = lib.lsap_host_lanes(cost.ctypes.data, cost.shape[1], m, cost.shape[0], lanes, out.ctypes.data)
         return st, out
     return solve
 
@@ -73,3 +79,21 @@ def test_output_reordering_equals_scipy_convention(lsap_host):
             rows, cols = linear_sum_assignment(cost[b, :, :m].astype(np.float64))
             assert i[b, :m].tolist() == rows.tolist() and j[b, :m].tolist() == cols.tolist()
         assert i[b, m:].abs().sum() == 0 and j[b, m:].abs().sum() == 0
+
+
+def test_warp_decomposition_emulated_on_the_host_matches_the_sequential_build(lsap_host):
+    """The kernel's 32-lane decomposition (lane-strided scans + xor-butterfly reduction with the shared ordering rule),
+    emulated lane by lane on the host: all lanes agree on every winner and the matching equals the sequential build's —
+    including cost matrices full of ties, where the tie rule decides."""
+    rng = np.random.default_rng(2)
+    for t in range(200):
+        N = int(rng.integers(1, 450))
+        M = int(rng.integers(1, min(N, 64) + 1))
+        c = rng.standard_normal((N, M)).astype(np.float32)
+        if t % 2 == 0:
+            c = np.round(c * 2)
+        st1, seq = lsap_host(c, M)
+        for lanes in (32, 4):
+            st2, par = lsap_host(c, M, lanes=lanes)
+            assert st1 == 0 and st2 == 0
+            assert (seq[:M] == par[:M]).all(), (t, lanes)
