@@ -49,7 +49,7 @@ def stem_forward(x: torch.Tensor, w: torch.Tensor, bias: torch.Tensor, dtype: to
                  impl: int = 0, w_packed: Optional[torch.Tensor] = None, relu: bool = True) -> torch.Tensor:
     B, H, W, Cin = x.shape
     y = torch.empty((B, (H - 1) // 2 + 1, (W - 1) // 2 + 1, 64), dtype=dtype, device=x.device)
-    if w_packed is None and impl in (2, 3):
+    if w_packed is None and impl == 2:
         w_packed = stem_pack_weights(w)
     st = _lib().dpft_stem_conv7x7_forward_ex(native.ptr(x), native.ptr(w), native.ptr(w_packed), native.ptr(bias), native.ptr(y), B, H, W,
                                              Cin, native.dtype_code(y), impl, int(relu), native.stream_ptr(x.device))
