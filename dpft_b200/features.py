@@ -10,6 +10,8 @@ FPN / embedding / pyramid in fp32.  Weights are re-laid-out once when the engine
 """
 from __future__ import annotations
 
+import os
+
 from typing import Dict, List, Optional, Tuple
 
 import torch
@@ -95,6 +97,10 @@ def fpn_output_forward(pyramid: torch.Tensor, start: int, H: int, W: int, w: tor
                                         impl, native.stream_ptr(pyramid.device))
     native.check(st, "dpft_fpn_output_forward")
     native.count_launch()
+
+
+# EXPERIMENTAL (DPFT_FPN_FORK=1; written without GPU access, off by default): see NativeView._pyramid_forked
+_FPN_FORK = os.environ.get("DPFT_FPN_FORK") == "1"
 
 
 class NativeView:
@@ -186,6 +192,38 @@ class NativeView:
             feats.append(y)
         return feats
 
+    def _pyramid_forked(self, x, feats, pyr, shapes, starts, first):
+        """Same kernels, same arguments, different order: the top-down chain of lateral GEMMs (each needs only the coarser
+        INNER map) runs first; the small output-stage launches of the backbone levels (latency-bound, ~15 us each) then go to a
+        forked stream and overlap the one large launch of the raw level instead of standing in front of it.  Results are
+        bit-identical (no kernel sees different inputs)."""
+        dev = x.device
+        main = torch.cuda.current_stream(dev)
+        if getattr(self, "_fork_stream", None) is None:
+            self._fork_stream = torch.cuda.Stream(device=dev)
+        inners, coarse = {}, None
+        for li in range(self.n_levels - 1, first - 1, -1):
+            coarse = inners[li] = lateral_forward(feats[li - first], self.lat_w[li], self.lat_b[li], coarse)
+        fork = torch.cuda.Event()
+        fork.record(main)
+        self._fork_stream.wait_event(fork)
+        with torch.cuda.stream(self._fork_stream):
+            for li in range(self.n_levels - 1, first - 1, -1):
+                H, W = shapes[li]
+                py, px = self._tables(li, H, W)
+                fpn_output_forward(pyr, starts[li], H, W, self.out_w[li], self.out_b[li], py, px, inner=inners[li],
+                                   w_packed=self.out_w_packed[li])
+            done = torch.cuda.Event()
+            done.record(self._fork_stream)
+        if self.skiplink:
+            H, W = shapes[0]
+            py, px = self._tables(0, H, W)
+            fpn_output_forward(pyr, 0, H, W, self.out_w[0], self.out_b[0], py, px, raw=x, lat_w=self.lat_w[0],
+                               lat_b=self.lat_b[0], coarse=inners[first], w_packed=self.out_w_packed[0])
+        main.wait_event(done)
+        del inners                      # alive until the join: their memory is not reused while the forked stream reads it
+        return pyr, shapes
+
     def pyramid(self, x: torch.Tensor) -> Tuple[torch.Tensor, List[Tuple[int, int]]]:
         x = x.contiguous()
         B = x.shape[0]
@@ -197,6 +235,8 @@ class NativeView:
         pyr = torch.empty((B, S, FC), dtype=self.pyramid_dtype, device=x.device)
         first = 1 if self.skiplink else 0
         coarse = None
+        if _FPN_FORK and x.is_cuda and self.n_levels - first >= 2:
+            return self._pyramid_forked(x, feats, pyr, shapes, starts, first)
         # top-down: coarsest level first
         for li in range(self.n_levels - 1, first - 1, -1):
             f = feats[li - first]

@@ -24,6 +24,13 @@ DPFT_HEAD_LANES=$v timeout 200 python bench.py --steps 20 --warmup 4 --no-cpu-ba
 import sys,json
 r=json.loads(sys.stdin.read()); print('head_lanes=$v', 'sequential ms', r['ms_per_step'])"
 done
+# 2c. forked FPN output launches (same kernels, different order / stream): model tests, then the A/B
+DPFT_FPN_FORK=1 timeout 300 python -m pytest tests/test_features_gpu.py tests/test_model_gpu.py tests/test_infer_stream_gpu.py -m gpu -q -x --timeout 120 2>&1 | tail -3
+for v in 0 1; do
+DPFT_FPN_FORK=$v timeout 200 python bench.py --steps 20 --warmup 4 --no-cpu-baseline 2>/dev/null | tail -1 | python -c "
+import sys,json
+r=json.loads(sys.stdin.read()); print('fpn_fork=$v', 'ms', r['ms_per_step'], 'seq', r['sequential']['ms_per_step'])"
+done
 # 3. per-stage times with the experimental builder (camera_mono.pyramid_total - camera_mono.backbone = the FPN part)
 DPFT_FPN_BUILD=2 timeout 200 python tools/stage_times.py 2>/dev/null | tail -1
 # 4. e2e through the batch feeder (uint8 camera frames uploaded, dataset arithmetic on the GPU): compare e2e_feeder with e2e
