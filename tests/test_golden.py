@@ -9,7 +9,7 @@ from dpft_b200 import models, synthetic
 from oracle import dprt_oracle
 
 CASES = ["radar_bev_native", "radar_bev_256", "radar_front_native", "camera_mono_small", "fusion_small_300q",
-         "fusion_native_1", "stress_4level_d64_900q"]
+         "fusion_native_1", "stress_4level_d64_900q", "radar_two_views"]
 
 
 @pytest.mark.parametrize("name", CASES)
@@ -25,7 +25,7 @@ def test_oracle_model_matches_reference_golden(name):
         assert rel_err(out[k], want) < 5e-4, k  # fp32 end-to-end; north_star bar is 1e-3 rel
 
 
-@pytest.mark.parametrize("name", ["radar_bev_native", "fusion_small_300q", "stress_4level_d64_900q"])
+@pytest.mark.parametrize("name", ["radar_bev_native", "fusion_small_300q", "stress_4level_d64_900q", "radar_two_views"])
 def test_product_host_logic_matches_reference_golden(name):
     rec = load_golden(name)
     cfg, batch = case_setup(rec)

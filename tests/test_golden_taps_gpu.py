@@ -60,3 +60,23 @@ def test_gpu_training_gradients_match_reference_digest(native_train):
     else:
         assert abs(float(loss.detach()) - rec["loss"]) < 1e-3 * abs(rec["loss"])
         assert worst_norm < 2e-2 and worst_val < 1e-1, (worst_norm, worst_val)
+
+
+@pytest.mark.parametrize("path", ["composed_fp32", "fused_decoder_fp32", "native_f16"])
+def test_two_view_radar_model_matches_reference_golden(path):
+    """config/kradar_radar.json (V = 2: range-azimuth + elevation-azimuth) through the module-by-module path, the fused decoder
+    on fp32 features and the native 16-bit pipeline — the shipped two-view configuration had no GPU golden case."""
+    fused, native_feats, tol = {"composed_fp32": (False, False, 1e-3), "fused_decoder_fp32": (True, False, 1e-3),
+                                "native_f16": (True, True, 1e-2)}[path]
+    rec = load_golden("radar_two_views")
+    cfg, batch = case_setup(rec)
+    model = models.build("dprt", cfg).eval()
+    model.load_state_dict(synthetic.seeded_state_dict(model.state_dict(), seed=rec["weight_seed"]), strict=True)
+    model = model.to(DEV)
+    model.use_fused, model.native_features = fused, native_feats
+    with torch.no_grad():
+        out = model({k: v.to(DEV) for k, v in batch.items()})
+    if fused:
+        assert model._engine is not None
+    for k, want in rec["outputs"].items():
+        assert rel_err(out[k].cpu(), want) < tol, (path, k, rel_err(out[k].cpu(), want))

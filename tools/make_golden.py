@@ -35,6 +35,9 @@ CASES = [
     dict(name="stress_4level_d64_900q", config="kradar", batch=1,
          sizes={"camera_mono": (96, 160, 3), "radar_bev": (64, 48, 6), "radar_front": (37, 48, 6)},
          n_queries=(30, 30, 1), multi_scale=3, d_model=64),
+    # the two-view radar configuration (config/kradar_radar.json): V = 2 in the view reduction and the fused decoder
+    dict(name="radar_two_views", config="kradar_radar", batch=2,
+         sizes={"radar_bev": (64, 107, 6), "radar_front": (37, 107, 6)}, n_queries=None),
 ]
 
 
