@@ -48,7 +48,11 @@ def parse():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=8, help="frames per GPU per step")
-    ap.add_argument("--cpu-sample", type=int, default=1, help="frames per CPU-baseline forward")
+    ap.add_argument("--cpu-sample", type=int, default=0,
+                    help="frames per CPU forward of the reference arm (0 = --batch, the GPU arm's batch size)")
+    ap.add_argument("--no-train", action="store_true", help="skip the `train` object (BASELINE config 4 step) of the default run")
+    ap.add_argument("--no-library-baseline", action="store_true", help="skip `gpu_library_baseline` (reference model through torch+cuDNN)")
+    ap.add_argument("--train-steps", type=int, default=10, help="timed steps of the `train` object")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--small", action="store_true", help="debug: tiny inputs (NOT a valid bench number)")
     ap.add_argument("--mode", default="infer", choices=["infer", "train"],
@@ -129,23 +133,53 @@ def build_case(args):
     return cfg, sizes
 
 
-def cpu_forward_fps(cfg, sizes, sd, frames, reps, seed=1234):
-    """Frames/s of the CPU oracle port of the reference forward (all host threads torch will use)."""
-    from dpft_b200 import synthetic
+def reference_package():
+    """The UNMODIFIED reference package installed by __graft_entry__.build() into the git-ignored baseline/_ref (it travels to
+    the GPU box; /root/reference does not exist there and is never read here).  Returns (dprt.models module or None, note)."""
+    os.environ["DPFT_REFERENCE_SRC"] = os.path.join(ROOT, "baseline", "_ref")
+    tools = os.path.join(ROOT, "tools")
+    if tools not in sys.path:
+        sys.path.insert(0, tools)
+    try:
+        import reference_shim
+        if not reference_shim.available():
+            return None, "baseline/_ref is not installed (run __graft_entry__.build() where /root/reference exists)"
+        return reference_shim.import_reference_models(), "unmodified dprt package from baseline/_ref"
+    except Exception as e:  # noqa: BLE001 - reported in the JSON line, the port is timed instead
+        return None, f"reference import failed: {type(e).__name__}: {e}"
+
+
+def reference_forward_fn(cfg, sd):
+    """(callable batch -> outputs on the CPU, kind, note): the reference's own eval forward with the seeded weights when the
+    package is importable (kind "reference"; its one absent native op is served by oracle/msda.py on CPU tensors), else the
+    oracle port (kind "port")."""
+    ref_models, note = reference_package()
+    if ref_models is not None:
+        ref = ref_models.build("dprt", cfg).eval()
+        ref.load_state_dict(sd, strict=True)
+        return (lambda batch: ref(batch)), "reference", note
     from oracle import dprt_oracle
-    batch = synthetic.synthetic_batch(cfg, frames, seed=seed, sizes=sizes)
+    return (lambda batch: dprt_oracle.forward(sd, cfg, batch)), "port", note + "; oracle/dprt_oracle.py timed instead"
+
+
+def cpu_forward_fps(fwd, cfg, sizes, frames, reps, seed=1234, batch=None):
+    """Frames/s of the reference's CPU forward (all host threads torch will use); returns (fps, best seconds, outputs)."""
+    from dpft_b200 import synthetic
+    if batch is None:
+        batch = synthetic.synthetic_batch(cfg, frames, seed=seed, sizes=sizes)
     with torch.no_grad():
-        dprt_oracle.forward(sd, cfg, batch)                   # warm-up
+        out = fwd(batch)                                      # warm-up
         best = float("inf")
         for _ in range(reps):
             t = time.perf_counter()
-            dprt_oracle.forward(sd, cfg, batch)
+            out = fwd(batch)
             best = min(best, time.perf_counter() - t)
-    return frames / best, best
+    return frames / best, best, out
 
 
 def run_reference(args):
-    """--impl reference: the reference's CPU forward (oracle port) on the same workload, rank 0 only."""
+    """--impl reference: the reference's own CPU eval forward (dprt.models.build('dprt', cfg) from baseline/_ref) on the same
+    workload and batch size, all host threads, rank 0 only."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
@@ -153,29 +187,89 @@ def run_reference(args):
     cfg, sizes = build_case(args)
     torch.set_num_threads(os.cpu_count())
     sd = synthetic.seeded_state_dict(models.build("dprt", cfg).state_dict(), seed=1)
-    from oracle import dprt_oracle
-    frames = args.cpu_sample
+    fwd, kind, note = reference_forward_fn(cfg, sd)
+    frames = args.cpu_sample if args.cpu_sample > 0 else args.batch
     batch = synthetic.synthetic_batch(cfg, frames, seed=1234, sizes=sizes)
     times = []
+    budget = time.perf_counter() + 240.0                     # the whole run ends within a few minutes
     with torch.no_grad():
         for i in range(args.warmup + args.steps):
+            if i >= min(args.warmup, 2) and i < args.warmup:
+                continue                                     # a CPU forward needs no more than two warm-up passes
             t = time.perf_counter()
-            dprt_oracle.forward(sd, cfg, batch)
+            fwd(batch)
             if i >= args.warmup:
                 times.append(time.perf_counter() - t)
+            if times and time.perf_counter() > budget:
+                break
     total = sum(times)
     fps = frames * len(times) / total
     sample = (f"{frames} frame(s) per step of the same workload ({'REDUCED sizes: --small' if args.small else 'full sizes'}), "
-              f"{len(times)} timed steps")
+              f"{len(times)} timed steps of {args.steps} requested (240 s budget); {note}")
     line = {"impl": "reference", "metric": METRIC, "value": fps, "unit": UNIT, "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / len(times),
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "frames_per_step": frames, "sizes": {k: list(v) for k, v in sizes.items()},
-                       "valid": not args.small},
-            "cpu_baseline": {"value": fps, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
+            "config": {"workload": WORKLOAD, "frames_per_gpu": frames, "frames_per_step": frames,
+                       "sizes": {k: list(v) for k, v in sizes.items()}, "valid": not args.small},
+            "cpu_baseline": {"value": fps, "unit": UNIT, "cores": torch.get_num_threads(), "kind": kind,
                              "sample": sample, "host_cpus": os.cpu_count()},
             "e2e": {"value": fps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
+
+
+def parity_report(got, want, grid=None):
+    """Per output: max-norm error relative to max|want| (the tests' metric) AND per-element relative error
+    |got - want| / max(|want|, 1e-3 * max|want|) as median / 99th percentile / max.  `center` is dominated by the static
+    query grid (up to 72 m), so it is also reported as `center_refinement` = center - grid: the part the network computes."""
+    rep = {}
+    items = [(k, got[k].detach().float().cpu(), want[k].detach().float().cpu()) for k in want]
+    if grid is not None and "center" in want:
+        g = grid.detach().float().cpu()
+        items.append(("center_refinement", got["center"].detach().float().cpu() - g, want["center"].detach().float().cpu() - g))
+    for k, a, b in items:
+        d = (a - b).abs().flatten()
+        scale = b.abs().max().clamp_min(1e-30)
+        el = d / b.abs().flatten().clamp_min(1e-3 * float(scale))
+        rep[k] = {"max_norm_rel": float(d.max() / scale), "elem_rel_p50": float(el.median()),
+                  "elem_rel_p99": float(torch.quantile(el, 0.99)), "elem_rel_max": float(el.max()),
+                  "max_abs": float(d.max()), "max_abs_want": float(scale)}
+    return rep
+
+
+def gpu_library_baseline(cfg, sd, resident, dev, B, reps=30):
+    """The same-box GPU yardstick: the UNMODIFIED reference model on this B200 through torch + cuDNN in
+    PyTorch's default precision (fp32 with TF32 convolutions), its absent native op served by dpft_msda_forward through
+    the plugin boundary; timed the way the reference times itself (evaluation/evaluator.py:96-135: 10 warm-up forwards, one
+    CUDA-event pair + synchronize per repetition, mean)."""
+    ref_models, note = reference_package()
+    if ref_models is None:
+        return {"unavailable": note}, None
+    tf32 = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32)
+    ref = ref_models.build("dprt", cfg).eval()
+    ref.load_state_dict(sd, strict=True)
+    ref = ref.to(dev)
+    ts = []
+    with torch.no_grad():
+        for _ in range(10):
+            out = ref(resident)
+        torch.cuda.synchronize()
+        for _ in range(reps):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            out = ref(resident)
+            e1.record()
+            torch.cuda.synchronize()
+            ts.append(e0.elapsed_time(e1))
+    ms = statistics.mean(ts)
+    out = {k: v.float().cpu() for k, v in out.items()}
+    del ref
+    torch.cuda.empty_cache()
+    return {"value": B * 1e3 / ms, "unit": UNIT, "ms_per_step": ms, "ms_std": statistics.pstdev(ts), "frames_per_step": B,
+            "impl": "unmodified reference package on cuda:0: torch eager + cuDNN; deformable attention = dpft_msda_forward "
+                    "through the plugin boundary (the reference's own CUDA op is not in /root/reference)",
+            "precision": "f32 parameters, cudnn.allow_tf32=%s, matmul.allow_tf32=%s (PyTorch defaults)" % tf32,
+            "method": "reference evaluator.py:96-135: 10 warm-up forwards, %d repetitions, event pair + synchronize each, mean" % reps,
+            "source": note}, out
 
 
 def conv_roofline(model, resident, dev, tf_peak, peak_src):
@@ -326,50 +420,77 @@ def run_train(args, cfg, sizes, rank, world, dev):
         loss_fn = lambda out, _b: criterion.forward_padded(out, tgt, tgt_mask)[0]
         loss_name = "reference criterion (HungarianAnassigner + SetCriterion: focal + L1; dpft_b200/criterion.py), synthetic labels"
     # the whole step (zero -> fwd -> loss -> bwd + all-reduce -> AdamW) is one CUDA graph, replayed per step
-    train_step = GraphedTrainStep(model, bucket, opt, loss_fn, graph=graphed, warmup=3)
+    n_steps = args.steps if args.mode == "train" else args.train_steps
+    n_warm = max(args.warmup, 3) if args.mode == "train" else 3
 
-    def step():
-        return train_step(batch)
+    def time_steps(communicate):
+        """Captures the step (with or without the bucket's all-reduces inside it) and times n_steps replays on the device."""
+        bucket.communicate = communicate
+        ts = GraphedTrainStep(model, bucket, opt, loss_fn, graph=graphed, warmup=3)
+        for _ in range(n_warm):
+            ts(batch)
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        l0 = native.launches()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(n_steps):
+            loss = ts(batch)
+        e1.record()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        t = torch.tensor([e0.elapsed_time(e1) * 1e-3], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        launches = ts.native_launches_per_step * n_steps if graphed else native.launches() - l0
+        final = float(loss)
+        if world > 1:
+            # a captured graph holds NCCL kernels of this communicator: release it before the communicator goes away
+            dist.barrier()
+            torch.cuda.synchronize()
+        ts.release()
+        return float(t.item()), launches, final
 
-    for _ in range(max(args.warmup, 3)):
-        step()
+    secs, launches, final_loss = time_steps(True)
+    exposed = 0.0
+    secs_nocomm = None
     if world > 1:
-        dist.barrier()
-    torch.cuda.synchronize()
-    l0 = native.launches()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(args.steps):
-        loss = step()
-    e1.record()
+        # the same step with the six all-reduces left out of the graph: the difference is the exposed communication time
+        secs_nocomm, _, _ = time_steps(False)
+        bucket.communicate = True
+        exposed = 1e3 * (secs - secs_nocomm) / n_steps
+    result = {"metric": "train_frames_per_sec", "value": B * world * n_steps / secs, "frames_per_sec": B * world * n_steps / secs,
+              "unit": UNIT, "n_gpus": world, "steps": n_steps, "warmup": n_warm,
+              "ms_per_step": 1e3 * secs / n_steps, "higher_is_better": True, "scaling": "weak",
+              "vs_baseline": None,
+              "allreduce_ms_exposed": exposed,
+              "ms_per_step_without_allreduce": None if secs_nocomm is None else 1e3 * secs_nocomm / n_steps,
+              "bucket_bytes": bucket.bytes(), "bucket_chunks": bucket.n_chunks,
+              "collective": ("NCCL all-reduce (sum) of the flat fp32 gradient bucket in %d chunks, launched from post-accumulate hooks "
+                             "inside the captured step, averaged after the last one" % bucket.n_chunks) if world > 1 else "none at N=1",
+              "dtype": ("f16 activations / fp32 accumulate + master weights in the ResNet stages (native sm_100a training "
+                        "kernels); stem, FPN, decoder fp32 through torch") if args.dtype != "f32"
+                       else "f32 (torch TF32 convs allowed, as the reference's default)",
+              "data": "synthetic",
+              "config": {"workload": WORKLOAD.replace("eval forward", "training step (fwd+bwd+all-reduce+AdamW)"),
+                         "frames_per_gpu": B, "parallelism": f"dp{world}", "loss": loss_name,
+                         "gradient_bucket_bytes": bucket.bytes(), "bucket_chunks": bucket.n_chunks,
+                         "launch": "one CUDA graph per step" if graphed else "eager",
+                         "reference_loop": "src/dprt/training/trainer.py:99-160 (zero_grad -> model -> loss -> backward -> step)"},
+              "gpu_launches": launches, "final_loss": final_loss}
+    del model, opt, bucket
+    torch.cuda.empty_cache()
+    return result
+
+
+def finish_distributed(world):
     if world > 1:
-        dist.barrier()
-    torch.cuda.synchronize()
-    t = torch.tensor([e0.elapsed_time(e1) * 1e-3], device=dev, dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    if rank == 0:
-        secs = float(t.item())
-        print(json.dumps({"metric": "train_frames_per_sec", "value": B * world * args.steps / secs, "unit": UNIT,
-                          "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
-                          "ms_per_step": 1e3 * secs / args.steps, "higher_is_better": True, "scaling": "weak",
-                          "vs_baseline": None,
-                          "dtype": ("f16 activations / fp32 accumulate + master weights in the ResNet stages (native sm_100a training "
-                                    "kernels); stem, FPN, decoder fp32 through torch") if args.dtype != "f32"
-                                   else "f32 (torch TF32 convs allowed, as the reference's default)",
-                          "data": "synthetic",
-                          "config": {"workload": WORKLOAD.replace("eval forward", "training step (fwd+bwd+all-reduce+AdamW)"),
-                                     "frames_per_gpu": B, "parallelism": f"dp{world}", "loss": loss_name,
-                                     "gradient_bucket_bytes": bucket.bytes(), "bucket_chunks": bucket.n_chunks,
-                                     "launch": "one CUDA graph per step" if graphed else "eager"},
-                          "gpu_launches": (train_step.native_launches_per_step * args.steps if graphed
-                                           else native.launches() - l0), "final_loss": float(loss)}), flush=True)
-    if world > 1:
-        # A captured graph holds NCCL kernels of this communicator: release it before the communicator goes away, and do not
-        # let a stuck teardown (seen once: destroy_process_group never returned after graph capture) keep the job alive.
+        import torch.distributed as dist
+        # do not let a stuck teardown (seen once: destroy_process_group never returned after graph capture) keep the job alive
         dist.barrier()
         torch.cuda.synchronize()
-        train_step.release()
         sys.stdout.flush()
         watchdog = threading.Timer(20.0, lambda: os._exit(0))
         watchdog.daemon = True
@@ -397,7 +518,10 @@ def main():
     from dpft_b200 import models, native, synthetic
     cfg, sizes = build_case(args)
     if args.mode == "train":
-        run_train(args, cfg, sizes, rank, world, dev)
+        result = run_train(args, cfg, sizes, rank, world, dev)
+        if rank == 0:
+            print(json.dumps(result), flush=True)
+        finish_distributed(world)
         return
     model = models.build("dprt", cfg).eval()
     sd = synthetic.seeded_state_dict(model.state_dict(), seed=1)
@@ -502,12 +626,18 @@ def main():
         clocks = sampler.stop()
     t_seq_e2e = timed(step_e2e, args.steps, 2)
     t_res, t_e2e = t_seq, t_seq_e2e
+    sustained = None
     if pipelined:
         if rank == 0:
             sampler.start()
         l0 = native.launches()
         t_res = timed_stream([resident, resident2], args.steps, max(args.warmup, 3), d2h=False)
         launches = native.launches() - l0
+        # the same loop held for >= 2 s so that clocks, power and throttle reasons are sampled under sustained load (the K timed
+        # steps above last ~0.1 s at the driver's --steps 20); reported beside `value`, never instead of it
+        n_sus = max(args.steps, int(2.0 / max(t_res / args.steps, 1e-4)) + 1)
+        t_sus = timed_stream([resident, resident2], n_sus, 0, d2h=False)
+        sustained = {"steps": n_sus, "ms_per_step": 1e3 * t_sus / n_sus, "value": B * world * n_sus / t_sus, "seconds": t_sus}
         clocks = sampler.stop() if rank == 0 else None
         t_e2e = timed_stream([host, host2], args.steps, max(args.warmup, 3), d2h=True)
     elif rank != 0:
@@ -538,6 +668,14 @@ def main():
             del pyr
         if roof is None:
             roof = roof_msda
+        else:
+            # the same FLOPs against the time of one step in the execution mode `value` is measured in (pipelined graphs,
+            # views on forked streams): the step also holds the stem, FPN and decoder kernels, so this is a LOWER bound
+            # on the convolutions' in-step rate, where `frac` (launch by launch, eager, serial) is the isolation figure
+            step_s = t_res / args.steps
+            roof["in_step"] = {"ms_per_step": 1e3 * step_s, "achieved_lower_bound": roof["algorithmic_flops_per_step"] / step_s / 1e12,
+                               "frac_lower_bound": roof["algorithmic_flops_per_step"] / step_s / 1e12 / tf_peak,
+                               "mode": "same as `value`"}
         torch.cuda.empty_cache()
         roof_msda["stress_config5"] = msda_stress(dev, hbm_peak) if world == 1 and not args.small else None
         line = {"metric": METRIC, "value": frames / t_res, "unit": UNIT, "n_gpus": world, "steps": args.steps,
@@ -555,20 +693,52 @@ def main():
                 "roofline": roof, "roofline_msda": roof_msda, "clocks": clocks,
                 "e2e": {"value": frames / t_e2e, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes,
                         "d2h_bytes_per_step": d2h_bytes, "ms_per_step": 1e3 * t_e2e / args.steps},
-                "gpu_launches": launches, "e2e_feeder": e2e_feeder,
+                "gpu_launches": launches, "e2e_feeder": e2e_feeder, "sustained": sustained,
                 "sequential": {"value": frames / t_seq, "ms_per_step": 1e3 * t_seq / args.steps, "e2e_value": frames / t_seq_e2e,
                                "note": "one forward at a time, per-step CUDA events, L2 flushed between steps"}}
         if world == 1 and not args.no_cpu_baseline:
+            # The reference's own CPU eval forward (baseline/_ref) on frames of the very batch the GPU just ran: the timing is
+            # `cpu_baseline`, its outputs are the yardstick of `parity`.  Bounded: 1 + 2 forwards of one frame, 1 + 1 of all B.
             torch.set_num_threads(os.cpu_count())
-            fps, secs = cpu_forward_fps(cfg, sizes, sd, args.cpu_sample, reps=3)
-            line["cpu_baseline"] = {"value": fps, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
-                                    "host_cpus": os.cpu_count(),
-                                    "sample": f"{args.cpu_sample} frame(s) of the same workload, best of 3 after 1 warm-up "
-                                              f"({secs:.2f} s per forward)"}
+            fwd, kind, note = reference_forward_fn(cfg, sd)
+            host_cpu = {k: v.clone() for k, v in host.items()}              # un-pinned copies for the CPU forward
+            one = {k: v[:1] for k, v in host_cpu.items()}
+            fps1, secs1, _ = cpu_forward_fps(fwd, cfg, sizes, 1, reps=2, batch=one)
+            fpsB, secsB, want = cpu_forward_fps(fwd, cfg, sizes, B, reps=1, batch=host_cpu)
+            best = max(fps1, fpsB)
+            line["cpu_baseline"] = {"value": best, "unit": UNIT, "cores": torch.get_num_threads(), "kind": kind,
+                                    "host_cpus": os.cpu_count(), "value_bs1": fps1, "value_bs%d" % B: fpsB,
+                                    "sample": f"frames of the timed batch itself: 1 frame best of 2 after 1 warm-up ({secs1:.2f} s per forward) "
+                                              f"and all {B} frames once after 1 warm-up ({secsB:.2f} s per forward); value = the faster; {note}"}
+            with torch.no_grad():
+                model.use_cuda_graph = True
+                got = {k: v.float().cpu() for k, v in model(resident).items()}
+            grid = model.querent.grid(torch.float32, dev).cpu()
+            line["parity"] = {"against": f"{kind}: the CPU forward above on all {B} frames of the timed batch (same seeded weights)",
+                              "arithmetic": args.dtype, "tolerance": 1e-2 if args.dtype != "f32" else 1e-3,
+                              "outputs": parity_report(got, want, grid)}
+            line["parity"]["max_norm_rel_worst"] = max(v["max_norm_rel"] for k, v in line["parity"]["outputs"].items()
+                                                       if k != "center_refinement")
+            line["parity"]["ok"] = line["parity"]["max_norm_rel_worst"] <= line["parity"]["tolerance"]
+        if world == 1 and not args.no_library_baseline and not args.small:
+            lib, lib_out = gpu_library_baseline(cfg, sd, resident, dev, B)
+            line["gpu_library_baseline"] = lib
+            if lib_out is not None:
+                with torch.no_grad():
+                    got = {k: v.float().cpu() for k, v in model(resident).items()}
+                lib["parity_of_this_repo_against_it"] = {k: v["max_norm_rel"] for k, v in
+                                                         parity_report(got, lib_out, model.querent.grid(torch.float32, dev).cpu()).items()}
+                lib["speedup_of_this_repo"] = line["sequential"]["value"] / lib["value"]
+    # BASELINE config 4 (north_star's only collective): the data-parallel training step, timed in the same run on every rank
+    train = None
+    if not args.no_train and not args.small:
+        del model
+        torch.cuda.empty_cache()
+        train = run_train(args, cfg, sizes, rank, world, dev)
+    if rank == 0:
+        line["train"] = train
         print(json.dumps(line), flush=True)
-    if world > 1:
-        torch.distributed.barrier()
-        torch.distributed.destroy_process_group()
+    finish_distributed(world)
 
 
 if __name__ == "__main__":

@@ -544,8 +544,8 @@ decoder_head_kernel(const HeadParams prm) {
     }
 }
 
-// EXPERIMENTAL (reduction | DPFT_HEAD_LANES16, or DPFT_HEAD_LANES=16 in the environment; off by default until it has run on a
-// B200): the same reduction + head with SIXTEEN lanes per query instead of one thread per query.  decoder_head_kernel is a
+// Default since round 2 (bit-identical to decoder_head_kernel on B200: tests/test_decoder_head16_gpu.py; DPFT_HEAD_LANES=1 in the
+// environment selects the one-thread-per-query kernel for A/B): the same reduction + head with SIXTEEN lanes per query instead of one thread per query.  decoder_head_kernel is a
 // serial chain of ~3000 instructions per thread on 19 CTAs (B*N = 2400 threads) at the end of every decoder iteration:
 // 19 us of pure latency, four times per forward.  Here lane o of a query owns output channel o of every layer (one dot16
 // per layer instead of sixteen), the 16-vectors go through a padded shared-memory row exactly as in decoder_layer_kernel,
@@ -699,10 +699,10 @@ extern "C" int dpft_decoder_head_forward(const float* views, const float* weight
                                          long long center_batch_stride, float* query_out, float* center_out, float* size_out,
                                          float* angle_out, float* class_out, int B, int V, int N, int n_cls, int reduction,
                                          int weight_floats, void* stream) {
-    // EXPERIMENTAL kernel selection: reduction | DPFT_HEAD_LANES16 (tests) or DPFT_HEAD_LANES=16 in the environment
-    static const int env_lanes = [] { const char* e = getenv("DPFT_HEAD_LANES"); return e ? atoi(e) : 1; }();
-    const bool lanes16 = (reduction & DPFT_HEAD_LANES16) != 0 || env_lanes == 16;
-    reduction &= ~DPFT_HEAD_LANES16;
+    // kernel selection: sixteen lanes per query unless DPFT_HEAD_LANES=1 (reduction | DPFT_HEAD_LANES16 forces it: tests)
+    static const int env_lanes = [] { const char* e = getenv("DPFT_HEAD_LANES"); return e ? atoi(e) : 16; }();
+    const bool lanes16 = (reduction & DPFT_HEAD_LANES16) != 0 || (env_lanes == 16 && (reduction & DPFT_HEAD_LANES1) == 0);
+    reduction &= ~(DPFT_HEAD_LANES16 | DPFT_HEAD_LANES1);
     DPFT_REQUIRE(reduction >= 0 && reduction <= 2, "decoder_head: reduction=%d (0 linear, 1 mean, 2 max)", reduction);
     DPFT_REQUIRE(views && weights && center_in && query_out && center_out, "decoder_head: null pointer");
     DPFT_REQUIRE(!size_out == !angle_out && !size_out == !class_out, "decoder_head: size/angle/class outputs go together");

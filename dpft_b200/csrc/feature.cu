@@ -470,8 +470,9 @@ fpn_output_tc_kernel(const FpnOutParams prm) {
 
 
 // ----------------------------------------------------------- FPN output, raw level: column-owning tile builder (v2)
-// EXPERIMENTAL (DPFT_FPN_BUILD=2 / impl 3; parity-checked on the CPU against an emulation of the index maps only — the
-// default stays fpn_output_tc_kernel until it is validated on a B200).  Same GEMM, same shared-memory operand image and
+// Default raw-level builder since round 2 (impl 3; DPFT_FPN_BUILD=1 selects fpn_output_tc_kernel for A/B): validated on B200
+// (tests/test_features_gpu.py column-builder cases + every whole-model golden case), bench step 4.841 -> 4.802 ms
+// (profiles/r02_ab_validated_paths.txt).  Same GEMM, same shared-memory operand image and
 // the same epilogue as fpn_output_tc_kernel<CIN>; only the construction of the inner halo tile differs.  ncu on the
 // 8x720x1280 camera level (gpurun_out/fpn_out_cam.raw.csv): 102.7 M warp instructions, issue slots 39 % active, two CTAs
 // per SM (96 registers) -> 243 us for 324 MB, i.e. the kernel is bound by the builders' instruction stream (~230 per halo
@@ -1187,9 +1188,9 @@ extern "C" int dpft_fpn_output_forward(const float* inner, const float* raw, int
         DPFT_REQUIRE(raw_channels == 3 || raw_channels == 6, "fpn_output: raw_channels=%d (3 or 6 supported)", raw_channels);
     }
     DPFT_REQUIRE(impl < 2 || w_packed, "fpn_output: the tensor-core kernel needs the packed weights (dpft_fpn_pack_weights)");
-    // EXPERIMENTAL raw-level tile builder (fpn_output_tc2_kernel): impl 3, or DPFT_FPN_BUILD=2 in the environment for the
-    // automatic choice; off by default until validated on a B200
-    static const int build_mode = [] { const char* e = getenv("DPFT_FPN_BUILD"); return e ? atoi(e) : 1; }();
+    // raw-level tile builder: the column-owning fpn_output_tc2_kernel where eligible (impl 3 forces it, DPFT_FPN_BUILD=1 in the
+    // environment keeps the automatic choice on fpn_output_tc_kernel for A/B timing)
+    static const int build_mode = [] { const char* e = getenv("DPFT_FPN_BUILD"); return e ? atoi(e) : 2; }();
     const bool column_builder = !inner && fpn_column_builder_eligible(H, W, Hc, Wc, coarse != nullptr) && ((uintptr_t)lat_b & 15) == 0 &&
                                 (impl == 3 || (impl == 0 && build_mode == 2 && W >= 96 && w_packed));
     DPFT_REQUIRE(impl != 3 || column_builder, "fpn_output: impl 3 needs the raw level with a coarser map of <= 1/%d x the size",

@@ -62,6 +62,7 @@ class GradientBucket:
     def __init__(self, model: nn.Module, n_chunks: int = 4, group=None, average: bool = True):
         self.group = group
         self.average = average
+        self.communicate = True          # False: skip the all-reduces (bench.py times the step with and without them)
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         skip = set(unused_parameter_names(model))
         named = [(n, p) for n, p in model.named_parameters() if p.requires_grad and n not in skip]
@@ -117,7 +118,7 @@ class GradientBucket:
         return hook
 
     def _launch(self, chunk: int) -> None:
-        if self.world == 1 or self._handles[chunk] is not None:
+        if self.world == 1 or not self.communicate or self._handles[chunk] is not None:
             return
         a, b = self.chunk_bounds[chunk]
         self._handles[chunk] = dist.all_reduce(self.flat[a:b], op=dist.ReduceOp.SUM, group=self.group, async_op=True)

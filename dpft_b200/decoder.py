@@ -68,6 +68,7 @@ def pack_layer(layer) -> torch.Tensor:
 
 
 HEAD_LANES16 = 0x100      # include/dpft_b200.h: DPFT_HEAD_LANES16
+HEAD_LANES1 = 0x200       # include/dpft_b200.h: DPFT_HEAD_LANES1
 
 
 def pack_head(reduction_layer, head, reduction: str) -> torch.Tensor:
@@ -113,11 +114,12 @@ def layer_forward(views: Sequence[DecoderView], query: torch.Tensor, pos: torch.
 
 def head_forward(views: torch.Tensor, weights: torch.Tensor, center_in: torch.Tensor, query_out: torch.Tensor,
                  center_out: torch.Tensor, size_out, angle_out, class_out, B: int, V: int, N: int, n_cls: int,
-                 reduction: int, lanes16: bool = False) -> None:
-    """``lanes16``: the experimental sixteen-lanes-per-query kernel (DPFT_HEAD_LANES16 in include/dpft_b200.h)."""
+                 reduction: int, lanes16: Optional[bool] = None) -> None:
+    """``lanes16``: None = the library's default kernel; True / False force the sixteen-lanes-per-query / one-thread-per-query
+    kernel (DPFT_HEAD_LANES16 / DPFT_HEAD_LANES1 in include/dpft_b200.h; bit-identical results)."""
     lib = native.load_library()
-    if lanes16:
-        reduction |= HEAD_LANES16
+    if lanes16 is not None:
+        reduction |= HEAD_LANES16 if lanes16 else HEAD_LANES1
     cs = 0 if center_in.dim() == 2 else N * 3
     st = lib.dpft_decoder_head_forward(native.ptr(views), native.ptr(weights), native.ptr(center_in), cs,
                                        native.ptr(query_out), native.ptr(center_out), native.ptr(size_out),

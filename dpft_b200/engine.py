@@ -300,7 +300,13 @@ class _CapturedForward:
         main = torch.cuda.current_stream(self.device)
         if copy_stream is None:
             for k in self.keys:
-                self.static_in[k].copy_(batch[k], non_blocking=True)
+                src = batch[k]
+                self.static_in[k].copy_(src, non_blocking=True)
+                # `main` may be a pipeline slot's private stream while `src` was allocated on the caller's (or the feeder's copy)
+                # stream: tell the caching allocator that this stream still reads it, or the block can be handed out again while
+                # the copy is queued behind the slot's previous replay
+                if src.is_cuda:
+                    src.record_stream(main)
         else:
             copy_stream.wait_event(self.consumed)
             with torch.cuda.stream(copy_stream):

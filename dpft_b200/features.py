@@ -99,8 +99,9 @@ def fpn_output_forward(pyramid: torch.Tensor, start: int, H: int, W: int, w: tor
     native.count_launch()
 
 
-# EXPERIMENTAL (DPFT_FPN_FORK=1; written without GPU access, off by default): see NativeView._pyramid_forked
-_FPN_FORK = os.environ.get("DPFT_FPN_FORK") == "1"
+# Forked FPN output launches (NativeView._pyramid_forked): default since round 2 (bit-identical on B200, bench step
+# 4.841 -> 4.775 ms, profiles/r02_ab_validated_paths.txt); DPFT_FPN_FORK=0 keeps everything on one stream for A/B timing
+_FPN_FORK = os.environ.get("DPFT_FPN_FORK", "1") == "1"
 
 
 class NativeView:

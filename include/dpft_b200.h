@@ -197,10 +197,12 @@ DPFT_API int dpft_decoder_layer_forward(const dpft_decoder_view* views, int V, c
  * refinement center += previous centre at :273).  size/angle/class outputs may be NULL on intermediate iterations
  * (only the centre feeds the next iteration, mpfusion.py:732-743).
  *   views (B, V, N, 16); weights packed by dpft_b200/decoder.py::pack_head; outputs (B, N, 16|3|3|2|n_cls) f32.
- * reduction | DPFT_HEAD_LANES16 selects an EXPERIMENTAL kernel with sixteen lanes per query (bit-identical results by
- * construction; not yet validated on a B200, so never the default).
+ * Two kernels with bit-identical results (tests/test_decoder_head16_gpu.py): sixteen lanes per query (the default) and one
+ * thread per query; reduction | DPFT_HEAD_LANES16 / reduction | DPFT_HEAD_LANES1 force one of them (DPFT_HEAD_LANES=1 in
+ * the environment changes the default for A/B timing).
  */
 #define DPFT_HEAD_LANES16 0x100
+#define DPFT_HEAD_LANES1 0x200
 DPFT_API int dpft_decoder_head_forward(const float* views, const float* weights, const float* center_in,
                                        long long center_batch_stride, float* query_out, float* center_out,
                                        float* size_out, float* angle_out, float* class_out, int B, int V, int N,

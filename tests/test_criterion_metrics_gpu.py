@@ -1,15 +1,12 @@
 """dpft_b200.criterion / dpft_b200.metrics on cuda tensors against the fixtures of the unmodified reference (the CPU tests
-hold the same modules to them on the host).  Written after round 1's GPU budget was spent: DPFT_EXPERIMENTAL=1 to run."""
-import os
-
+hold the same modules to them on the host).  Green on B200 since round 2 (gpurun call r02_call01)."""
 import pytest
 import torch
 
 from conftest import load_golden
 from dpft_b200 import criterion, metrics
 
-pytestmark = [pytest.mark.gpu,
-              pytest.mark.skipif(os.environ.get("DPFT_EXPERIMENTAL") != "1", reason="not yet validated on a B200: DPFT_EXPERIMENTAL=1")]
+pytestmark = [pytest.mark.gpu]
 DEV = "cuda:0"
 
 

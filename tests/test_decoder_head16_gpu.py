@@ -1,15 +1,12 @@
 """decoder_head16_kernel (sixteen lanes per query; dpft_decoder_head_forward with DPFT_HEAD_LANES16) against the validated
 one-thread-per-query decoder_head_kernel: every output is accumulated in the same order, so the results must be
-BIT-IDENTICAL.  Written after round 1's GPU budget was spent: opt in with DPFT_EXPERIMENTAL=1 until it has run on a B200."""
-import os
-
+BIT-IDENTICAL (green on B200 since round 2, gpurun call r02_call01; the sixteen-lane kernel is the default now)."""
 import pytest
 import torch
 
 from dpft_b200 import decoder as dec
 
-pytestmark = [pytest.mark.gpu,
-              pytest.mark.skipif(os.environ.get("DPFT_EXPERIMENTAL") != "1", reason="not yet validated on a B200: DPFT_EXPERIMENTAL=1")]
+pytestmark = [pytest.mark.gpu]
 DEV = "cuda:0"
 
 

@@ -146,11 +146,6 @@ def test_fpn_output_tensor_core_matches_cuda_core(cin, H, W):
 
 
 
-EXPERIMENTAL = __import__("os").environ.get("DPFT_EXPERIMENTAL") == "1"
-
-
-@pytest.mark.skipif(not EXPERIMENTAL, reason="kernel written without GPU access (no budget left in round 1): opt in with "
-                                             "DPFT_EXPERIMENTAL=1 until it has been validated on a B200")
 @pytest.mark.parametrize("cin,H,W", [(3, 45, 300), (6, 17, 129), (6, 37, 107), (3, 90, 160), (6, 64, 256)])
 def test_fpn_output_column_builder_matches_cuda_core(cin, H, W):
     """impl 3 (fpn_output_tc2_kernel: column-owning tile builder, staged coarse patch) against the fp32 CUDA-core kernel

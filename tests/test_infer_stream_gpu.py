@@ -66,7 +66,6 @@ def test_stream_falls_back_to_sequential_without_the_graph():
             assert torch.equal(a[k], b[k])
 
 
-@pytest.mark.skipif(__import__("os").environ.get("DPFT_EXPERIMENTAL") != "1", reason="not yet validated on a B200: DPFT_EXPERIMENTAL=1")
 def test_feeder_on_the_gpu_matches_the_cpu_and_feeds_the_stream():
     """dpft_b200.feeder on cuda (uint8 frames uploaded on the copy stream, arithmetic on the GPU) against the same feeder on
     the CPU (bit-exact against the reference dataset methods, tests/test_feeder.py), then DPRT.infer_stream fed by it."""
@@ -81,7 +80,9 @@ def test_feeder_on_the_gpu_matches_the_cpu_and_feeds_the_stream():
         want = cpu.prepare(raw)
         for k, w in want.items():
             assert got[k].shape == w.shape and got[k].dtype == w.dtype, k
-            tol = 1e-3 if k == "camera_mono" else 0.0          # the library resize differs in rounding between CPU and CUDA
+            # the library resize differs in rounding between CPU and CUDA; the radar power scaling (log10 / divisions) differs
+            # by one fp32 ulp at the 255 end of the range between the CPU and the CUDA math libraries (measured: 1.5e-5)
+            tol = 1e-3 if k == "camera_mono" else 2 * 2.0 ** -23
             assert float((got[k].cpu().double() - w.double()).abs().max()) <= tol * 255, k
     model = models.build("dprt", cfg).eval()
     model.load_state_dict(synthetic.seeded_state_dict(model.state_dict(), seed=3))

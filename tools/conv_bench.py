@@ -74,10 +74,42 @@ for name, (H, W, Cin, Cout, R, stride, pad, res) in LAYERS.items():
             e1.record()
             e1.synchronize()
             (ts_cold if cold else ts_warm).append(e0.elapsed_time(e1) * 1e3)
+    # the library on the same box: cuDNN through torch, f16 channels_last, bias fused into the conv call;
+    # `cudnn_chain` adds what eval-mode torch would run after it for this layer (residual add, ReLU) as separate kernels
+    torch.backends.cudnn.benchmark = True
+    xc = x.permute(0, 3, 1, 2)                                  # NHWC storage seen as NCHW = channels_last
+    wc = w.permute(0, 3, 1, 2).contiguous(memory_format=torch.channels_last)
+    bc = bias.half()
+    rc = r.permute(0, 3, 1, 2) if res else None
+
+    def lib_conv():
+        return torch.nn.functional.conv2d(xc, wc, bc, stride, pad)
+
+    def lib_chain():
+        y = torch.nn.functional.conv2d(xc, wc, bc, stride, pad)
+        if res:
+            y += rc
+        return torch.relu_(y)
+
+    lib = {}
+    for nm, fn in (("cudnn_conv", lib_conv), ("cudnn_chain", lib_chain)):
+        for _ in range(3):
+            fn()
+        tl = []
+        for _ in range(5):
+            flush.zero_()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            fn()
+            e1.record()
+            e1.synchronize()
+            tl.append(e0.elapsed_time(e1) * 1e3)
+        lib[nm + "_us_cold"] = round(min(tl), 1)
     M = B * P * Q
     flops = 2.0 * M * Cout * R * R * Cin
     bytes_ = 2.0 * (B * H * W * Cin + Cout * R * R * Cin + M * Cout * (2 if res else 1))
     tc, tw = min(ts_cold), min(ts_warm)
     print(json.dumps({"layer": name, "M": M, "N": Cout, "K": R * R * Cin, "us_cold": round(tc, 1), "us_warm": round(tw, 1),
                       "tflops_cold": round(flops / tc / 1e6, 1), "gbps_cold": round(bytes_ / tc / 1e3, 1),
-                      "tflops_warm": round(flops / tw / 1e6, 1), "MB": round(bytes_ / 1e6, 1)}), flush=True)
+                      "tflops_warm": round(flops / tw / 1e6, 1), "MB": round(bytes_ / 1e6, 1), **lib,
+                      "speedup_vs_cudnn_chain": round(lib["cudnn_chain_us_cold"] / tc, 2)}), flush=True)

@@ -1,18 +1,37 @@
-"""Imports the UNMODIFIED reference package from /root/reference in the build container.
+"""Imports the UNMODIFIED reference package: from /root/reference in the build container, or from the copy that
+``__graft_entry__.build()`` installs into the git-ignored ``baseline/_ref`` (it travels to the GPU box with gpurun).
 
-The reference's one compiled dependency (``MultiScaleDeformableAttention``) is absent, so a stand-in module
-backed by the CPU oracle (oracle/msda.py) is registered under that name first.  Used only by
-tools/make_golden.py and the in-container parity tests; /root/reference does not exist on the GPU box.
+The reference's one compiled dependency (``MultiScaleDeformableAttention``) is absent from both, so a stand-in module is
+registered under that name first: CUDA tensors go to this repo's kernels (``dpft_b200.msda``, the plugin boundary of
+INTEGRATION.md §1), CPU tensors to the CPU oracle (oracle/msda.py).  Used by tools/make_golden*.py, the parity tests and
+bench.py's reference / library-baseline legs — never by the product path.
 """
 import os
 import sys
 import types
 
-REFERENCE_SRC = "/root/reference/src"
+_ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+_CANDIDATES = ("/root/reference/src", os.path.join(_ROOT, "baseline", "_ref"))
+
+
+def _find_src():
+    override = os.environ.get("DPFT_REFERENCE_SRC")          # tests: force the installed copy in the build container
+    for c in ((override,) if override else _CANDIDATES):
+        if os.path.isfile(os.path.join(c, "dprt", "models", "__init__.py")):
+            return c
+    return _CANDIDATES[0]
+
+
+REFERENCE_SRC = _find_src()
 
 
 def available() -> bool:
-    return os.path.isdir(os.path.join(REFERENCE_SRC, "dprt"))
+    return os.path.isfile(os.path.join(REFERENCE_SRC, "dprt", "models", "__init__.py"))
+
+
+def source() -> str:
+    """Which copy of the reference package gets imported (for bench.py's `cpu_baseline.sample`)."""
+    return REFERENCE_SRC
 
 
 def import_reference_models():
@@ -22,9 +41,15 @@ def import_reference_models():
     shim = types.ModuleType("MultiScaleDeformableAttention")
 
     def fwd(value, shapes, lsi, loc, attn, im2col_step):
+        if value.is_cuda:                    # the native-op plugin boundary: this repo's kernels under the unmodified reference
+            from dpft_b200 import msda
+            return msda.ms_deform_attn_forward(value, shapes, lsi, loc, attn, im2col_step)
         return O.msda_forward_torch(value, shapes, loc, attn)
 
     def bwd(value, shapes, lsi, loc, attn, grad_out, im2col_step):
+        if value.is_cuda:
+            from dpft_b200 import msda
+            return msda.ms_deform_attn_backward(value, shapes, lsi, loc, attn, grad_out, im2col_step)
         return O.msda_backward_torch(value, shapes, loc, attn, grad_out)
 
     shim.ms_deform_attn_forward = fwd
