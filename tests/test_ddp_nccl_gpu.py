@@ -1,0 +1,102 @@
+"""Two-GPU NCCL test of the flat gradient bucket (dpft_b200/ddp.py): one process per GPU, the eval-mode model on CUDA through
+the native deformable-attention forward/backward, two batch shards; the averaged per-rank gradients must equal the
+single-GPU gradients of the whole batch, with and without the all-reduces captured inside a CUDA graph of the step.
+Needs two visible GPUs (`gpurun --gpus 2`); on a one-GPU box it is skipped."""
+import os
+import socket
+import sys
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from conftest import ROOT
+
+pytestmark = pytest.mark.gpu
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _build(dev):
+    from dpft_b200 import configs, models, synthetic
+    cfg = synthetic.offline_config(configs.make_config("kradar_radar_front"), dropout=0.0)
+    model = models.build("dprt", cfg)
+    model.load_state_dict(synthetic.seeded_state_dict(model.state_dict(), seed=5))
+    model = model.to(dev).eval()        # BatchNorm on running statistics: samples are independent, so shards average exactly
+    for p in model.parameters():
+        p.requires_grad_(True)
+    batch = synthetic.synthetic_batch(cfg, 4, seed=6, sizes={"radar_front": (37, 40, 6)}, device=dev)
+    return model, batch
+
+
+def _loss(out):
+    return sum((v ** 2).mean() for v in out.values())
+
+
+def _worker(rank, world, port, result_path):
+    sys.path.insert(0, ROOT)
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    torch.cuda.set_device(rank)
+    dev = torch.device("cuda", rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    from dpft_b200 import ddp
+    model, batch = _build(dev)
+    if rank == 1:
+        with torch.no_grad():
+            for p in model.parameters():
+                p.add_(1.0)
+    ddp.broadcast_parameters(model, src=0)
+    bucket = ddp.GradientBucket(model, n_chunks=3)
+    shard = {k: v[rank * 2:(rank + 1) * 2].contiguous() for k, v in batch.items()}
+    _loss(model(shard)).backward()
+    bucket.finish()
+    torch.cuda.synchronize()
+    eager = bucket.flat.clone()
+    # the same step with the chunked all-reduces captured inside a CUDA graph (what GraphedTrainStep / bench.py replay)
+    side = torch.cuda.Stream(device=dev)
+    side.wait_stream(torch.cuda.current_stream(dev))
+    with torch.cuda.stream(side):
+        for _ in range(2):
+            bucket.zero()
+            _loss(model(shard)).backward()
+            bucket.finish()
+    torch.cuda.current_stream(dev).wait_stream(side)
+    torch.cuda.synchronize()
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph):
+        bucket.zero()
+        _loss(model(shard)).backward()
+        bucket.finish()
+    graph.replay()
+    torch.cuda.synchronize()
+    replayed = bucket.flat.clone()
+    if rank == 0:
+        torch.save({"eager": {n: eager[a:b].view_as(p).cpu() for n, p, (a, b) in zip(bucket.names, bucket.params, bucket.offsets)},
+                    "graph_max_diff": float((replayed - eager).abs().max()), "scale": float(eager.abs().max())}, result_path)
+    dist.barrier()
+    torch.cuda.synchronize()
+    del graph
+    dist.destroy_process_group()
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs (gpurun --gpus 2)")
+def test_flat_bucket_nccl_allreduce_matches_full_batch(tmp_path):
+    from dpft_b200 import ddp
+    result = str(tmp_path / "grads.pt")
+    mp.spawn(_worker, args=(2, _free_port(), result), nprocs=2, join=True)
+    got = torch.load(result)
+    model, batch = _build(torch.device("cuda", 0))
+    _loss(model(batch)).backward()
+    want = {n: p.grad for n, p in model.named_parameters() if p.grad is not None}
+    assert set(got["eager"]) == set(want)
+    assert len(list(model.named_parameters())) - len(want) == 39 == len(ddp.unused_parameter_names(model))
+    for n, g in got["eager"].items():
+        w = want[n].cpu()
+        # fp32 sums in a different order (two half-batch means averaged vs one full-batch mean) + atomics in the op's backward
+        assert float((g - w).abs().max()) <= 2e-4 * max(float(w.abs().max()), 1e-6) + 1e-7, n
+    assert got["graph_max_diff"] <= 2e-4 * got["scale"], got["graph_max_diff"]
