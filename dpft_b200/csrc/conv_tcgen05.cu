@@ -468,6 +468,238 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     }
 }
 
+// ---- weight-stationary variant for the 1x1 "expand" convolutions with a residual (conv3 of every Bottleneck) -------------
+// These layers have a short K (Cin = 64 .. 256) and a wide N (4 x Cin): per 128 x 256 output tile the generic kernel moves
+// A 128 x K, B 256 x K, the residual and the output, i.e. for K = 256 it re-reads 128 KB of weights for 64 KB of output, and
+// on the 900-tile stage-3 layer the sum of operand + residual + output traffic (~290 MB in 34 us) runs at the chip's L2
+// throughput, not at the tensor pipe (26 % active) or at HBM.  Here a CTA keeps its n-tile for its whole life (the grid is a
+// multiple of n_tiles), loads that weight slice ONCE into shared memory and streams only A; the epilogue works IN PLACE on a
+// ring of [32 x 64] buffers per TMEM lane quadrant: the residual sub-tile lands in a buffer by TMA, the warps add accumulator
+// + bias, apply the ReLU and overwrite it with the packed outputs, the TMA store reads it, and the same thread refills it
+// with the residual NB - 1 items ahead.  One 32*EG-thread barrier per item instead of two; the bias is staged once per CTA.
+template <int BLOCK_N, int KB, int A_STAGES, int NB> struct WsLayout {
+    static constexpr int kABytes = BLOCK_M * BLOCK_K * 2;
+    static constexpr int kBBytes = BLOCK_N * BLOCK_K * 2;
+    static constexpr int kBResident = KB * kBBytes;
+    static constexpr int kBufBytes = 4 * NB * EPI_BUF_BYTES;
+    static constexpr int kBiasBytes = BLOCK_N * 4;
+    static constexpr int kBarrierBytes = (1 + 2 * A_STAGES + 4 + 4 * NB) * 8 + 16;
+    static constexpr int kTotal = kBResident + A_STAGES * kABytes + kBufBytes + kBiasBytes + kBarrierBytes;
+};
+
+template <int BLOCK_N, int KB, int A_STAGES, int NB, int EG>
+__global__ void __launch_bounds__(threads_for(EG), 1)
+conv_expand_ws_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+                      const __grid_constant__ CUtensorMap tmap_d, const __grid_constant__ CUtensorMap tmap_r,
+                      const ConvParams prm) {
+    using L = WsLayout<BLOCK_N, KB, A_STAGES, NB>;
+    extern __shared__ __align__(1024) uint8_t smem[];
+    if ((smem_u32(smem) & 1023u) != 0) __trap();
+    uint8_t* smem_b = smem;                                              // [KB][BLOCK_N x 64] resident weight slice
+    uint8_t* smem_a = smem + L::kBResident;                              // [A_STAGES][128 x 64]
+    uint8_t* smem_buf = smem_a + A_STAGES * L::kABytes;                  // [4 quadrants][NB][32 x 64]
+    float* smem_bias = reinterpret_cast<float*>(smem_buf + L::kBufBytes);
+    uint64_t* b_full = reinterpret_cast<uint64_t*>(smem_buf + L::kBufBytes + L::kBiasBytes);
+    uint64_t* full_bar = b_full + 1;
+    uint64_t* empty_bar = full_bar + A_STAGES;
+    uint64_t* tmem_full = empty_bar + A_STAGES;
+    uint64_t* tmem_empty = tmem_full + 2;
+    uint64_t* res_bar = tmem_empty + 2;                                  // [4 quadrants][NB]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(res_bar + 4 * NB);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    constexpr uint32_t kTmemCols = 2 * BLOCK_N;
+    const int cta_id = blockIdx.x, num_ctas = gridDim.x;                 // num_ctas % n_tiles == 0 (host): n_tile is fixed per CTA
+    const int n_tile = cta_id % prm.n_tiles;
+    const int num_tiles = prm.m_tiles * prm.n_tiles;
+
+    if (warp == 0 && elect_one()) {
+        prefetch_tmap(&tmap_a);
+        prefetch_tmap(&tmap_b);
+        prefetch_tmap(&tmap_d);
+        prefetch_tmap(&tmap_r);
+        mbar_init(b_full, 1);
+        for (int i = 0; i < A_STAGES; ++i) {
+            mbar_init(&full_bar[i], 1);
+            mbar_init(&empty_bar[i], 1);
+        }
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(&tmem_full[i], 1);
+            mbar_init(&tmem_empty[i], 4 * EG);
+        }
+        for (int i = 0; i < 4 * NB; ++i) mbar_init(&res_bar[i], 1);
+        fence_barrier_init();
+    } else if (warp == 1) {
+        tmem_alloc(tmem_slot, kTmemCols);
+    }
+    tcgen05_fence_before();
+    __syncthreads();
+    tcgen05_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+
+    if (warp == 0) {
+        // ===================================== TMA producer: weights once, then A =====================================
+        if (elect_one()) {
+            mbar_expect_tx(b_full, (uint32_t)(prm.kblocks * L::kBBytes));
+            for (int kb = 0; kb < prm.kblocks; ++kb)
+                tma_load_2d(&tmap_b, b_full, smem_b + kb * L::kBBytes, kb * BLOCK_K, n_tile * BLOCK_N);
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int tile = cta_id; tile < num_tiles; tile += num_ctas) {
+                const int m_tile = tile / prm.n_tiles;
+                for (int kb = 0; kb < prm.kblocks; ++kb) {
+                    mbar_wait(&empty_bar[stage], phase ^ 1);
+                    mbar_expect_tx(&full_bar[stage], L::kABytes);
+                    tma_load_2d(&tmap_a, &full_bar[stage], smem_a + stage * L::kABytes, kb * BLOCK_K, m_tile * BLOCK_M);
+                    if (++stage == A_STAGES) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ====================================== MMA issuer ======================================
+        const uint32_t idesc = tc::umma_idesc_16bit(BLOCK_M, BLOCK_N, prm.is_f16 != 0);
+        int stage = 0;
+        uint32_t phase = 0;
+        int acc = 0;
+        uint32_t acc_phase = 0;
+        mbar_wait(b_full, 0);
+        for (int tile = cta_id; tile < num_tiles; tile += num_ctas) {
+            mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+            tcgen05_fence_after();
+            const uint32_t tmem_d = tmem_base + acc * BLOCK_N;
+            for (int kb = 0; kb < prm.kblocks; ++kb) {
+                mbar_wait(&full_bar[stage], phase);
+                tcgen05_fence_after();
+                if (elect_one()) {
+                    const uint64_t adesc = umma_desc_sw128(smem_u32(smem_a + stage * L::kABytes));
+                    const uint64_t bdesc = umma_desc_sw128(smem_u32(smem_b + kb * L::kBBytes));
+#pragma unroll
+                    for (int k = 0; k < BLOCK_K / UMMA_K; ++k)
+                        umma_bf16(tmem_d, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) ? 1u : 0u);
+                    umma_commit(&empty_bar[stage]);
+                    if (kb == prm.kblocks - 1) umma_commit(&tmem_full[acc]);
+                }
+                __syncwarp();
+                if (++stage == A_STAGES) { stage = 0; phase ^= 1; }
+            }
+            if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+        }
+    } else {
+        // ======================================= epilogue (in place) =======================================
+        const int quad = warp & 3;
+        const int grp = (warp - 2) >> 2;
+        constexpr int WCOLS = EPI_COLS / EG;
+        constexpr int WCHUNKS = WCOLS / 8;
+        constexpr int kChunks = BLOCK_N / EPI_COLS;
+        uint8_t* my_buf = smem_buf + quad * NB * EPI_BUF_BYTES;
+        uint64_t* my_res_bar = res_bar + quad * NB;
+        const int my_tiles = cta_id < num_tiles ? (num_tiles - 1 - cta_id) / num_ctas + 1 : 0;
+        const int total_items = my_tiles * kChunks;
+        const bool issuer = grp == 0 && lane == 0;          // issues the stores AND the residual loads of its quadrant
+        auto quad_sync = [&]() { asm volatile("bar.sync %0, %1;" ::"r"(2 + quad), "n"(32 * EG) : "memory"); };
+        const int n0 = n_tile * BLOCK_N;
+
+        auto load_residual = [&](int item) {                // issuer only
+            if (item >= total_items) return;
+            const int m_tile = (cta_id + (item / kChunks) * num_ctas) / prm.n_tiles;
+            const int b = item % NB;
+            mbar_expect_tx(&my_res_bar[b], EPI_BUF_BYTES);
+            tma_load_2d(&tmap_r, &my_res_bar[b], my_buf + b * EPI_BUF_BYTES, n0 + (item % kChunks) * EPI_COLS,
+                        m_tile * BLOCK_M + quad * 32);
+        };
+        if (issuer) {
+#pragma unroll
+            for (int i = 0; i < NB; ++i) load_residual(i);
+        }
+        // the CTA's bias slice, once (n_tile never changes): every epilogue thread copies a part, all of them meet at barrier 1
+        for (int i = (warp - 2) * 32 + lane; i < BLOCK_N; i += 128 * EG) smem_bias[i] = __ldg(prm.bias + n0 + i);
+        asm volatile("bar.sync 1, %0;" ::"n"(128 * EG) : "memory");
+
+        int acc = 0;
+        uint32_t acc_phase = 0;
+        int item = 0;
+        const int sw = lane & 7;
+        for (int tile = cta_id; tile < num_tiles; tile += num_ctas) {
+            const int m_tile = tile / prm.n_tiles;
+            mbar_wait(&tmem_full[acc], acc_phase);
+            tcgen05_fence_after();
+#pragma unroll 1
+            for (int c = 0; c < kChunks; ++c, ++item) {
+                uint32_t v[WCOLS];
+                const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) +
+                                       (uint32_t)(acc * BLOCK_N + c * EPI_COLS + grp * WCOLS);
+                if constexpr (EG == 2) tmem_ld_32x32b_x32(taddr, v);
+                else tmem_ld_32x32b_x16(taddr, v);
+                tmem_ld_wait();
+                const int b = item % NB;
+                const float4* bias4 = reinterpret_cast<const float4*>(smem_bias + c * EPI_COLS + grp * WCOLS);
+                uint8_t* row = my_buf + b * EPI_BUF_BYTES + lane * 128;
+                mbar_wait(&my_res_bar[b], (uint32_t)((item / NB) & 1));      // the residual sub-tile has landed in buffer b
+#pragma unroll
+                for (int jj = 0; jj < WCHUNKS; ++jj) {
+                    const int j = grp * WCHUNKS + jj;
+                    const int phys = (j ^ sw) << 4;
+                    float f[8];
+                    const float4 b0 = bias4[2 * jj], b1 = bias4[2 * jj + 1];
+                    f[0] = __uint_as_float(v[8 * jj]) + b0.x;     f[1] = __uint_as_float(v[8 * jj + 1]) + b0.y;
+                    f[2] = __uint_as_float(v[8 * jj + 2]) + b0.z; f[3] = __uint_as_float(v[8 * jj + 3]) + b0.w;
+                    f[4] = __uint_as_float(v[8 * jj + 4]) + b1.x; f[5] = __uint_as_float(v[8 * jj + 5]) + b1.y;
+                    f[6] = __uint_as_float(v[8 * jj + 6]) + b1.z; f[7] = __uint_as_float(v[8 * jj + 7]) + b1.w;
+                    const uint4 rv = *reinterpret_cast<const uint4*>(row + phys);
+#pragma unroll
+                    for (int t = 0; t < 4; ++t) {
+                        const float2 rf = prm.is_f16 ? __half22float2(reinterpret_cast<const __half2*>(&rv)[t])
+                                                     : __bfloat1622float2(reinterpret_cast<const __nv_bfloat162*>(&rv)[t]);
+                        f[2 * t] += rf.x;
+                        f[2 * t + 1] += rf.y;
+                    }
+                    if (prm.relu) {
+#pragma unroll
+                        for (int t = 0; t < 8; ++t) f[t] = fmaxf(f[t], 0.0f);
+                    }
+                    uint4 ov;
+                    uint32_t* ow = reinterpret_cast<uint32_t*>(&ov);
+                    if (prm.is_f16) {
+#pragma unroll
+                        for (int t = 0; t < 4; ++t)
+                            asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(ow[t]) : "f"(f[2 * t + 1]), "f"(f[2 * t]));
+                    } else {
+#pragma unroll
+                        for (int t = 0; t < 4; ++t)
+                            asm("cvt.rn.satfinite.bf16x2.f32 %0, %1, %2;" : "=r"(ow[t]) : "f"(f[2 * t + 1]), "f"(f[2 * t]));
+                    }
+                    *reinterpret_cast<uint4*>(row + phys) = ov;      // same 16 bytes this thread just read: in place
+                }
+                fence_proxy_async();
+                quad_sync();                          // every warp of the quadrant has overwritten its columns of buffer b
+                if (issuer) {
+                    tma_store_2d(&tmap_d, my_buf + b * EPI_BUF_BYTES, n0 + c * EPI_COLS, m_tile * BLOCK_M + quad * 32);
+                    bulk_commit();
+                    if (item >= 1) {
+                        bulk_wait_read<1>();          // the store of item - 1 has read its buffer: refill it NB - 1 items ahead
+                        load_residual(item - 1 + NB);
+                    }
+                }
+            }
+            tcgen05_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+            if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+        }
+        if (issuer) bulk_wait_read<0>();
+    }
+
+    tcgen05_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tcgen05_fence_after();
+        tmem_dealloc(tmem_base, kTmemCols);
+    }
+}
+
 // ---- host side: tensor maps through the driver entry points (no link-time libcuda dependency) -----------------
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
@@ -565,6 +797,52 @@ int launch(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& td, 
     if (st) return st;
     DPFT_LAUNCH_CHECK("conv_gemm_kernel");
     return DPFT_OK;
+}
+
+template <int BLOCK_N, int KB, int A_STAGES, int NB, int EG = 4>
+int launch_ws(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& td, const CUtensorMap& tr, const ConvParams& prm,
+              cudaStream_t stream) {
+    using L = WsLayout<BLOCK_N, KB, A_STAGES, NB>;
+    static_assert(L::kTotal <= 232448, "shared memory budget of one CTA exceeded");
+    auto kern = conv_expand_ws_kernel<BLOCK_N, KB, A_STAGES, NB, EG>;
+    static bool configured = false;
+    if (!configured) {
+        int st = cuda_status(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kTotal),
+                             "cudaFuncSetAttribute(conv_expand_ws_kernel)");
+        if (st) return st;
+        configured = true;
+    }
+    const int tiles = prm.m_tiles * prm.n_tiles;
+    int grid = (g_sm_count / prm.n_tiles) * prm.n_tiles;      // a multiple of n_tiles: tile -> n_tile is constant per CTA
+    if (grid > tiles) grid = tiles;                           // (tiles is a multiple of n_tiles as well)
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(threads_for(EG));
+    cfg.dynamicSmemBytes = L::kTotal;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    int n_attr = 0;
+    if (use_pdl()) {
+        attr[n_attr].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[n_attr].val.programmaticStreamSerializationAllowed = 1;
+        ++n_attr;
+    }
+    cfg.attrs = attr;
+    cfg.numAttrs = n_attr;
+    int st = cuda_status(cudaLaunchKernelEx(&cfg, kern, ta, tb, td, tr, prm), "cudaLaunchKernelEx(conv_expand_ws_kernel)");
+    if (st) return st;
+    DPFT_LAUNCH_CHECK("conv_expand_ws_kernel");
+    return DPFT_OK;
+}
+
+// DPFT_CONV_WS=0 in the environment keeps the expand layers on the generic kernel (A/B timing)
+bool use_ws() {
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("DPFT_CONV_WS");
+        v = (e && e[0] == '0') ? 0 : 1;
+    }
+    return v != 0;
 }
 
 int pick_block_n(int Cout, int m_tiles, int want) {
@@ -667,10 +945,29 @@ extern "C" int dpft_conv2d_nhwc(const void* x, const void* w, const float* bias,
     st = encode_2d(&tr, residual ? residual : y, (uint64_t)Cout, (uint64_t)prm.M, (uint64_t)Cout * 2, EPI_COLS, 32, is_f16);
     if (st) return st;
     cudaStream_t s = (cudaStream_t)stream;
+    // weight-stationary kernel for the expand 1x1 + residual layers with enough tiles to amortise the resident weight slice
+    // (cluster_mode 3 forces it: tests); 256-wide n-tiles, K <= 256
+    if (pointwise && residual != nullptr && Cout % 256 == 0 && prm.kblocks <= 4 && (block_n == 0 || block_n == 256) &&
+        (cluster_mode == 3 || (cluster_mode == 0 && use_ws() && (long long)prm.m_tiles * (Cout / 256) >= 2LL * g_sm_count))) {
+        prm.n_tiles = Cout / 256;
+        if (prm.n_tiles <= g_sm_count) {
+            st = encode_2d(&tb, w, (uint64_t)Cin, (uint64_t)Cout, (uint64_t)Cin * 2, BLOCK_K, 256, is_f16);
+            if (st) return st;
+            if (prm.kblocks == 1) return launch_ws<256, 1, 4, 8>(ta, tb, td, tr, prm, s);
+            if (prm.kblocks == 2) return launch_ws<256, 2, 4, 6>(ta, tb, td, tr, prm, s);
+            return launch_ws<256, 4, 2, 4>(ta, tb, td, tr, prm, s);
+        }
+        prm.n_tiles = Cout / bn;
+    }
+    DPFT_REQUIRE(cluster_mode != 3, "conv2d: cluster_mode 3 (weight-stationary) needs a 1x1 stride-1 layer with a residual, Cout %% 256 == 0, Cin <= 256");
     // tuning hook (with tools/conv_bench.py): DPFT_CONV_STREAM_VARIANT picks another stage / residual-buffer / epilogue-warp split
     static const int variant = [] { const char* e = getenv("DPFT_CONV_STREAM_VARIANT"); return e ? atoi(e) : 0; }();
     if (pairs) {
         cudaStream_t s2 = (cudaStream_t)stream;
+        if (residual != nullptr && prm.kblocks <= 4) {   // forced pairs on an expand layer (cluster_mode 2): the stream-tuned split
+            if (bn == 256) return launch<256, 2, 5, 2, 4>(ta, tb, td, tr, prm, s2);
+            return launch<128, 2, 7, 2, 4>(ta, tb, td, tr, prm, s2);
+        }
         // (four epilogue warps per lane quadrant were tried here as well: no gain, 37.9 -> 38.9 us on s3_conv2)
         if (bn == 256) return launch<256, 4, 3, 2>(ta, tb, td, tr, prm, s2);
         return launch<128, 6, 3, 2>(ta, tb, td, tr, prm, s2);

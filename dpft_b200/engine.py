@@ -58,6 +58,7 @@ class FusedEngine:
         self.pos = fuser.query_embedding.weight.detach().float().contiguous()
         self._row_0001 = torch.tensor([0.0, 0.0, 0.0, 1.0], device=self.device)
         self._param_version = self._version(model)
+        self._mode = self._mode_of(model)
         self._graphs: Dict[tuple, List["_CapturedForward"]] = {}
         self._pipelines: Dict[tuple, List["_PipelineSlot"]] = {}
         self._seen: Dict[tuple, int] = {}
@@ -70,6 +71,12 @@ class FusedEngine:
     @staticmethod
     def _version(model) -> int:
         return sum(p._version for p in model.parameters()) + sum(b._version for b in model.buffers())
+
+    @staticmethod
+    def _mode_of(model) -> tuple:
+        """The model switches a captured graph bakes in: changing one of them must not replay a graph captured under another."""
+        return (getattr(model, "native_features", True), getattr(model, "parallel_views", True),
+                getattr(model, "side_view_priority", False))
 
     @staticmethod
     def ineligible_reason(model) -> Optional[str]:
@@ -109,6 +116,11 @@ class FusedEngine:
                 or getattr(self.model, "feature_dtype", torch.float16) != self.feature_dtype
                 or getattr(self.model, "pyramid_dtype", torch.float16) != self.pyramid_dtype):   # repack
             self.__init__(self.model)
+        if self._mode_of(self.model) != self._mode:       # same weights, another path: drop the graphs captured under the old one
+            self._mode = self._mode_of(self.model)
+            self._graphs.clear()
+            self._pipelines.clear()
+            self._seen.clear()
         x = batch[self.model.inputs[0]]
         return x.dtype == torch.float32 and (x.is_cuda or x.device.type == "cpu")
 

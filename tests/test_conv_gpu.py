@@ -62,7 +62,7 @@ def test_conv_matches_torch_fp32(shape, block_n, relu, with_res):
 # the pointwise "expand" convs with a residual (conv3 of every Bottleneck: the stream-bound configuration of the kernel): several
 # waves of m-tiles per CTA, M tails, 1 / 2 / 4 n-tiles, grid smaller and larger than the SM count
 EXPAND_SHAPES = [(2, 45, 80, 256, 1024), (3, 30, 33, 128, 512), (2, 16, 24, 64, 256), (8, 45, 80, 256, 1024), (1, 5, 5, 192, 768),
-                 (4, 90, 160, 128, 512)]
+                 (4, 90, 160, 128, 512), (1, 3, 5, 64, 256), (2, 90, 160, 64, 256), (1, 2, 2, 256, 2048), (8, 23, 41, 256, 1280)]
 
 
 @pytest.mark.parametrize("shape", EXPAND_SHAPES)
@@ -89,6 +89,14 @@ def test_expand_conv_with_residual_matches_torch_fp32(shape, dtype, relu):
     assert err <= (2.0 ** -7 if dtype == torch.bfloat16 else 2.0 ** -10) * scale, (err, scale)   # output rounding only
     auto = conv.conv2d_nhwc(x, w, bias, 1, 0, relu, res)                  # whatever tile the heuristic picks agrees
     assert (auto.float() - got.float()).abs().max().item() <= 2.0 ** -7 * scale
+    if Cin <= 256:
+        # cluster_mode 3: the weight-stationary kernel (resident weight slice, in-place residual / output ring) — the same
+        # fp32 sums in the same order as the generic kernel, so the 16-bit outputs must be bit-identical
+        ws = conv.conv2d_nhwc(x, w, bias, 1, 0, relu, res, cluster_mode=3)
+        ws2 = conv.conv2d_nhwc(x, w, bias, 1, 0, relu, res, cluster_mode=3)
+        torch.cuda.synchronize()
+        assert torch.equal(ws, ws2)
+        assert torch.equal(ws, got), (ws.float() - got.float()).abs().max().item()
 
 
 # 64 -> 64 channel 3x3 layers on wide maps go through the halo-tile kernel (conv3x3_halo.cu): width / height tails, a width that

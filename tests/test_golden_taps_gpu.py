@@ -40,32 +40,49 @@ def test_composed_gpu_path_intermediates_match_reference_taps():
         assert rel_err(out[k].cpu(), w) < 1e-3, k
 
 
-@pytest.mark.parametrize("native_train", [False, True])
-def test_gpu_training_gradients_match_reference_digest(native_train):
-    rec = load_golden("grads_radar_small")
+def _digest_run(rec, native_train, tf32):
     cfg = synthetic.offline_config(configs.make_config(rec["config"]), dropout=rec["dropout"])
     model = models.build("dprt", cfg).train()
     model.load_state_dict(synthetic.seeded_state_dict(model.state_dict(), seed=rec["weight_seed"]))
     model = model.to(DEV)
     model.native_train = native_train          # False: torch fp32 dense layers + the native deformable-attention fwd/bwd
     batch = synthetic.synthetic_batch(cfg, rec["batch"], seed=rec["input_seed"], sizes=rec["sizes"], device=DEV)
-    loss = sum((v ** 2).mean() for v in model(batch).values())
-    loss.backward()
+    old = torch.backends.cudnn.allow_tf32
+    torch.backends.cudnn.allow_tf32 = tf32
+    try:
+        loss = sum((v ** 2).mean() for v in model(batch).values())
+        loss.backward()
+    finally:
+        torch.backends.cudnn.allow_tf32 = old
     details = []
     worst_norm, worst_val = model_taps.digest_errors({k: p.grad for k, p in model.named_parameters()}, rec["grads"], details)
+    details.sort(key=lambda r: -max(r[1], r[2]))
+    return float(loss.detach()), worst_norm, worst_val, details
+
+
+def test_gpu_training_gradients_match_reference_digest():
+    """Gradient digests of the unmodified reference's train-mode step (CPU, fp32) against three GPU runs of the product:
+    torch fp32 dense layers (TF32 off) + the native deformable-attention backward — held to the digest directly; the same with
+    PyTorch's default TF32 convolutions — the yardstick (what the reference's own GPU training computes; 10-bit operands like
+    float16); and the native 16-bit backbone kernels.  Train-mode BatchNorm over the few hundred samples of these small maps
+    amplifies any rounding (tests/test_train_backbone_gpu.py measures 3-5x per stage), so the native path is bounded relative
+    to the yardstick, as there: norms within 4x of TF32's own error, single entries within 4x, with floors."""
+    rec = load_golden("grads_radar_small")
+    loss32, norm32, val32, _ = _digest_run(rec, False, False)
+    assert abs(loss32 - rec["loss"]) < 1e-3 * abs(rec["loss"])
+    assert norm32 < 2e-2 and val32 < 1e-1, (norm32, val32)
+    loss_tf, norm_tf, val_tf, _ = _digest_run(rec, False, True)
+    loss_n, norm_n, val_n, details = _digest_run(rec, True, False)
     report = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gpurun_out")
     if os.path.isdir(report):                  # per-parameter errors, worst first (evidence under profiles/ once promoted)
         import json
-        details.sort(key=lambda r: -max(r[1], r[2]))
-        with open(os.path.join(report, f"grad_digest_native_{int(native_train)}.json"), "w") as f:
-            json.dump({"loss": float(loss.detach()), "want_loss": rec["loss"], "worst_norm": worst_norm, "worst_val": worst_val,
-                       "rows(name, norm_err, entry_err, rms, max_sampled)": details[:40]}, f, indent=1)
-    if native_train:                           # 16-bit activations in the ResNet stages: the 1e-2 bar, looser on single entries
-        assert abs(float(loss.detach()) - rec["loss"]) < 2e-2 * abs(rec["loss"])
-        assert worst_norm < 1e-1 and worst_val < 5e-1, (worst_norm, worst_val)
-    else:
-        assert abs(float(loss.detach()) - rec["loss"]) < 1e-3 * abs(rec["loss"])
-        assert worst_norm < 2e-2 and worst_val < 1e-1, (worst_norm, worst_val)
+        with open(os.path.join(report, "grad_digest_native.json"), "w") as f:
+            json.dump({"want_loss": rec["loss"], "fp32": [loss32, norm32, val32], "tf32_yardstick": [loss_tf, norm_tf, val_tf],
+                       "native_f16": [loss_n, norm_n, val_n],
+                       "native rows(name, norm_err, entry_err, rms, max_sampled)": details[:40]}, f, indent=1)
+    assert abs(loss_n - rec["loss"]) < 2e-2 * abs(rec["loss"])
+    assert norm_n <= max(4.0 * norm_tf, 2e-2), (norm_n, norm_tf)
+    assert val_n <= max(4.0 * val_tf, 1e-1), (val_n, val_tf)
 
 
 @pytest.mark.parametrize("path", ["composed_fp32", "fused_decoder_fp32", "native_f16"])
