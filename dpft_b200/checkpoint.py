@@ -67,11 +67,32 @@ def _standin_class(module: str, name: str):
     return type(name, (_Standin,), {"__module__": module, "_standin_origin": f"{module}.{name}"})
 
 
+# Globals a pickled reference model legitimately needs to rebuild its TENSORS and containers.  Everything else — the model
+# classes themselves (dprt.*, torchvision.*, torch.nn.*) and anything unknown — becomes an inert stand-in whose constructor
+# and __reduce__ hooks never run, so a crafted "checkpoint" cannot execute code through this loader.
+_SAFE_GLOBALS = {
+    ("collections", "OrderedDict"), ("collections", "defaultdict"), ("builtins", "set"), ("builtins", "frozenset"),
+    ("builtins", "list"), ("builtins", "dict"), ("builtins", "tuple"), ("builtins", "int"), ("builtins", "float"),
+    ("builtins", "bool"), ("builtins", "str"), ("builtins", "bytes"), ("builtins", "complex"), ("builtins", "slice"),
+    ("builtins", "range"), ("__builtin__", "set"), ("__builtin__", "frozenset"),
+    ("torch._utils", "_rebuild_tensor_v2"), ("torch._utils", "_rebuild_tensor"), ("torch._utils", "_rebuild_parameter"),
+    ("torch._utils", "_rebuild_parameter_with_state"), ("torch._utils", "_rebuild_qtensor"),
+    ("torch._tensor", "_rebuild_from_type_v2"), ("torch", "Size"), ("torch", "device"), ("torch", "dtype"),
+    ("torch", "Tensor"), ("torch.nn.parameter", "Parameter"), ("torch.nn.parameter", "Buffer"),
+    ("torch.serialization", "_get_layout"), ("numpy.core.multiarray", "_reconstruct"), ("numpy._core.multiarray", "_reconstruct"),
+    ("numpy", "ndarray"), ("numpy", "dtype"), ("numpy.core.multiarray", "scalar"), ("numpy._core.multiarray", "scalar"),
+}
+_SAFE_TORCH_STORAGES = ("FloatStorage", "DoubleStorage", "HalfStorage", "BFloat16Storage", "LongStorage", "IntStorage",
+                        "ShortStorage", "CharStorage", "ByteStorage", "BoolStorage", "UntypedStorage")
+
+
 class _TolerantUnpickler(pickle.Unpickler):
     force_standin: Tuple[str, ...] = ()
 
     def find_class(self, module: str, name: str):
-        if not any(module == p or module.startswith(p + ".") for p in self.force_standin):
+        forced = any(module == p or module.startswith(p + ".") for p in self.force_standin)
+        allowed = (module, name) in _SAFE_GLOBALS or (module in ("torch", "torch.storage") and name in _SAFE_TORCH_STORAGES)
+        if allowed and not forced:
             try:
                 return super().find_class(module, name)     # also applies pickle's Python-2 name mapping (__builtin__.set ...)
             except (ImportError, AttributeError):

@@ -217,6 +217,12 @@ def order_like_scipy(col4row: torch.Tensor, counts: torch.Tensor, N: int):
     B, Mmax = col4row.shape
     slot = torch.arange(Mmax, device=col4row.device)
     valid = slot[None, :] < counts[:, None]
+    # A cost matrix with NaN / inf entries has no assignment: the kernel reports -1 for that sample's slots (scipy raises a
+    # ValueError the reference never catches).  Without a host round trip nothing can be raised here, so the whole sample is
+    # masked out instead — its losses become 0 and no -1 ever reaches a gather / scatter — and `SetCriterion` consumers can see
+    # the divergence as `mask.sum() < counts.sum()`.
+    solved = ((col4row >= 0) | ~valid).all(dim=1, keepdim=True)
+    valid = valid & solved
     key = torch.where(valid, col4row, N + slot[None, :].expand(B, -1))          # padded slots sort behind every prediction
     index_i, index_j = torch.sort(key, dim=1)
     return torch.where(valid, index_i, torch.zeros_like(index_i)), torch.where(valid, index_j, torch.zeros_like(index_j)), valid
@@ -224,7 +230,9 @@ def order_like_scipy(col4row: torch.Tensor, counts: torch.Tensor, N: int):
 
 def lsap_device(cost: torch.Tensor, counts: torch.Tensor) -> torch.Tensor:
     """``dpft_lsap_forward`` (csrc/lsap.cu): cost (B, N, Mmax) float32 cuda, counts (B,) int32 cuda -> (B, Mmax) int64, the
-    prediction matched to each ground-truth box.  EXPERIMENTAL (not yet validated on a B200)."""
+    prediction matched to each ground-truth box (-1 for every slot of a sample whose cost matrix holds NaN / inf).  Validated
+    against scipy on B200 (tests/test_criterion_metrics_gpu.py).  Ties between equal costs are broken by lane order, which can
+    differ from scipy's remaining-column order: the optimal COST is always equal, the matching only when it is unique."""
     from . import native
     native.require_cuda(cost, counts)
     if cost.dtype != torch.float32 or counts.dtype != torch.int32:

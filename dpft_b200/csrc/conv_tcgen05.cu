@@ -949,10 +949,23 @@ extern "C" int dpft_conv2d_nhwc(const void* x, const void* w, const float* bias,
     // (cluster_mode 3 forces it: tests); 256-wide n-tiles, K <= 256
     if (pointwise && residual != nullptr && Cout % 256 == 0 && prm.kblocks <= 4 && (block_n == 0 || block_n == 256) &&
         (cluster_mode == 3 || (cluster_mode == 0 && use_ws() && (long long)prm.m_tiles * (Cout / 256) >= 2LL * g_sm_count))) {
-        prm.n_tiles = Cout / 256;
+        // tuning hook (tools/conv_bench.py): DPFT_WS_VARIANT picks another tile width / stage / ring split of the same kernel
+        static const int ws_variant = [] { const char* e = getenv("DPFT_WS_VARIANT"); return e ? atoi(e) : 0; }();
+        const int wbn = ((ws_variant >= 2 && ws_variant <= 4) || (ws_variant >= 6 && ws_variant <= 9)) ? 128 : 256;
+        DPFT_REQUIRE(ws_variant < 8 || prm.kblocks <= 2, "DPFT_WS_VARIANT 8/9 hold two k-blocks of weights");
+        prm.n_tiles = Cout / wbn;
         if (prm.n_tiles <= g_sm_count) {
-            st = encode_2d(&tb, w, (uint64_t)Cin, (uint64_t)Cout, (uint64_t)Cin * 2, BLOCK_K, 256, is_f16);
+            st = encode_2d(&tb, w, (uint64_t)Cin, (uint64_t)Cout, (uint64_t)Cin * 2, BLOCK_K, wbn, is_f16);
             if (st) return st;
+            if (ws_variant == 1) return launch_ws<256, 4, 3, 2>(ta, tb, td, tr, prm, s);
+            if (ws_variant == 2) return launch_ws<128, 4, 4, 6>(ta, tb, td, tr, prm, s);
+            if (ws_variant == 3) return launch_ws<128, 4, 6, 4>(ta, tb, td, tr, prm, s);
+            if (ws_variant == 4) return launch_ws<128, 4, 4, 6, 2>(ta, tb, td, tr, prm, s);
+            if (ws_variant == 5) return launch_ws<256, 4, 2, 4, 2>(ta, tb, td, tr, prm, s);
+            if (ws_variant == 6) return launch_ws<128, 4, 5, 5>(ta, tb, td, tr, prm, s);
+            if (ws_variant == 7) return launch_ws<128, 4, 7, 3>(ta, tb, td, tr, prm, s);
+            if (ws_variant == 8) return launch_ws<128, 2, 8, 4>(ta, tb, td, tr, prm, s);
+            if (ws_variant == 9) return launch_ws<128, 2, 6, 6>(ta, tb, td, tr, prm, s);
             if (prm.kblocks == 1) return launch_ws<256, 1, 4, 8>(ta, tb, td, tr, prm, s);
             if (prm.kblocks == 2) return launch_ws<256, 2, 4, 6>(ta, tb, td, tr, prm, s);
             return launch_ws<256, 4, 2, 4>(ta, tb, td, tr, prm, s);
@@ -969,6 +982,13 @@ extern "C" int dpft_conv2d_nhwc(const void* x, const void* w, const float* bias,
             return launch<128, 2, 7, 2, 4>(ta, tb, td, tr, prm, s2);
         }
         // (four epilogue warps per lane quadrant were tried here as well: no gain, 37.9 -> 38.9 us on s3_conv2)
+        // tuning hook: layers without a residual do not need the residual sub-tile ring — DPFT_CONV_DEEP_VARIANT=1 trades it
+        // for operand stages (more bytes in flight per SM)
+        static const int deep_variant = [] { const char* e = getenv("DPFT_CONV_DEEP_VARIANT"); return e ? atoi(e) : 0; }();
+        if (deep_variant == 1 && residual == nullptr) {
+            if (bn == 256) return launch<256, 5, 1, 2>(ta, tb, td, tr, prm, s2);
+            return launch<128, 7, 1, 2>(ta, tb, td, tr, prm, s2);
+        }
         if (bn == 256) return launch<256, 4, 3, 2>(ta, tb, td, tr, prm, s2);
         return launch<128, 6, 3, 2>(ta, tb, td, tr, prm, s2);
     }

@@ -97,10 +97,18 @@ def head_eligible(head) -> Optional[str]:
     return None
 
 
+# bench.py sets this to a list to collect (gathered bytes, start_event, end_event) of every decoder-layer launch of one step
+PROFILE = None
+
+
 def layer_forward(views: Sequence[DecoderView], query: torch.Tensor, pos: torch.Tensor, center: torch.Tensor,
                   out: torch.Tensor, B: int, N: int, L: int, P: int, d_ffn: int, act: int, weight_floats: int,
                   pyramid_dtype: torch.dtype = torch.float32) -> None:
     lib = native.load_library()
+    prof = PROFILE
+    if prof is not None:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
     V = len(views)
     arr = (DecoderView * V)(*views)
     qs = 0 if query.dim() == 2 else N * C
@@ -110,6 +118,11 @@ def layer_forward(views: Sequence[DecoderView], query: torch.Tensor, pos: torch.
                                         native._DTYPE_CODE[pyramid_dtype], native.stream_ptr(out.device))
     native.check(st, "dpft_decoder_layer_forward")
     native.count_launch()
+    if prof is not None:
+        e1.record()
+        # per sample 4 bilinear corners x one 16-channel pyramid row (32 B in f16, 64 B in f32), M = 8 heads
+        row = 16 * (2 if pyramid_dtype == torch.float16 else 4)
+        prof.append((float(B) * len(views) * N * 8 * L * P * 4 * row, e0, e1))
 
 
 def head_forward(views: torch.Tensor, weights: torch.Tensor, center_in: torch.Tensor, query_out: torch.Tensor,

@@ -252,6 +252,25 @@ class FusedEngine:
         return {k: batch[k].to(self.device, non_blocking=True) for k in self._keys()}
 
     # -- pipelined replay: consecutive forwards overlap on the GPU -------------------------------------------------------
+    def _pipeline(self, batch: Dict[str, torch.Tensor], depth: int) -> List["_PipelineSlot"]:
+        on_host = not batch[self.model.inputs[0]].is_cuda
+        sig = ("stream", depth) + tuple((k, tuple(batch[k].shape), batch[k].dtype) for k in self._keys())
+        slots = self._pipelines.get(sig)
+        if slots is None:
+            with torch.no_grad():
+                dev_batch = self._to_device(batch) if on_host else batch
+                self.forward_eager(dev_batch)                # fills the per-shape caches outside any capture
+                slots = self._pipelines[sig] = [_PipelineSlot(self, dev_batch) for _ in range(depth)]
+        return slots
+
+    def stream_slots(self, example: Dict[str, torch.Tensor], depth: int = 2) -> List[Dict[str, torch.Tensor]]:
+        """The captured INPUT buffers of the ``depth`` pipeline slots for batches shaped like ``example``.  A producer that
+        already works on the device (a decode / pre-processing kernel, a DMA engine) can write batch i straight into
+        ``slots[i % depth]`` and hand that very dictionary to ``stream``: the replay then reads it in place and the
+        device-to-device staging copy of the input (113.6 MB per step on the bench workload) is skipped.  The buffer of a slot
+        may be refilled once the output of the forward that read it has been handed out."""
+        return [s.captured.static_in for s in self._pipeline(example, max(1, int(depth)))]
+
     def stream(self, batches, depth: int = 2):
         """Generator over ``batches`` (same shapes) yielding their outputs in order, with up to ``depth`` forwards in flight:
         forward k+1 is replayed on its own stream, from its own captured graph and memory pool, before the outputs of
@@ -267,13 +286,7 @@ class FusedEngine:
         for batch in batches:
             on_host = not batch[self.model.inputs[0]].is_cuda
             if slots is None:
-                sig = ("stream", depth) + tuple((k, tuple(batch[k].shape), batch[k].dtype) for k in self._keys())
-                slots = self._pipelines.get(sig)
-                if slots is None:
-                    with torch.no_grad():
-                        dev_batch = self._to_device(batch) if on_host else batch
-                        self.forward_eager(dev_batch)                # fills the per-shape caches outside any capture
-                        slots = self._pipelines[sig] = [_PipelineSlot(self, dev_batch) for _ in range(depth)]
+                slots = self._pipeline(batch, depth)
                 shapes = {k: tuple(batch[k].shape) for k in self._keys()}
             elif {k: tuple(batch[k].shape) for k in self._keys()} != shapes:
                 raise RuntimeError("FusedEngine.stream: every batch of one stream must have the same shapes")
@@ -313,6 +326,8 @@ class _CapturedForward:
         if copy_stream is None:
             for k in self.keys:
                 src = batch[k]
+                if src.data_ptr() == self.static_in[k].data_ptr():
+                    continue                     # the caller filled this slot's captured input buffer in place (stream_slots)
                 self.static_in[k].copy_(src, non_blocking=True)
                 # `main` may be a pipeline slot's private stream while `src` was allocated on the caller's (or the feeder's copy)
                 # stream: tell the caching allocator that this stream still reads it, or the block can be handed out again while

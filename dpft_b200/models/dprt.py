@@ -141,5 +141,19 @@ class DPRT(nn.Module):
             yield out
 
 
+    def stream_input_slots(self, example: Dict[str, torch.Tensor], depth: int = 2):
+        """Device input buffers of the ``depth`` pipeline slots of ``infer_stream`` (``FusedEngine.stream_slots``): fill
+        ``slots[i % depth]`` in place with batch i and pass that dictionary as the i-th item of ``infer_stream(..., depth)`` to
+        skip the input staging copy.  ``None`` when the fused pipeline does not serve this model / batch."""
+        from ..engine import FusedEngine
+        if not (self.use_fused and not self.training and self.use_cuda_graph):
+            return None
+        if self._engine is None:
+            self._engine = FusedEngine.try_create(self)
+        if self._engine is None or not self._engine.accepts(example):
+            return None
+        return self._engine.stream_slots(example, depth)
+
+
 def build_dprt(config: Dict[str, Any], *args, **kwargs) -> DPRT:
     return DPRT.from_config(config)

@@ -63,11 +63,30 @@ class GraphedTrainStep:
             raise RuntimeError("GraphedTrainStep: the model must be on a CUDA device and in train() mode")
         self._static = {k: torch.empty(v.shape, dtype=v.dtype, device=dev) for k, v in batch.items()}
         self._load(batch)
+        # The warm-up passes exist for the allocator, lazy initialisations and the weight-packer tables — they must not train:
+        # learning rate 0 (AdamW then leaves every parameter bit-identical), BatchNorm buffers snapshotted and restored in
+        # place, and the optimiser moments / step counters the passes created zeroed in place afterwards, so that the first
+        # replayed step is step 1 on untouched statistics, exactly as the reference loop's first iteration (trainer.py:116-135).
+        groups = self.optimizer.param_groups
+        saved_lr = [g["lr"] for g in groups]
+        buffers = [b for b in self.model.buffers()]
+        saved_buffers = [b.detach().clone() for b in buffers]
+        for g in groups:
+            g["lr"] = g["lr"] * 0.0                      # keeps a tensor learning rate a tensor
         side = torch.cuda.Stream(device=dev)
         side.wait_stream(torch.cuda.current_stream(dev))
         with torch.cuda.stream(side):
-            for _ in range(self.warmup):                 # allocator warm-up, lazy initialisations, weight-packer tables
+            for _ in range(self.warmup):
                 self._eager(self._static)
+            with torch.no_grad():
+                for b, s0 in zip(buffers, saved_buffers):
+                    b.copy_(s0)
+                for state in self.optimizer.state.values():
+                    for v in state.values():
+                        if isinstance(v, torch.Tensor):
+                            v.zero_()
+        for g, lr in zip(groups, saved_lr):
+            g["lr"] = lr
         torch.cuda.current_stream(dev).wait_stream(side)
         torch.cuda.synchronize(dev)
         self._graph = torch.cuda.CUDAGraph()
@@ -101,5 +120,6 @@ class GraphedTrainStep:
 
     @property
     def warmup_steps_taken(self) -> int:
-        """Optimiser updates applied by the capture warm-up (they are real training steps on the first batch)."""
-        return self.warmup if self._signature is not None or self._graph is not None else 0
+        """Optimiser updates applied by the capture warm-up: none (the warm-up passes run at learning rate 0 and their side
+        effects on BatchNorm buffers and optimiser state are undone before the capture)."""
+        return 0

@@ -18,6 +18,7 @@ LAYERS = {
     "s3_conv3": (45, 80, 256, 1024, 1, 1, 0, True),
     "s4_conv1": (23, 40, 2048, 512, 1, 1, 0, False), "s4_conv2": (23, 40, 512, 512, 3, 1, 1, False),
     "s4_conv3": (23, 40, 512, 2048, 1, 1, 0, True),
+    "s3_conv3_nores": (45, 80, 256, 1024, 1, 1, 0, False),
     "s3_down": (90, 160, 512, 1024, 1, 2, 0, False), "s3_conv2_s2": (90, 160, 256, 256, 3, 2, 1, False),
     # radar ResNet-50 at 256x256 (bs 8): small-M layers
     "r1_conv2": (64, 64, 64, 64, 3, 1, 1, False), "r2_conv3": (32, 32, 128, 512, 1, 1, 0, True),
@@ -27,6 +28,7 @@ LAYERS = {
 B = 8
 dev = "cuda:0"
 SWEEP = "--sweep" in sys.argv
+NO_LIB = "--no-lib" in sys.argv          # skip the cuDNN timings (variant sweeps)
 only = [a for a in sys.argv[1:] if not a.startswith("--")] or None
 flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
 for name, (H, W, Cin, Cout, R, stride, pad, res) in LAYERS.items():
@@ -92,7 +94,7 @@ for name, (H, W, Cin, Cout, R, stride, pad, res) in LAYERS.items():
         return torch.relu_(y)
 
     lib = {}
-    for nm, fn in (("cudnn_conv", lib_conv), ("cudnn_chain", lib_chain)):
+    for nm, fn in (() if NO_LIB else (("cudnn_conv", lib_conv), ("cudnn_chain", lib_chain))):
         for _ in range(3):
             fn()
         tl = []
@@ -112,4 +114,4 @@ for name, (H, W, Cin, Cout, R, stride, pad, res) in LAYERS.items():
     print(json.dumps({"layer": name, "M": M, "N": Cout, "K": R * R * Cin, "us_cold": round(tc, 1), "us_warm": round(tw, 1),
                       "tflops_cold": round(flops / tc / 1e6, 1), "gbps_cold": round(bytes_ / tc / 1e3, 1),
                       "tflops_warm": round(flops / tw / 1e6, 1), "MB": round(bytes_ / 1e6, 1), **lib,
-                      "speedup_vs_cudnn_chain": round(lib["cudnn_chain_us_cold"] / tc, 2)}), flush=True)
+                      **({} if NO_LIB else {"speedup_vs_cudnn_chain": round(lib["cudnn_chain_us_cold"] / tc, 2)})}), flush=True)
