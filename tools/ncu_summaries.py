@@ -75,7 +75,7 @@ def conv_traffic(path, out_prefix):
     key = "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active"
     tw = sum(s[key][0] * to_us(s["gpu__time_duration.sum"]) for s in sel) / us
     summary = {"source": "ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum," + key +
-                         " --clock-control none --profile-from-start off -k 'regex:conv_gemm|conv3x3_halo' python tools/one_forward.py (one eager forward, serial streams)",
+                         " --clock-control none --profile-from-start off -k 'regex:conv_gemm|conv3x3_halo|conv_expand' python tools/one_forward.py (one eager forward, serial streams)",
                "launches": len(sel), "dram_read_bytes": rd, "dram_write_bytes": wr, "dram_bytes": rd + wr,
                "sum_duration_us_under_ncu": us, "tensor_pipe_active_pct_time_weighted": tw}
     with open(out_prefix + "_ncu_conv_traffic.json", "w") as f:
