@@ -316,7 +316,7 @@ def conv_roofline(model, resident, dev, tf_peak, peak_src):
                 f"{t['launches']} tcgen05 convolution launches of one step (ncu, bs 8 bench workload); tensor pipe active " \
                 f"{t['tensor_pipe_active_pct_time_weighted']:.1f} % time-weighted"
             break
-    return {"kernel": "conv_gemm_kernel / conv3x3_halo_kernel (all %d backbone conv launches of one step)" % len(prof), "bound": "tensor",
+    return {"kernel": "conv_gemm_kernel / conv_expand_ws_kernel / conv3x3_halo_kernel (all %d backbone conv launches of one step)" % len(prof), "bound": "tensor",
             "achieved": achieved, "peak": tf_peak, "unit": "TFLOP/s", "frac": achieved / tf_peak, "traffic": traffic,
             "traffic_source": traffic_src,
             "peak_source": peak_src + ", bf16_tflops_sustained (kernel timed inside a long step)",
@@ -766,6 +766,9 @@ def main():
                               "outputs": parity_report(got, want, grid)}
             line["parity"]["max_norm_rel_worst"] = max(v["max_norm_rel"] for k, v in line["parity"]["outputs"].items()
                                                        if k != "center_refinement")
+            # `ok` = every output within north_star's tolerance for this arithmetic; for the 16-bit path `ok_vs_yardstick`
+            # (set below when the library baseline runs) = within max(tolerance, 2 x what the reference's own default GPU
+            # arithmetic deviates on the same frames) — the bar tests/test_full_size_gpu.py applies
             line["parity"]["ok"] = line["parity"]["max_norm_rel_worst"] <= line["parity"]["tolerance"]
         if world == 1 and not args.no_library_baseline and not args.small:
             lib, lib_out = gpu_library_baseline(cfg, sd, resident, dev, B)
@@ -782,6 +785,9 @@ def main():
                     line["parity"]["yardstick_reference_on_gpu_tf32_default"] = yard
                     line["parity"]["max_norm_rel_worst_over_yardstick"] = max(
                         line["parity"]["outputs"][k]["max_norm_rel"] / max(yard[k], 1e-12) for k in yard if k != "center_refinement")
+                    tol = line["parity"]["tolerance"]
+                    line["parity"]["ok_vs_yardstick"] = all(
+                        line["parity"]["outputs"][k]["max_norm_rel"] <= max(tol, 2.0 * yard[k]) for k in yard if k != "center_refinement")
                 lib["speedup_of_this_repo"] = line["sequential"]["value"] / lib["value"]
     # BASELINE config 4 (north_star's only collective): the data-parallel training step, timed in the same run on every rank
     train = None

@@ -16,6 +16,25 @@ from . import native
 # bench.py sets this to a list to collect (flops, bytes, start_event, end_event) of every conv launch of one step
 PROFILE = None
 
+# Cap on the persistent grid of the launches issued inside `cta_budget(n)` (0 = one CTA per SM): the engine runs the small
+# side views (radar) under it so that their latency-bound layers do not take every SM from the view on the critical path.
+_MAX_CTAS = 0
+
+
+class cta_budget:
+    def __init__(self, n: int):
+        self.n = int(n or 0)
+
+    def __enter__(self):
+        global _MAX_CTAS
+        self.saved, _MAX_CTAS = _MAX_CTAS, self.n
+        return self
+
+    def __exit__(self, *exc):
+        global _MAX_CTAS
+        _MAX_CTAS = self.saved
+        return False
+
 
 def fold_conv_bn(conv: nn.Conv2d, bn: Optional[nn.Module]) -> Tuple[torch.Tensor, torch.Tensor]:
     """Returns (weight (Cout, R, S, Cin) fp32, bias (Cout,) fp32) of conv followed by eval-mode BatchNorm."""
@@ -73,9 +92,9 @@ def conv2d_nhwc(x: torch.Tensor, weight: torch.Tensor, bias: torch.Tensor, strid
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
     with torch.cuda.device(x.device):
-        st = lib.dpft_conv2d_nhwc(native.ptr(x), native.ptr(weight), native.ptr(bias), native.ptr(residual),
-                                  native.ptr(out), B, H, W, Cin, Cout, R, S, stride, pad, int(relu), block_n, cluster_mode,
-                                  native.dtype_code(x), native.stream_ptr(x.device))
+        st = lib.dpft_conv2d_nhwc_ex(native.ptr(x), native.ptr(weight), native.ptr(bias), native.ptr(residual),
+                                     native.ptr(out), B, H, W, Cin, Cout, R, S, stride, pad, int(relu), block_n, cluster_mode,
+                                     native.dtype_code(x), _MAX_CTAS, native.stream_ptr(x.device))
     native.check(st, "dpft_conv2d_nhwc")
     native.count_launch()
     if prof is not None:

@@ -712,6 +712,9 @@ EncodeTiledFn g_encode_tiled = nullptr;
 EncodeIm2colFn g_encode_im2col = nullptr;
 int g_driver_version = 0;
 int g_sm_count = 0;
+thread_local int t_max_ctas = 0;      // per-call cap on the persistent grid (dpft_conv2d_nhwc_ex), 0 = one CTA per SM
+
+int cta_budget() { return (t_max_ctas > 0 && t_max_ctas < g_sm_count) ? t_max_ctas : g_sm_count; }
 
 int resolve_driver() {
     if (g_encode_tiled && g_encode_im2col) return 0;
@@ -770,7 +773,7 @@ int launch(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& td, 
         configured = true;
     }
     const int tiles = ((prm.m_tiles + CG - 1) / CG) * prm.n_tiles;
-    const int max_ctas = g_sm_count / CG;
+    const int max_ctas = cta_budget() / CG > 0 ? cta_budget() / CG : 1;
     const int grid = CG * (tiles < max_ctas ? tiles : max_ctas);
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3(grid);
@@ -813,7 +816,8 @@ int launch_ws(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& t
         configured = true;
     }
     const int tiles = prm.m_tiles * prm.n_tiles;
-    int grid = (g_sm_count / prm.n_tiles) * prm.n_tiles;      // a multiple of n_tiles: tile -> n_tile is constant per CTA
+    int grid = (cta_budget() / prm.n_tiles) * prm.n_tiles;    // a multiple of n_tiles: tile -> n_tile is constant per CTA
+    if (grid < prm.n_tiles) grid = prm.n_tiles;
     if (grid > tiles) grid = tiles;                           // (tiles is a multiple of n_tiles as well)
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3(grid);
@@ -870,6 +874,7 @@ extern "C" int dpft_fpn_lateral_forward(const void* x, const void* w, const floa
     DPFT_REQUIRE(x && w && bias && out, "fpn_lateral: null pointer");
     DPFT_REQUIRE(B > 0 && H > 0 && W > 0 && Cin % 64 == 0, "fpn_lateral: bad size B=%d H=%d W=%d Cin=%d", B, H, W, Cin);
     DPFT_REQUIRE(coarse == nullptr || (Hc > 0 && Wc > 0), "fpn_lateral: bad coarse size");
+    t_max_ctas = 0;
     int st = resolve_driver();
     if (st) return st;
     ConvParams prm{};
@@ -885,9 +890,30 @@ extern "C" int dpft_fpn_lateral_forward(const void* x, const void* w, const floa
     return launch<64, 6, 3, 1>(ta, tb, ta, ta, prm, (cudaStream_t)stream);   // d / r maps unused in the fp32 lateral form
 }
 
+static int conv2d_nhwc_impl(const void* x, const void* w, const float* bias, const void* residual, void* y,
+                            int B, int H, int W, int Cin, int Cout, int R, int S, int stride, int pad, int relu,
+                            int block_n, int cluster_mode, int dtype, void* stream);
+
 extern "C" int dpft_conv2d_nhwc(const void* x, const void* w, const float* bias, const void* residual, void* y,
                                 int B, int H, int W, int Cin, int Cout, int R, int S, int stride, int pad, int relu,
                                 int block_n, int cluster_mode, int dtype, void* stream) {
+    t_max_ctas = 0;
+    return conv2d_nhwc_impl(x, w, bias, residual, y, B, H, W, Cin, Cout, R, S, stride, pad, relu, block_n, cluster_mode, dtype, stream);
+}
+
+extern "C" int dpft_conv2d_nhwc_ex(const void* x, const void* w, const float* bias, const void* residual, void* y,
+                                   int B, int H, int W, int Cin, int Cout, int R, int S, int stride, int pad, int relu,
+                                   int block_n, int cluster_mode, int dtype, int max_ctas, void* stream) {
+    DPFT_REQUIRE(max_ctas >= 0, "conv2d: max_ctas=%d", max_ctas);
+    t_max_ctas = max_ctas;
+    const int st = conv2d_nhwc_impl(x, w, bias, residual, y, B, H, W, Cin, Cout, R, S, stride, pad, relu, block_n, cluster_mode, dtype, stream);
+    t_max_ctas = 0;
+    return st;
+}
+
+static int conv2d_nhwc_impl(const void* x, const void* w, const float* bias, const void* residual, void* y,
+                            int B, int H, int W, int Cin, int Cout, int R, int S, int stride, int pad, int relu,
+                            int block_n, int cluster_mode, int dtype, void* stream) {
     DPFT_REQUIRE(x && w && bias && y, "conv2d: null pointer");
     DPFT_REQUIRE(dtype == DPFT_BF16 || dtype == DPFT_F16, "conv2d: dtype must be DPFT_BF16 or DPFT_F16");
     const bool is_f16 = dtype == DPFT_F16;

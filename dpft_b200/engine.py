@@ -76,7 +76,7 @@ class FusedEngine:
     def _mode_of(model) -> tuple:
         """The model switches a captured graph bakes in: changing one of them must not replay a graph captured under another."""
         return (getattr(model, "native_features", True), getattr(model, "parallel_views", True),
-                getattr(model, "side_view_priority", False))
+                getattr(model, "side_view_priority", False), getattr(model, "side_view_ctas", 0))
 
     @staticmethod
     def ineligible_reason(model) -> Optional[str]:
@@ -150,7 +150,8 @@ class FusedEngine:
                     hp = getattr(model, "side_view_priority", False)
                     side = (self._side_streams_hp if hp else self._side_streams)[k - 1]
                     side.wait_event(fork)
-                    with torch.cuda.stream(side):
+                    from . import conv as _conv
+                    with torch.cuda.stream(side), _conv.cta_budget(getattr(model, "side_view_ctas", 0)):
                         flat, shapes = self.views[i].pyramid(batch[name])
                         done = torch.cuda.Event()
                         done.record(side)

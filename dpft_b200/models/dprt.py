@@ -9,6 +9,8 @@ deformable-attention op from libdpft_b200.so.
 """
 from __future__ import annotations
 
+import os
+
 from collections import OrderedDict
 from typing import Any, Callable, Dict, List, Optional, Tuple
 
@@ -62,6 +64,7 @@ class DPRT(nn.Module):
         self.use_cuda_graph = True     # fused pipeline: replay a captured graph once an input shape repeats
         self.parallel_views = True     # fused pipeline: run the per-view feature extractors on forked streams
         self.side_view_priority = False     # ... the other views on high-priority streams (measured: no gain)
+        self.side_view_ctas = int(os.environ.get("DPFT_SIDE_VIEW_CTAS", "0"))   # cap on the persistent conv grid of the other views (0 = none)
         self.native_train = True       # train() on CUDA: ResNet stages through the sm_100a training kernels (16-bit
                                        # activations, dpft_b200/train_backbone.py); False = torch/cuDNN autograd in fp32
         self.train_dtype = torch.float16

@@ -95,6 +95,12 @@ DPFT_API int dpft_msda_backward(const void* value, const int64_t* shapes, const 
 DPFT_API int dpft_conv2d_nhwc(const void* x, const void* w, const float* bias, const void* residual, void* y,
                               int B, int H, int W, int Cin, int Cout, int R, int S, int stride, int pad, int relu,
                               int block_n, int cluster_mode, int dtype, void* stream);
+/* Same, with a cap on the number of persistent CTAs (0 = one per SM).  The kernels are persistent with ~200 KB of shared
+ * memory per CTA, i.e. a CTA owns its SM; a small layer of a side view (the radar backbones beside the camera's) is
+ * latency-bound, so spreading it over every SM buys it nothing and takes the SMs from the view on the critical path. */
+DPFT_API int dpft_conv2d_nhwc_ex(const void* x, const void* w, const float* bias, const void* residual, void* y,
+                                 int B, int H, int W, int Cin, int Cout, int R, int S, int stride, int pad, int relu,
+                                 int block_n, int cluster_mode, int dtype, int max_ctas, void* stream);
 
 /*
  * ResNet stem: [1x1 adjustment conv (radar, 6 -> 3, resnet.py:47-51) folded into] conv1 7x7 stride 2 pad 3 + BatchNorm

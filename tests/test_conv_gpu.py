@@ -155,3 +155,27 @@ def test_folded_bottleneck_matches_torch_block():
     torch.cuda.synchronize()
     rel = (y.float() - want).abs().max().item() / want.abs().max().item()
     assert rel < 2e-2, rel
+
+
+@pytest.mark.parametrize("budget", [1, 2, 7, 40])
+@pytest.mark.parametrize("case", [(2, 32, 32, 128, 512, 1, 1, 0, True), (2, 16, 16, 256, 256, 3, 1, 1, False),
+                                  (1, 64, 64, 64, 64, 3, 1, 1, False), (2, 32, 32, 512, 128, 1, 1, 0, False),
+                                  (8, 45, 80, 256, 1024, 1, 1, 0, True)])
+def test_cta_budget_changes_only_the_grid(budget, case):
+    """dpft_conv2d_nhwc_ex with a cap on the persistent grid (the engine runs the side views under it): every tile is still
+    computed, by fewer CTAs, so the output is bit-identical to the uncapped launch — generic kernel, CTA pairs and the
+    weight-stationary kernel (whose grid must stay a multiple of its n-tile count)."""
+    from dpft_b200 import conv
+    B, H, W, Cin, Cout, R, stride, pad, with_res = case
+    dev = "cuda:0"
+    g = torch.Generator(device=dev).manual_seed(budget + Cin)
+    x = torch.randn(B, H, W, Cin, generator=g, device=dev).half()
+    w = (torch.randn(Cout, R, R, Cin, generator=g, device=dev) / (R * R * Cin) ** 0.5).half()
+    bias = torch.randn(Cout, generator=g, device=dev)
+    res = torch.randn(B, H, W, Cout, generator=g, device=dev).half() if with_res else None
+    want = conv.conv2d_nhwc(x, w, bias, stride, pad, True, res)
+    with conv.cta_budget(budget):
+        got = conv.conv2d_nhwc(x, w, bias, stride, pad, True, res)
+    after = conv.conv2d_nhwc(x, w, bias, stride, pad, True, res)          # the cap does not leak into later calls
+    torch.cuda.synchronize()
+    assert torch.equal(got, want) and torch.equal(after, want)
