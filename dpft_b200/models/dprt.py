@@ -64,7 +64,12 @@ class DPRT(nn.Module):
         self.use_cuda_graph = True     # fused pipeline: replay a captured graph once an input shape repeats
         self.parallel_views = True     # fused pipeline: run the per-view feature extractors on forked streams
         self.side_view_priority = False     # ... the other views on high-priority streams (measured: no gain)
-        self.side_view_ctas = int(os.environ.get("DPFT_SIDE_VIEW_CTAS", "0"))   # cap on the persistent conv grid of the other views (0 = none)
+        # ... and with their persistent convolution grids capped at this many CTAs (0 = one per SM).  A conv CTA owns its SM
+        # (~200 KB of shared memory); the radar layers are latency-bound, so 148 CTAs buy them nothing and starve the camera's
+        # kernels of the neighbouring forwards: bench step 4.64 -> 4.49 ms at 48, one forward at a time unchanged (4.74 -> 4.72);
+        # 16 is best pipelined (4.45) but makes the radar the critical path of a single forward (5.12)
+        # (profiles/r02_side_view_ctas_ab.txt)
+        self.side_view_ctas = int(os.environ.get("DPFT_SIDE_VIEW_CTAS", "48"))
         self.native_train = True       # train() on CUDA: ResNet stages through the sm_100a training kernels (16-bit
                                        # activations, dpft_b200/train_backbone.py); False = torch/cuDNN autograd in fp32
         self.train_dtype = torch.float16
