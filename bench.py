@@ -53,6 +53,7 @@ def parse():
     ap.add_argument("--no-train", action="store_true", help="skip the `train` object (BASELINE config 4 step) of the default run")
     ap.add_argument("--no-library-baseline", action="store_true", help="skip `gpu_library_baseline` (reference model through torch+cuDNN)")
     ap.add_argument("--train-steps", type=int, default=10, help="timed steps of the `train` object")
+    ap.add_argument("--train-timeout", type=int, default=420, help="seconds after which the line is printed without `train`")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--small", action="store_true", help="debug: tiny inputs (NOT a valid bench number)")
     ap.add_argument("--mode", default="infer", choices=["infer", "train"],
@@ -524,13 +525,14 @@ def run_train(args, cfg, sizes, rank, world, dev):
 def finish_distributed(world):
     if world > 1:
         import torch.distributed as dist
-        # do not let a stuck teardown (seen once: destroy_process_group never returned after graph capture) keep the job alive
-        dist.barrier()
-        torch.cuda.synchronize()
+        # do not let a stuck teardown (seen once: destroy_process_group never returned after graph capture; or a peer that left
+        # early after an error) keep the job alive: the line is already printed
         sys.stdout.flush()
-        watchdog = threading.Timer(20.0, lambda: os._exit(0))
+        watchdog = threading.Timer(45.0, lambda: os._exit(0))
         watchdog.daemon = True
         watchdog.start()
+        dist.barrier()
+        torch.cuda.synchronize()
         dist.destroy_process_group()
         watchdog.cancel()
 
@@ -794,9 +796,31 @@ def main():
     if not args.no_train and not args.small:
         del model
         torch.cuda.empty_cache()
-        train = run_train(args, cfg, sizes, rank, world, dev)
-    if rank == 0:
-        line["train"] = train
+        # The inference numbers above are complete: whatever happens in the training leg (an exception, or a collective that
+        # never returns inside the captured graph) must not cost the driver its one JSON line.
+        printed = threading.Event()
+
+        def emit(tr):
+            if rank == 0 and not printed.is_set():
+                printed.set()
+                line["train"] = tr
+                print(json.dumps(line), flush=True)
+
+        def give_up():
+            emit({"error": "training leg did not finish within %d s; line printed without it" % args.train_timeout})
+            os._exit(0)
+
+        watchdog = threading.Timer(float(args.train_timeout), give_up)
+        watchdog.daemon = True
+        watchdog.start()
+        try:
+            train = run_train(args, cfg, sizes, rank, world, dev)
+        except Exception as e:  # noqa: BLE001 - reported in the line
+            train = {"error": f"{type(e).__name__}: {e}"[:500]}
+        watchdog.cancel()
+        emit(train)
+    elif rank == 0:
+        line["train"] = None
         print(json.dumps(line), flush=True)
     finish_distributed(world)
 

@@ -3,7 +3,7 @@
 # training step with its NCCL all-reduces inside the captured graph), and at N=4; wall time of each.
 O=gpurun_out/r02c09; mkdir -p $O
 nvidia-smi -L | wc -l
-for N in 8 4; do
+for N in 8; do
 T0=$(date +%s)
 timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port $((29520 + N)) bench.py --gpus $N --steps 20 --warmup 5 > $O/bench_n$N.out 2> $O/bench_n$N.err
 echo "bench N=$N rc=$? wall=$(( $(date +%s) - T0 )) s"
