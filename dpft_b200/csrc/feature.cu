@@ -156,7 +156,13 @@ struct FpnOutParams {
     int pyramid_f16;
     long long S, start;
     int H, W, Hc, Wc;
+    int raw_u8;                // raw is (B, H, W, CIN) uint8 (what an image decoder produces): converted on load, values exact
 };
+
+// element idx of the raw input as fp32
+__device__ __forceinline__ float raw_ld(const FpnOutParams& prm, long long idx) {
+    return prm.raw_u8 ? (float)__ldg(reinterpret_cast<const unsigned char*>(prm.raw) + idx) : __ldg(prm.raw + idx);
+}
 
 // one pyramid row (16 channels of one pixel): 64 B as fp32 or 32 B as f16 (saturating)
 __device__ __forceinline__ void store_pyramid_row(void* pyramid, long long pixel, const float* v, bool f16) {
@@ -209,9 +215,9 @@ fpn_output_kernel(const FpnOutParams prm) {
         if (hh >= 0 && hh < H && ww >= 0 && ww < W) {
             if (CIN > 0) {
                 float xin[CIN > 0 ? CIN : 1];
-                const float* xp = prm.raw + (((long long)b * H + hh) * W + ww) * CIN;
+                const long long xi = (((long long)b * H + hh) * W + ww) * CIN;
 #pragma unroll
-                for (int c = 0; c < CIN; ++c) xin[c] = __ldg(xp + c);
+                for (int c = 0; c < CIN; ++c) xin[c] = raw_ld(prm, xi + c);
 #pragma unroll
                 for (int o = 0; o < FC; ++o) {
                     float a = s_lat[FC * CIN + o];
@@ -364,9 +370,9 @@ fpn_output_tc_kernel(const FpnOutParams prm) {
             okv[u] = ok;
             const int hs = ok ? hh : 0, ws = ok ? ww : 0;
             if (CIN > 0) {
-                const float* xp = prm.raw + (((long long)b * H + hs) * W + ws) * CIN;
+                const long long xi = (((long long)b * H + hs) * W + ws) * CIN;
 #pragma unroll
-                for (int c = 0; c < CIN; ++c) xin[u][c] = ok ? __ldg(xp + c) : 0.0f;
+                for (int c = 0; c < CIN; ++c) xin[u][c] = ok ? raw_ld(prm, xi + c) : 0.0f;
                 if (prm.coarse) {
                     const int hc = nearest_src(hs, prm.Hc, H), wc = nearest_src(ws, prm.Wc, W);
                     const float4* cp = reinterpret_cast<const float4*>(prm.coarse + (((long long)b * prm.Hc + hc) * prm.Wc + wc) * FC);
@@ -508,9 +514,9 @@ __device__ __forceinline__ void fpn_build_column(const FpnOutParams& prm, uint8_
     for (int u = 0; u < ROWS; ++u) {                 // every raw load of the column is issued before any is consumed
         const int hh = p0 - 1 + rr0 + u;
         ok[u] = col_ok && hh >= 0 && hh < H;
-        const float* xp = prm.raw + (((long long)b * H + (ok[u] ? hh : 0)) * W + ws) * CIN;
+        const long long xi = (((long long)b * H + (ok[u] ? hh : 0)) * W + ws) * CIN;
 #pragma unroll
-        for (int c = 0; c < CIN; ++c) xin[u][c] = ok[u] ? __ldg(xp + c) : 0.0f;
+        for (int c = 0; c < CIN; ++c) xin[u][c] = ok[u] ? raw_ld(prm, xi + c) : 0.0f;
     }
     float cb[FC];
 #pragma unroll
@@ -854,9 +860,9 @@ constexpr int SS_SMEM = ST_B_BYTES + SS_RING * ST_ROWB + STEM_COUT * 4 + (2 * SS
 // Cin == 3 uses the 4-channels-per-tap operands (stem_pack_weights4_kernel): an A entry is [pixel x: 4 ch | pixel x + 2: 4 ch],
 // i.e. every pixel is written into two entries of its parity plane; the MMA count per output row drops from 28 to 14.
 
-template <int CIN, typename OT>
+template <int CIN, typename OT, typename IT>
 __global__ void __launch_bounds__(SS_THREADS)
-stem_stream_kernel(const float* __restrict__ x, const uint4* __restrict__ w_packed, const float* __restrict__ bias,
+stem_stream_kernel(const IT* __restrict__ x, const uint4* __restrict__ w_packed, const float* __restrict__ bias,
                    OT* __restrict__ y, int H, int W, int P, int Q, float lo, int strips, int chunks, int chunk_rows) {
     extern __shared__ __align__(128) uint8_t tsm[];
     uint8_t* s_b = tsm;
@@ -911,16 +917,16 @@ stem_stream_kernel(const float* __restrict__ x, const uint4* __restrict__ w_pack
             tc::mbar_wait(&row_empty[slot], ((i / SS_RING) & 1) ^ 1);
             const int hh = h_base + i;
             const bool row_ok = hh >= 0 && hh < H;
-            const float* xrow = x + ((long long)b * H + (row_ok ? hh : 0)) * W * CIN;
+            const IT* xrow = x + ((long long)b * H + (row_ok ? hh : 0)) * W * CIN;     // IT = float, or uint8 frames (exact in f16)
             float v[PER_LANE][CIN];
 #pragma unroll
             for (int u = 0; u < PER_LANE; ++u) {             // all global loads of the row first
                 const int xl = lane + u * 32;
                 const int ww = w_base + xl;
                 const bool ok = row_ok && xl < ENTRIES && ww >= 0 && ww < W;
-                const float* xp = xrow + (long long)(ok ? ww : 0) * CIN;
+                const IT* xp = xrow + (long long)(ok ? ww : 0) * CIN;
 #pragma unroll
-                for (int c = 0; c < CIN; ++c) v[u][c] = ok ? __ldg(xp + c) : 0.0f;
+                for (int c = 0; c < CIN; ++c) v[u][c] = ok ? (float)__ldg(xp + c) : 0.0f;
             }
             uint8_t* dst = s_a + slot * ST_ROWB;
 #pragma unroll
@@ -1033,10 +1039,10 @@ stem_stream_kernel(const float* __restrict__ x, const uint4* __restrict__ w_pack
     }
 }
 
-template <int CIN, typename OT>
-static int launch_stem_stream(const float* x, const void* w_packed, const float* bias, void* y, int B, int H, int W, int P, int Q,
+template <int CIN, typename OT, typename IT>
+static int launch_stem_stream(const IT* x, const void* w_packed, const float* bias, void* y, int B, int H, int W, int P, int Q,
                               float lo, cudaStream_t s) {
-    auto kern = stem_stream_kernel<CIN, OT>;
+    auto kern = stem_stream_kernel<CIN, OT, IT>;
     static bool configured = false;
     if (!configured) {
         int st = cuda_status(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SS_SMEM), "stem stream attr");
@@ -1061,7 +1067,7 @@ template <int CIN, typename OT>
 static int launch_stem_tc(const float* x, const void* w_packed, const float* bias, void* y, int B, int H, int W, int P, int Q,
                           float lo, cudaStream_t s) {
     static const int stream_mode = [] { const char* e = getenv("DPFT_STEM_STREAM"); return (e && e[0] == '0') ? 0 : 1; }();
-    if (stream_mode) return launch_stem_stream<CIN, OT>(x, w_packed, bias, y, B, H, W, P, Q, lo, s);
+    if (stream_mode) return launch_stem_stream<CIN, OT, float>(x, w_packed, bias, y, B, H, W, P, Q, lo, s);
     auto kern = stem_tc_kernel<CIN, OT>;
     const size_t smem = ST_A_BYTES + ST_B_BYTES + (ST_TH + 2) * 8 + 16 + STEM_COUT * sizeof(float);
     static bool configured = false;
@@ -1117,6 +1123,22 @@ extern "C" int dpft_stem_conv7x7_forward(const float* x, const float* w, const v
 extern "C" int dpft_stem_conv7x7_forward_ex(const float* x, const float* w, const void* w_packed, const float* bias, void* y,
                                             int B, int H, int W, int Cin, int dtype, int impl, int relu, void* stream) {
     const float lo = relu ? 0.0f : (dtype == DPFT_F16 ? -65504.0f : -3.0e38f);
+    const bool x_u8 = (Cin & DPFT_RAW_U8) != 0;                    // x is (B, H, W, Cin) uint8
+    Cin &= ~DPFT_RAW_U8;
+    if (x_u8) {
+        // uint8 frames go through the row-streaming tensor-core kernel only (the camera stem); other shapes convert first
+        DPFT_REQUIRE(Cin == 3 && w_packed && impl != 1 && (W - 1) / 2 + 1 >= 64 && x && bias && y && B > 0 && H > 0,
+                     "stem: uint8 input needs Cin = 3, the packed weights and an output width >= 64");
+        DPFT_REQUIRE(dtype == DPFT_BF16 || dtype == DPFT_F16, "stem: output dtype must be DPFT_BF16 or DPFT_F16");
+        const int P8 = (H - 1) / 2 + 1, Q8 = (W - 1) / 2 + 1;
+        const unsigned char* x8 = reinterpret_cast<const unsigned char*>(x);
+        const int st8 = dtype == DPFT_F16
+            ? launch_stem_stream<3, __half, unsigned char>(x8, w_packed, bias, y, B, H, W, P8, Q8, lo, (cudaStream_t)stream)
+            : launch_stem_stream<3, __nv_bfloat16, unsigned char>(x8, w_packed, bias, y, B, H, W, P8, Q8, lo, (cudaStream_t)stream);
+        if (st8) return st8;
+        DPFT_LAUNCH_CHECK("stem_stream_kernel<uint8>");
+        return DPFT_OK;
+    }
     DPFT_REQUIRE(impl != 2 || w_packed, "stem: the tensor-core kernel needs the packed weights (dpft_stem_pack_weights)");
     DPFT_REQUIRE(impl >= 0 && impl <= 2, "stem: impl must be 0 (auto), 1 (CUDA cores) or 2 (tensor cores)");
     DPFT_REQUIRE(x && w && bias && y, "stem: null pointer");
@@ -1177,8 +1199,10 @@ extern "C" int dpft_fpn_output_forward(const float* inner, const float* raw, int
     DPFT_REQUIRE(w && bias && pos_y && pos_x && pyramid, "fpn_output: null pointer");
     DPFT_REQUIRE((inner != nullptr) != (raw != nullptr), "fpn_output: exactly one of inner / raw must be given");
     DPFT_REQUIRE(B > 0 && H > 0 && W > 0, "fpn_output: bad size");
+    const int raw_u8 = (raw_channels & DPFT_RAW_U8) ? 1 : 0;       // the raw level handed over as uint8
+    raw_channels &= ~DPFT_RAW_U8;
     FpnOutParams prm{inner, raw, lat_w, lat_b, coarse, w, (const uint4*)w_packed, bias, pos_y, pos_x, pyramid, pyramid_dtype == DPFT_F16 ? 1 : 0,
-                     S, start, H, W, Hc, Wc};
+                     S, start, H, W, Hc, Wc, raw_u8};
     cudaStream_t s = (cudaStream_t)stream;
     DPFT_REQUIRE(impl >= 0 && impl <= 3, "fpn_output: impl must be 0 (auto), 1 (CUDA cores), 2 (tensor cores) or 3 (tensor cores, "
                  "column-owning tile builder: experimental)");

@@ -73,27 +73,30 @@ __device__ __forceinline__ void block_reduce_to_partials(const float (&v)[NV], i
     }
 }
 
-// column sums of a [nparts][n] partial buffer; blockDim = (32, 8), one block per 32 columns
+// column sums of a [nparts][n] partial buffer; blockDim = (32, CS_ROWS), one block per 32 columns.  These are the 420 tiny
+// launches between the streaming passes of a training step: each thread's chain of dependent L2 round trips is what they
+// cost, so the rows are spread over 32 threads per column (was 8: ~10 round trips per thread, ~8 us per launch).
+constexpr int CS_ROWS = 32;
 __device__ __forceinline__ float column_sum(const float* __restrict__ partials, int nparts, int n, int col) {
-    __shared__ float part[8][33];
+    __shared__ float part[CS_ROWS][33];
     float acc = 0.0f;
     if (col < n) {
         float a0 = 0.0f, a1 = 0.0f, a2 = 0.0f, a3 = 0.0f;                 // four independent loads in flight
         int r = threadIdx.y;
-        for (; r + 24 < nparts; r += 32) {
+        for (; r + 3 * CS_ROWS < nparts; r += 4 * CS_ROWS) {
             a0 += partials[(size_t)r * n + col];
-            a1 += partials[(size_t)(r + 8) * n + col];
-            a2 += partials[(size_t)(r + 16) * n + col];
-            a3 += partials[(size_t)(r + 24) * n + col];
+            a1 += partials[(size_t)(r + CS_ROWS) * n + col];
+            a2 += partials[(size_t)(r + 2 * CS_ROWS) * n + col];
+            a3 += partials[(size_t)(r + 3 * CS_ROWS) * n + col];
         }
-        for (; r < nparts; r += 8) a0 += partials[(size_t)r * n + col];
+        for (; r < nparts; r += CS_ROWS) a0 += partials[(size_t)r * n + col];
         acc = (a0 + a1) + (a2 + a3);
     }
     part[threadIdx.y][threadIdx.x] = acc;
     __syncthreads();
     float tot = 0.0f;
 #pragma unroll
-    for (int r = 0; r < 8; ++r) tot += part[r][threadIdx.x];
+    for (int r = 0; r < CS_ROWS; ++r) tot += part[r][threadIdx.x];
     __syncthreads();
     return tot;
 }
@@ -578,7 +581,7 @@ extern "C" int dpft_bn_forward_stats(const void* y, float* workspace, const floa
     if (is_f16) bn_stats_kernel<true><<<grid, RB, 0, (cudaStream_t)stream>>>((const uint4*)y, workspace, nvec, C / 8);
     else bn_stats_kernel<false><<<grid, RB, 0, (cudaStream_t)stream>>>((const uint4*)y, workspace, nvec, C / 8);
     DPFT_LAUNCH_CHECK("bn_stats_kernel");
-    bn_finalize_kernel<<<(C + 31) / 32, dim3(32, 8), 0, (cudaStream_t)stream>>>(workspace, grid, gamma, beta, running_mean, running_var,
+    bn_finalize_kernel<<<(C + 31) / 32, dim3(32, CS_ROWS), 0, (cudaStream_t)stream>>>(workspace, grid, gamma, beta, running_mean, running_var,
                                                                                momentum, eps, (float)M, C, scale, shift, mean, invstd);
     DPFT_LAUNCH_CHECK("bn_finalize_kernel");
     return DPFT_OK;
@@ -609,7 +612,7 @@ extern "C" int dpft_bn_backward_reduce(const void* dz, const void* z, const void
     if (is_f16) bn_bwd_reduce_kernel<true><<<grid, RB, 0, (cudaStream_t)stream>>>((const uint4*)dz, (const uint4*)z, (const uint4*)y, mean, invstd, workspace, nvec, C / 8, relu);
     else bn_bwd_reduce_kernel<false><<<grid, RB, 0, (cudaStream_t)stream>>>((const uint4*)dz, (const uint4*)z, (const uint4*)y, mean, invstd, workspace, nvec, C / 8, relu);
     DPFT_LAUNCH_CHECK("bn_bwd_reduce_kernel");
-    bn_bwd_sums_kernel<<<(C + 31) / 32, dim3(32, 8), 0, (cudaStream_t)stream>>>(workspace, grid, C, sum_g, sum_gx, dgamma, dbeta);
+    bn_bwd_sums_kernel<<<(C + 31) / 32, dim3(32, CS_ROWS), 0, (cudaStream_t)stream>>>(workspace, grid, C, sum_g, sum_gx, dgamma, dbeta);
     DPFT_LAUNCH_CHECK("bn_bwd_sums_kernel");
     return DPFT_OK;
 }
@@ -697,7 +700,7 @@ extern "C" int dpft_stem_conv7x7_wgrad(const float* x, const void* dy, float* wo
     else { if (is_f16) DPFT_SW_LAUNCH(6, true); else DPFT_SW_LAUNCH(6, false); }
 #undef DPFT_SW_LAUNCH
     DPFT_LAUNCH_CHECK("stem_wgrad_kernel");
-    rows_sum_add_kernel<<<(n + 31) / 32, dim3(32, 8), 0, s>>>(workspace, grid, n, dw);
+    rows_sum_add_kernel<<<(n + 31) / 32, dim3(32, CS_ROWS), 0, s>>>(workspace, grid, n, dw);
     DPFT_LAUNCH_CHECK("rows_sum_add_kernel");
     return DPFT_OK;
 }

@@ -10,6 +10,7 @@ kernels do not cover fall back to the composed GPU path in ``DPRT.forward_compos
 """
 from __future__ import annotations
 
+import os
 from collections import OrderedDict
 from typing import Dict, List, Optional
 
@@ -66,6 +67,7 @@ class FusedEngine:
         self._side_streams = [torch.cuda.Stream(device=self.device) for _ in range(max(0, len(model.inputs) - 1))]
         self._side_streams_hp = [torch.cuda.Stream(device=self.device, priority=-1) for _ in range(max(0, len(model.inputs) - 1))]
         self._copy_stream = torch.cuda.Stream(device=self.device)
+        self.upload_slots = int(os.environ.get("DPFT_UPLOAD_SLOTS", "2"))     # spare pipeline slots for host batches (stream())
 
     # -- construction ---------------------------------------------------------------------------------------------
     @staticmethod
@@ -121,8 +123,19 @@ class FusedEngine:
             self._graphs.clear()
             self._pipelines.clear()
             self._seen.clear()
-        x = batch[self.model.inputs[0]]
-        return x.dtype == torch.float32 and (x.is_cuda or x.device.type == "cpu")
+        # float32 tensors (the reference's dataset contract) or, for a view on the native feature path, the uint8 frames an image
+        # decoder produces (a quarter of the bytes over PCIe and out of HBM; converted on load inside the stem / FPN kernels)
+        native_ok = getattr(self.model, "native_features", True)
+        for name, nv in zip(self.model.inputs, self.views):
+            x = batch[name]
+            if not (x.is_cuda or x.device.type == "cpu"):
+                return False
+            if x.dtype == torch.uint8:
+                if nv is None or not native_ok:
+                    return False
+            elif x.dtype != torch.float32:
+                return False
+        return True
 
     # -- stage 1: feature pyramids --------------------------------------------------------------------------------
     def pyramids(self, batch: Dict[str, torch.Tensor]) -> List[FeaturePyramid]:
@@ -282,17 +295,26 @@ class FusedEngine:
         from collections import deque
         depth = max(1, int(depth))
         pending = deque()
+        done_events = deque(maxlen=depth)          # completion events of the last `depth` forwards launched
         slots = None
         index = 0
         for batch in batches:
             on_host = not batch[self.model.inputs[0]].is_cuda
             if slots is None:
-                slots = self._pipeline(batch, depth)
+                # Host batches get two slots more than forwards in flight: a slot's captured input buffer is read until the very
+                # end of its forward (the FPN raw level), so with `depth` slots the upload of batch k+1 could only start when
+                # forward k+1-depth had finished and its 2 ms sat exposed in front of every replay.  With spare slots the
+                # upload lands in a buffer nobody reads while `depth` forwards run; the replay itself is still gated on the
+                # completion of forward k+1-depth, so never more than `depth` forwards share the GPU.
+                n_slots = depth + (self.upload_slots if on_host else 0)
+                slots = self._pipeline(batch, n_slots)
                 shapes = {k: tuple(batch[k].shape) for k in self._keys()}
             elif {k: tuple(batch[k].shape) for k in self._keys()} != shapes:
                 raise RuntimeError("FusedEngine.stream: every batch of one stream must have the same shapes")
+            gate = done_events[0] if (len(slots) > depth and len(done_events) == depth) else None
             with torch.no_grad():
-                pending.append(slots[index % depth].launch(batch, self._copy_stream if on_host else None))
+                pending.append(slots[index % len(slots)].launch(batch, self._copy_stream if on_host else None, gate))
+            done_events.append(pending[-1][1])
             index += 1
             if len(pending) >= depth:
                 yield _PipelineSlot.collect(pending.popleft(), self.device)
@@ -357,9 +379,11 @@ class _PipelineSlot:
         self.stream = torch.cuda.Stream(device=engine.device)
         self.device = engine.device
 
-    def launch(self, batch: Dict[str, torch.Tensor], copy_stream):
+    def launch(self, batch: Dict[str, torch.Tensor], copy_stream, gate=None):
         caller = torch.cuda.current_stream(self.device)
         self.stream.wait_stream(caller)          # inputs made on the caller's stream; also orders after this slot's last hand-out
+        if gate is not None:
+            self.stream.wait_event(gate)         # the replay (not the upload) waits until an older forward has left the GPU
         with torch.cuda.stream(self.stream):
             outs = self.captured.replay(batch, copy_stream)
             done = torch.cuda.Event()

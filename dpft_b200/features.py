@@ -53,8 +53,10 @@ def stem_forward(x: torch.Tensor, w: torch.Tensor, bias: torch.Tensor, dtype: to
     y = torch.empty((B, (H - 1) // 2 + 1, (W - 1) // 2 + 1, 64), dtype=dtype, device=x.device)
     if w_packed is None and impl == 2:
         w_packed = stem_pack_weights(w)
+    # uint8 frames (include/dpft_b200.h: DPFT_RAW_U8) are converted on load inside the row-streaming kernel
+    cin_code = Cin | RAW_U8 if x.dtype == torch.uint8 else Cin
     st = _lib().dpft_stem_conv7x7_forward_ex(native.ptr(x), native.ptr(w), native.ptr(w_packed), native.ptr(bias), native.ptr(y), B, H, W,
-                                             Cin, native.dtype_code(y), impl, int(relu), native.stream_ptr(x.device))
+                                             cin_code, native.dtype_code(y), impl, int(relu), native.stream_ptr(x.device))
     native.check(st, "dpft_stem_conv7x7_forward_ex")
     native.count_launch()
     return y
@@ -91,12 +93,17 @@ def fpn_output_forward(pyramid: torch.Tensor, start: int, H: int, W: int, w: tor
         w_packed = fpn_pack_weights(w)
     hc, wc = (coarse.shape[1], coarse.shape[2]) if coarse is not None else (0, 0)
     raw_c = raw.shape[-1] if raw is not None else 0
+    if raw is not None and raw.dtype == torch.uint8:
+        raw_c |= RAW_U8
     st = _lib().dpft_fpn_output_forward(native.ptr(inner), native.ptr(raw), raw_c, native.ptr(lat_w), native.ptr(lat_b),
                                         native.ptr(coarse), hc, wc, native.ptr(w), native.ptr(w_packed), native.ptr(bias), native.ptr(pos_y),
                                         native.ptr(pos_x), native.ptr(pyramid), native.dtype_code(pyramid), S, start, B, H, W,
                                         impl, native.stream_ptr(pyramid.device))
     native.check(st, "dpft_fpn_output_forward")
     native.count_launch()
+
+
+RAW_U8 = 0x100            # include/dpft_b200.h: DPFT_RAW_U8
 
 
 # Forked FPN output launches (NativeView._pyramid_forked): default since round 2 (bit-identical on B200, bench step
@@ -225,8 +232,15 @@ class NativeView:
         del inners                      # alive until the join: their memory is not reused while the forked stream reads it
         return pyr, shapes
 
+    def accepts_uint8(self, x: torch.Tensor) -> bool:
+        """uint8 frames are read directly by the stem's row-streaming kernel and the FPN raw-level kernels when the view is a
+        3-channel image at least 127 pixels wide (the camera); anything else is converted to float32 first (plumbing)."""
+        return self.cin == 3 and (x.shape[2] - 1) // 2 + 1 >= 64 and self.stem_w_packed is not None
+
     def pyramid(self, x: torch.Tensor) -> Tuple[torch.Tensor, List[Tuple[int, int]]]:
         x = x.contiguous()
+        if x.dtype == torch.uint8 and not self.accepts_uint8(x):
+            x = x.float()
         B = x.shape[0]
         feats = self.backbone(x)
         shapes = ([(x.shape[1], x.shape[2])] if self.skiplink else []) + [(f.shape[1], f.shape[2]) for f in feats]

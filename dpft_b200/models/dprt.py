@@ -122,6 +122,11 @@ class DPRT(nn.Module):
                 self._engine = FusedEngine.try_create(self)
             if self._engine is not None and self._engine.accepts(batch):
                 return self._engine.forward(batch)
+        if any(batch[name].dtype == torch.uint8 for name in self.inputs):      # uint8 frames outside the native feature path:
+            batch = {k: (v.float() if k in self.inputs and v.dtype == torch.uint8 else v) for k, v in batch.items()}   # plumbing
+            if self.use_fused and not self.training and not torch.is_grad_enabled() and self._engine is not None \
+                    and self._engine.accepts(batch):
+                return self._engine.forward(batch)
         return self.forward_composed(batch)
 
     def infer_stream(self, batches, depth: int = 2):

@@ -102,6 +102,12 @@ DPFT_API int dpft_conv2d_nhwc_ex(const void* x, const void* w, const float* bias
                                  int B, int H, int W, int Cin, int Cout, int R, int S, int stride, int pad, int relu,
                                  int block_n, int cluster_mode, int dtype, int max_ctas, void* stream);
 
+/* OR-ed into `Cin` of dpft_stem_conv7x7_forward_ex and into `raw_channels` of dpft_fpn_output_forward: the raw input is
+ * (B, H, W, C) uint8 — the frames an image decoder produces, before the reference's `.type(float32)`
+ * (src/dprt/datasets/kradar/dataset.py read_image) — and is converted on load (0..255 is exact in f16): a quarter of the
+ * bytes over PCIe and out of HBM.  Stem: Cin = 3, packed weights, output width >= 64 (the camera path). */
+#define DPFT_RAW_U8 0x100
+
 /*
  * ResNet stem: [1x1 adjustment conv (radar, 6 -> 3, resnet.py:47-51) folded into] conv1 7x7 stride 2 pad 3 + BatchNorm
  * (folded) + ReLU, reference src/dprt/models/backbones/resnet.py:98-101 (torchvision conv1/bn1/relu).

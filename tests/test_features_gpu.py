@@ -171,3 +171,32 @@ def test_fpn_output_column_builder_matches_cuda_core(cin, H, W):
     assert float(c[:, :7].abs().max()) == 0.0                      # nothing written before `start`
     assert _rel(c, a) < 2e-3, _rel(c, a)
     assert _rel(c, b) < 1e-3, _rel(c, b)                           # same operand image up to the rounding of the FMA chain
+
+
+@pytest.mark.parametrize("size", [(2, 70, 131, 3), (1, 128, 228, 3), (3, 33, 300, 3)])
+def test_uint8_frames_are_read_in_place_of_float32(size):
+    """DPFT_RAW_U8: the camera view handed over as the uint8 frames an image decoder produces (before the reference's
+    `.type(float32)`, dataset.py read_image).  The stem's row-streaming kernel and the FPN raw-level kernels convert on load;
+    0..255 is exact in fp32 / f16, so every result must be BIT-IDENTICAL to the float32 path on the same values."""
+    from dpft_b200 import features
+    from dpft_b200.features import NativeView
+    cfg, m = _model("kradar_camera_mono")
+    nv = NativeView(m.backbones["camera_mono"], m.necks["camera_mono"], m.embeddings["camera_mono"], True, DEV,
+                    torch.float16, torch.float16)
+    g = torch.Generator(device=DEV).manual_seed(size[1])
+    x8 = torch.randint(0, 256, size, generator=g, device=DEV, dtype=torch.uint8)
+    xf = x8.float()
+    assert nv.accepts_uint8(x8)
+    for dt in (torch.float16, torch.bfloat16):
+        a = features.stem_forward(x8, nv.stem_w, nv.stem_b, dt, w_packed=nv.stem_w_packed)
+        b = features.stem_forward(xf, nv.stem_w, nv.stem_b, dt, w_packed=nv.stem_w_packed)
+        assert torch.equal(a, b), dt
+    with torch.no_grad():
+        p8, shapes8 = nv.pyramid(x8)                     # stem, stages, lateral chain, every FPN output kernel incl. the raw level
+        pf, shapesf = nv.pyramid(xf)
+    torch.cuda.synchronize()
+    assert shapes8 == shapesf and torch.equal(p8, pf)
+    narrow = torch.randint(0, 256, (1, 40, 90, 3), generator=g, device=DEV, dtype=torch.uint8)     # below the streaming kernel's width
+    assert not nv.accepts_uint8(narrow)
+    with torch.no_grad():
+        assert torch.equal(nv.pyramid(narrow)[0], nv.pyramid(narrow.float())[0])                  # converted first (plumbing)

@@ -95,3 +95,36 @@ def test_feeder_on_the_gpu_matches_the_cpu_and_feeds_the_stream():
     for g, w in zip(got, want):
         for k in w:
             assert torch.allclose(g[k], w[k], rtol=1e-5, atol=1e-5), k
+
+
+def test_uint8_camera_frames_through_the_model_api():
+    """The full fusion model fed with uint8 camera frames (device tensors, pinned host tensors, and through infer_stream) gives
+    exactly the outputs of the same frames as float32 — the e2e leg of bench.py uploads a quarter of the camera bytes."""
+    from dpft_b200 import configs
+    cfg = synthetic.offline_config(configs.make_config("kradar"), n_queries=(20, 15, 1))
+    sizes = {"camera_mono": (96, 160, 3), "radar_bev": (64, 48, 6), "radar_front": (37, 48, 6)}
+    model = models.build("dprt", cfg).eval()
+    model.load_state_dict(synthetic.seeded_state_dict(model.state_dict(), seed=3))
+    model = model.to("cuda:0")
+    batches = [synthetic.synthetic_batch(cfg, 2, seed=70 + i, sizes=sizes) for i in range(4)]
+    for b in batches:
+        b["camera_mono"] = b["camera_mono"].round().clamp(0, 255)
+    as_u8 = [{k: (v.to(torch.uint8) if k == "camera_mono" else v) for k, v in b.items()} for b in batches]
+    with torch.no_grad():
+        want = [model({k: v.to("cuda:0") for k, v in b.items()}) for b in batches]
+        want = [{k: v.clone() for k, v in o.items()} for o in want]
+        got_dev = [model({k: v.to("cuda:0") for k, v in b.items()}) for b in as_u8]          # eager, then captured graphs
+        got_dev = [{k: v.clone() for k, v in o.items()} for o in got_dev]
+        got_host = [{k: v.clone() for k, v in model({k: v.pin_memory() for k, v in b.items()}).items()} for b in as_u8]
+    got_stream = list(model.infer_stream([{k: v.pin_memory() for k, v in b.items()} for b in as_u8], depth=2))
+    torch.cuda.synchronize()
+    for w, a, b, c in zip(want, got_dev, got_host, got_stream):
+        for k in w:
+            assert torch.equal(a[k], w[k]) and torch.equal(b[k], w[k]) and torch.equal(c[k], w[k]), k
+    # outside the native feature path the frames are converted first (plumbing): still the same model
+    model.native_features = False
+    with torch.no_grad():
+        f32 = model({k: v.to("cuda:0") for k, v in batches[0].items()})
+        u8 = model({k: v.to("cuda:0") for k, v in as_u8[0].items()})
+    for k in f32:
+        assert torch.equal(f32[k], u8[k]), k
