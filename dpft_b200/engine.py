@@ -67,7 +67,9 @@ class FusedEngine:
         self._side_streams = [torch.cuda.Stream(device=self.device) for _ in range(max(0, len(model.inputs) - 1))]
         self._side_streams_hp = [torch.cuda.Stream(device=self.device, priority=-1) for _ in range(max(0, len(model.inputs) - 1))]
         self._copy_stream = torch.cuda.Stream(device=self.device)
-        self.upload_slots = int(os.environ.get("DPFT_UPLOAD_SLOTS", "2"))     # spare pipeline slots for host batches (stream())
+        # spare pipeline slots for host batches (stream()): e2e 4.73 -> 4.61 ms per step with one, no further gain with two or
+        # three (profiles/r02_upload_slots_ab.txt; the differences are close to the run-to-run spread of a power-capped box)
+        self.upload_slots = int(os.environ.get("DPFT_UPLOAD_SLOTS", "1"))
 
     # -- construction ---------------------------------------------------------------------------------------------
     @staticmethod
@@ -301,7 +303,7 @@ class FusedEngine:
         for batch in batches:
             on_host = not batch[self.model.inputs[0]].is_cuda
             if slots is None:
-                # Host batches get two slots more than forwards in flight: a slot's captured input buffer is read until the very
+                # Host batches get `upload_slots` slots more than forwards in flight: a slot's captured input buffer is read until the very
                 # end of its forward (the FPN raw level), so with `depth` slots the upload of batch k+1 could only start when
                 # forward k+1-depth had finished and its 2 ms sat exposed in front of every replay.  With spare slots the
                 # upload lands in a buffer nobody reads while `depth` forwards run; the replay itself is still gated on the
