@@ -103,3 +103,43 @@ def test_two_view_radar_model_matches_reference_golden(path):
         assert model._engine is not None
     for k, want in rec["outputs"].items():
         assert rel_err(out[k].cpu(), want) < tol, (path, k, rel_err(out[k].cpu(), want))
+
+
+def test_reference_point_edge_cases_through_the_fused_decoder():
+    """The reference-point projection of the FUSED decoder kernel (decoder_layer_kernel: rigid transform, cart2spher, 3x4 / 4x4
+    projection with perspective division, normalisation by the stored shape, clipping) on the edge points of
+    tests/golden/refpoints_edge_cases.pt — r = 0, points on the axes, w = 0 and w < 0, far outside the field of view — with
+    that fixture's calibrations.  The host logic of the module-by-module path is held to the reference's values on exactly
+    these cases on the CPU (tests/test_golden_taps.py); here the fused kernel must agree with that path on the GPU, through all
+    four decoder iterations (the refined centres of later iterations start from these points)."""
+    rec = load_golden("refpoints_edge_cases")
+    cases = {c["name"]: c for c in rec["cases"]}
+    pts = torch.cat((cases["radar_bev"]["query"][0], cases["camera"]["query"][0]), dim=0)          # 24 query centres
+    cfg = synthetic.offline_config(configs.make_config("kradar"), n_queries=(24, 1, 1))
+    model = models.build("dprt", cfg).eval()
+    model.load_state_dict(synthetic.seeded_state_dict(model.state_dict(), seed=21))
+    model = model.to(DEV)
+    model.querent.grid = lambda dtype, device: pts.to(device=device, dtype=dtype)
+    sizes = {"camera_mono": (96, 160, 3), "radar_bev": (64, 48, 6), "radar_front": (37, 48, 6)}
+    batch = synthetic.synthetic_batch(cfg, 2, seed=22, sizes=sizes)
+    for view, name in (("camera_mono", "camera"), ("radar_bev", "radar_bev"), ("radar_front", "radar_front")):
+        c = cases[name]
+        batch[f"label_to_{view}_t"] = c["t"].clone()
+        batch[f"label_to_{view}_p"] = c["p"].clone()
+        batch[f"{view}_shape"] = torch.cat((c["shape"], torch.full((2, 1), sizes[view][2])), dim=1).to(torch.int64)
+    gb = {k: v.to(DEV) for k, v in batch.items()}
+    old = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32)
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    try:
+        with torch.no_grad():
+            model.use_fused, model.native_features = False, False
+            want = model(gb)                               # module by module: IMPFusion.get_reference_points in torch
+            model.use_fused = True
+            got = model(gb)                                # fused decoder on the same fp32 features
+            assert model._engine is not None
+    finally:
+        torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = old
+    for k in want:
+        assert torch.isfinite(got[k]).all(), k
+        assert rel_err(got[k].cpu(), want[k].cpu()) < 1e-3, (k, rel_err(got[k].cpu(), want[k].cpu()))
