@@ -103,3 +103,39 @@ def conv2d_nhwc(x: torch.Tensor, weight: torch.Tensor, bias: torch.Tensor, strid
         prof.append((2.0 * M * Cout * R * S * Cin,
                      2.0 * (x.numel() + weight.numel() + M * Cout * (2 if residual is not None else 1)), e0, e1))
     return out
+
+
+def conv2d_nhwc_pair(xs, weights, biases, stride: int, pad: int, relu: bool, residuals=(None, None)):
+    """Two convolutions of IDENTICAL shape (different inputs / weights / residuals) in ONE launch (``dpft_conv2d_nhwc_pair``):
+    -> (y0, y1).  Falls back to two launches for a layer the pair entry does not serve (halo / weight-stationary kernels)."""
+    x0, x1 = xs
+    w0, w1 = weights
+    if x0.shape != x1.shape or w0.shape != w1.shape or x0.dtype != x1.dtype or (residuals[0] is None) != (residuals[1] is None):
+        raise RuntimeError("conv2d_nhwc_pair: the two problems must have identical shapes and types")
+    native.require_cuda(x0, x1, w0, w1)
+    B, H, W, Cin = x0.shape
+    Cout, R, S, _ = w0.shape
+    P, Q = (H + 2 * pad - R) // stride + 1, (W + 2 * pad - S) // stride + 1
+    outs = [torch.empty((B, P, Q, Cout), dtype=x0.dtype, device=x0.device) for _ in range(2)]
+    lib = native.load_library()
+    prof = PROFILE
+    if prof is not None:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+    with torch.cuda.device(x0.device):
+        st = lib.dpft_conv2d_nhwc_pair(native.ptr(x0), native.ptr(w0), native.ptr(biases[0]), native.ptr(residuals[0]), native.ptr(outs[0]),
+                                       native.ptr(x1), native.ptr(w1), native.ptr(biases[1]), native.ptr(residuals[1]), native.ptr(outs[1]),
+                                       B, H, W, Cin, Cout, R, S, stride, pad, int(relu), native.dtype_code(x0), _MAX_CTAS,
+                                       native.stream_ptr(x0.device))
+    if st == -2:                                  # DPFT_ERR_UNSUPPORTED: not a layer of the generic kernel
+        y0 = conv2d_nhwc(x0, w0, biases[0], stride, pad, relu, residuals[0], outs[0])
+        y1 = conv2d_nhwc(x1, w1, biases[1], stride, pad, relu, residuals[1], outs[1])
+        return y0, y1
+    native.check(st, "dpft_conv2d_nhwc_pair")
+    native.count_launch()
+    if prof is not None:
+        e1.record()
+        M = B * P * Q
+        prof.append((2 * 2.0 * M * Cout * R * S * Cin,
+                     2 * 2.0 * (x0.numel() + w0.numel() + M * Cout * (2 if residuals[0] is not None else 1)), e0, e1))
+    return outs[0], outs[1]

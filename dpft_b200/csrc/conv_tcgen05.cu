@@ -159,11 +159,22 @@ __device__ __forceinline__ void tmem_dealloc_2sm(uint32_t base, uint32_t cols) {
 }
 
 // ---- the kernel -------------------------------------------------------------------------------------------------
+// One launch serves one problem, or TWO problems of identical shape (gridDim.y = 2: the two radar views of the fusion model
+// run the same ResNet-50 on equally sized inputs with different weights).  Their layers are latency-bound (~10 us for < 1 us of
+// math), so a second problem in the same launch costs the first one nothing and halves the launches and the SM-time of the pair.
+struct alignas(64) ConvLaunch {
+    CUtensorMap ta[2], tb[2], td[2], tr[2];
+    ConvParams prm[2];
+};
+
 template <int BLOCK_N, int STAGES, int EPI_RES_BUFS, int CG, int EG>
 __global__ void __launch_bounds__(threads_for(EG), 1)
-conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
-                 const __grid_constant__ CUtensorMap tmap_d, const __grid_constant__ CUtensorMap tmap_r,
-                 const ConvParams prm) {
+conv_gemm_kernel(const __grid_constant__ ConvLaunch launch_desc) {
+    const CUtensorMap& tmap_a = launch_desc.ta[blockIdx.y];
+    const CUtensorMap& tmap_b = launch_desc.tb[blockIdx.y];
+    const CUtensorMap& tmap_d = launch_desc.td[blockIdx.y];
+    const CUtensorMap& tmap_r = launch_desc.tr[blockIdx.y];
+    const ConvParams& prm = launch_desc.prm[blockIdx.y];
     using L = SmemLayout<BLOCK_N, STAGES, EPI_RES_BUFS, CG>;
     extern __shared__ __align__(1024) uint8_t smem[];                    // 128-byte swizzle needs 1024-byte alignment
     if ((smem_u32(smem) & 1023u) != 0) __trap();
@@ -759,12 +770,37 @@ bool use_pdl() {
     return v != 0;
 }
 
+// dpft_conv2d_nhwc_pair: the first problem is RECORDED (its tensor maps and parameters, and which kernel variant the
+// dispatch chose), the second one is launched together with it.  Both take the same dispatch decisions (identical shapes).
+enum PairMode : int { kPairOff = 0, kPairRecord = 1, kPairLaunch = 2 };
+thread_local int t_pair_mode = kPairOff;
+thread_local ConvLaunch t_pair_desc;
+thread_local const void* t_pair_kernel = nullptr;
+
 template <int BLOCK_N, int STAGES, int RES_BUFS, int CG = 1, int EG = 2>
 int launch(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& td, const CUtensorMap& tr, const ConvParams& prm,
            cudaStream_t stream) {
     using L = SmemLayout<BLOCK_N, STAGES, RES_BUFS, CG>;
     static_assert(L::kTotal <= 232448, "shared memory budget of one CTA exceeded");
     auto kern = conv_gemm_kernel<BLOCK_N, STAGES, RES_BUFS, CG, EG>;
+    if (t_pair_mode == kPairRecord) {
+        t_pair_desc.ta[0] = ta; t_pair_desc.tb[0] = tb; t_pair_desc.td[0] = td; t_pair_desc.tr[0] = tr; t_pair_desc.prm[0] = prm;
+        t_pair_kernel = (const void*)kern;
+        return DPFT_OK;
+    }
+    int groups = 1;
+    if (t_pair_mode == kPairLaunch) {
+        if (t_pair_kernel != (const void*)kern) { set_error("conv2d_pair: the two problems chose different kernels"); return DPFT_ERR_INVALID_ARGUMENT; }
+        groups = 2;
+    }
+    ConvLaunch desc;
+    if (groups == 2) {
+        desc = t_pair_desc;
+        desc.ta[1] = ta; desc.tb[1] = tb; desc.td[1] = td; desc.tr[1] = tr; desc.prm[1] = prm;
+    } else {
+        desc.ta[0] = ta; desc.tb[0] = tb; desc.td[0] = td; desc.tr[0] = tr; desc.prm[0] = prm;
+        desc.ta[1] = ta; desc.tb[1] = tb; desc.td[1] = td; desc.tr[1] = tr; desc.prm[1] = prm;
+    }
     static bool configured = false;
     if (!configured) {
         int st = cuda_status(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -773,10 +809,11 @@ int launch(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& td, 
         configured = true;
     }
     const int tiles = ((prm.m_tiles + CG - 1) / CG) * prm.n_tiles;
-    const int max_ctas = cta_budget() / CG > 0 ? cta_budget() / CG : 1;
+    const int budget = cta_budget() / groups;                    // the two problems of a pair share the SMs
+    const int max_ctas = budget / CG > 0 ? budget / CG : 1;
     const int grid = CG * (tiles < max_ctas ? tiles : max_ctas);
     cudaLaunchConfig_t cfg{};
-    cfg.gridDim = dim3(grid);
+    cfg.gridDim = dim3(grid, groups);
     cfg.blockDim = dim3(threads_for(EG));
     cfg.dynamicSmemBytes = L::kTotal;
     cfg.stream = stream;
@@ -796,7 +833,7 @@ int launch(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& td, 
     }
     cfg.attrs = attr;
     cfg.numAttrs = n_attr;
-    int st = cuda_status(cudaLaunchKernelEx(&cfg, kern, ta, tb, td, tr, prm), "cudaLaunchKernelEx(conv_gemm_kernel)");
+    int st = cuda_status(cudaLaunchKernelEx(&cfg, kern, desc), "cudaLaunchKernelEx(conv_gemm_kernel)");
     if (st) return st;
     DPFT_LAUNCH_CHECK("conv_gemm_kernel");
     return DPFT_OK;
@@ -805,6 +842,7 @@ int launch(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& td, 
 template <int BLOCK_N, int KB, int A_STAGES, int NB, int EG = 4>
 int launch_ws(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& td, const CUtensorMap& tr, const ConvParams& prm,
               cudaStream_t stream) {
+    if (t_pair_mode != kPairOff) { set_error("conv2d_pair: layer is served by the weight-stationary kernel"); return DPFT_ERR_UNSUPPORTED; }
     using L = WsLayout<BLOCK_N, KB, A_STAGES, NB>;
     static_assert(L::kTotal <= 232448, "shared memory budget of one CTA exceeded");
     auto kern = conv_expand_ws_kernel<BLOCK_N, KB, A_STAGES, NB, EG>;
@@ -875,6 +913,7 @@ extern "C" int dpft_fpn_lateral_forward(const void* x, const void* w, const floa
     DPFT_REQUIRE(B > 0 && H > 0 && W > 0 && Cin % 64 == 0, "fpn_lateral: bad size B=%d H=%d W=%d Cin=%d", B, H, W, Cin);
     DPFT_REQUIRE(coarse == nullptr || (Hc > 0 && Wc > 0), "fpn_lateral: bad coarse size");
     t_max_ctas = 0;
+    t_pair_mode = kPairOff;
     int st = resolve_driver();
     if (st) return st;
     ConvParams prm{};
@@ -911,6 +950,24 @@ extern "C" int dpft_conv2d_nhwc_ex(const void* x, const void* w, const float* bi
     return st;
 }
 
+extern "C" int dpft_conv2d_nhwc_pair(const void* x0, const void* w0, const float* bias0, const void* residual0, void* y0,
+                                     const void* x1, const void* w1, const float* bias1, const void* residual1, void* y1,
+                                     int B, int H, int W, int Cin, int Cout, int R, int S, int stride, int pad, int relu,
+                                     int dtype, int max_ctas, void* stream) {
+    DPFT_REQUIRE(max_ctas >= 0, "conv2d_pair: max_ctas=%d", max_ctas);
+    DPFT_REQUIRE((residual0 == nullptr) == (residual1 == nullptr), "conv2d_pair: both problems need a residual, or neither");
+    t_max_ctas = max_ctas;
+    t_pair_mode = kPairRecord;
+    int st = conv2d_nhwc_impl(x0, w0, bias0, residual0, y0, B, H, W, Cin, Cout, R, S, stride, pad, relu, 0, 0, dtype, stream);
+    if (st == DPFT_OK) {
+        t_pair_mode = kPairLaunch;
+        st = conv2d_nhwc_impl(x1, w1, bias1, residual1, y1, B, H, W, Cin, Cout, R, S, stride, pad, relu, 0, 0, dtype, stream);
+    }
+    t_pair_mode = kPairOff;
+    t_max_ctas = 0;
+    return st;
+}
+
 static int conv2d_nhwc_impl(const void* x, const void* w, const float* bias, const void* residual, void* y,
                             int B, int H, int W, int Cin, int Cout, int R, int S, int stride, int pad, int relu,
                             int block_n, int cluster_mode, int dtype, void* stream) {
@@ -927,8 +984,10 @@ static int conv2d_nhwc_impl(const void* x, const void* w, const float* bias, con
     const int P = (H + 2 * pad - R) / stride + 1, Q = (W + 2 * pad - S) / stride + 1;
     DPFT_REQUIRE(P > 0 && Q > 0, "conv2d: empty output");
     // 64 -> 64 channel 3x3 layers on wide maps: halo-tile kernel (input staged once instead of once per tap)
-    if (block_n == 0 && cluster_mode == 0 && conv3x3_halo_eligible(H, W, Cin, Cout, R, S, stride, pad, residual != nullptr))
+    if (block_n == 0 && cluster_mode == 0 && conv3x3_halo_eligible(H, W, Cin, Cout, R, S, stride, pad, residual != nullptr)) {
+        if (t_pair_mode != kPairOff) { set_error("conv2d_pair: layer is served by the halo kernel"); return DPFT_ERR_UNSUPPORTED; }
         return conv3x3_halo_launch(x, w, bias, y, B, H, W, relu, is_f16, (cudaStream_t)stream);
+    }
     ConvParams prm{};
     prm.M = B * P * Q; prm.N = Cout; prm.P = P; prm.Q = Q; prm.taps_s = S; prm.cblocks = Cin / 64;
     prm.kblocks = R * S * prm.cblocks; prm.stride = stride; prm.pad = pad; prm.relu = relu; prm.is_f16 = is_f16;

@@ -80,7 +80,8 @@ class FusedEngine:
     def _mode_of(model) -> tuple:
         """The model switches a captured graph bakes in: changing one of them must not replay a graph captured under another."""
         return (getattr(model, "native_features", True), getattr(model, "parallel_views", True),
-                getattr(model, "side_view_priority", False), getattr(model, "side_view_ctas", 0))
+                getattr(model, "side_view_priority", False), getattr(model, "side_view_ctas", 0),
+                getattr(model, "pair_side_views", True))
 
     @staticmethod
     def ineligible_reason(model) -> Optional[str]:
@@ -148,6 +149,17 @@ class FusedEngine:
         feats = model.extract_features(batch, only=torch_views) if torch_views else {}
         native_idx = [i for i, nv in enumerate(self.views) if nv is not None and use_native]
         results: Dict[int, FeaturePyramid] = {}
+        # Two side views with the same architecture on equally shaped inputs (the range-azimuth and elevation-azimuth radar
+        # projections of the shipped fusion config) share the launches of their Bottleneck convolutions
+        pair = self._paired_side_views(batch, native_idx) if getattr(model, "pair_side_views", True) else None
+        if pair is not None and not getattr(model, "parallel_views", True):
+            ia, ib = pair
+            xa, xb = batch[model.inputs[ia]].contiguous(), batch[model.inputs[ib]].contiguous()
+            fa, fb = NativeView.backbone_pair(self.views[ia], self.views[ib], xa, xb)
+            for i, x, f in ((ia, xa, fa), (ib, xb, fb)):
+                flat, shapes = self.views[i].pyramid(x, feats=f)
+                results[i] = FeaturePyramid(flat, shapes)
+            native_idx = [i for i in native_idx if i not in pair]
         if len(native_idx) > 1 and getattr(model, "parallel_views", True):
             # the views are independent until the decoder: fork one stream per extra view (the small radar backbones
             # fill the tails of the camera's kernels), join before decoding
@@ -155,7 +167,23 @@ class FusedEngine:
             fork = torch.cuda.Event()
             fork.record(main)
             joins = []
-            for k, i in enumerate(native_idx):
+            if pair is not None:
+                # both paired views on ONE forked stream: shared backbone launches, then each view's neck
+                ia, ib = pair
+                from . import conv as _conv
+                side = self._side_streams[-1]
+                side.wait_event(fork)
+                with torch.cuda.stream(side), _conv.cta_budget(getattr(model, "side_view_ctas", 0)):
+                    xa, xb = batch[model.inputs[ia]].contiguous(), batch[model.inputs[ib]].contiguous()
+                    fa, fb = NativeView.backbone_pair(self.views[ia], self.views[ib], xa, xb)
+                    for i, x, f in ((ia, xa, fa), (ib, xb, fb)):
+                        flat, shapes = self.views[i].pyramid(x, feats=f)
+                        flat.record_stream(main)
+                        results[i] = FeaturePyramid(flat, shapes)
+                    done = torch.cuda.Event()
+                    done.record(side)
+                joins.append(done)
+            for k, i in enumerate(i for i in native_idx if pair is None or i not in pair):
                 name = model.inputs[i]
                 if k == 0:
                     flat, shapes = self.views[i].pyramid(batch[name])
@@ -182,6 +210,17 @@ class FusedEngine:
         for i, name in enumerate(model.inputs):
             out.append(results[i] if i in results else FeaturePyramid.from_levels(feats[name]))
         return out
+
+    def _paired_side_views(self, batch, native_idx):
+        """(i, j): two native views other than the first one with the same architecture and equally shaped float32 inputs."""
+        side = native_idx[1:]
+        for a in range(len(side)):
+            for b in range(a + 1, len(side)):
+                i, j = side[a], side[b]
+                xi, xj = batch[self.model.inputs[i]], batch[self.model.inputs[j]]
+                if xi.shape == xj.shape and xi.dtype == xj.dtype == torch.float32 and self.views[i].same_architecture(self.views[j]):
+                    return i, j
+        return None
 
     # -- stage 2: decoder -----------------------------------------------------------------------------------------
     def decode(self, batch: Dict[str, torch.Tensor], pyramids: List[FeaturePyramid]) -> "OrderedDict[str, torch.Tensor]":

@@ -237,12 +237,51 @@ class NativeView:
         3-channel image at least 127 pixels wide (the camera); anything else is converted to float32 first (plumbing)."""
         return self.cin == 3 and (x.shape[2] - 1) // 2 + 1 >= 64 and self.stem_w_packed is not None
 
-    def pyramid(self, x: torch.Tensor) -> Tuple[torch.Tensor, List[Tuple[int, int]]]:
+    def same_architecture(self, other: "NativeView") -> bool:
+        """Every convolution of the two backbones has the same shape (different weights): they can share launches."""
+        if self.cin != other.cin or self.dtype != other.dtype or len(self.stages) != len(other.stages):
+            return False
+        for ba, bb in zip(self.stages, other.stages):
+            if len(ba) != len(bb):
+                return False
+            for ca, cb in zip(ba, bb):
+                for fa, fb in zip(ca, cb):
+                    if (fa is None) != (fb is None):
+                        return False
+                    if fa is not None and (fa.weight.shape != fb.weight.shape or fa.stride != fb.stride or fa.pad != fb.pad):
+                        return False
+        return True
+
+    @staticmethod
+    def backbone_pair(va: "NativeView", vb: "NativeView", xa: torch.Tensor, xb: torch.Tensor):
+        """``backbone`` of two views with the same architecture on equally shaped inputs: stem and max-pool per view, every
+        Bottleneck convolution of the two as ONE launch (``conv2d_nhwc_pair``).  Bit-identical to two ``backbone`` calls."""
+        from .conv import conv2d_nhwc_pair
+        ya = maxpool_forward(stem_forward(xa, va.stem_w, va.stem_b, va.dtype, w_packed=va.stem_w_packed))
+        yb = maxpool_forward(stem_forward(xb, vb.stem_w, vb.stem_b, vb.dtype, w_packed=vb.stem_w_packed))
+        fa, fb = [], []
+
+        def both(ca, cb, ia, ib, relu, ra=None, rb=None):
+            return conv2d_nhwc_pair((ia, ib), (ca.weight, cb.weight), (ca.bias, cb.bias), ca.stride, ca.pad, relu, (ra, rb))
+
+        for blocks_a, blocks_b in zip(va.stages, vb.stages):
+            for (a1, a2, a3, ad), (b1, b2, b3, bd) in zip(blocks_a, blocks_b):
+                ida, idb = both(ad, bd, ya, yb, False) if ad is not None else (ya, yb)
+                ta, tb = both(a1, b1, ya, yb, True)
+                ta, tb = both(a2, b2, ta, tb, True)
+                ya, yb = both(a3, b3, ta, tb, True, ida, idb)
+            fa.append(ya)
+            fb.append(yb)
+        return fa, fb
+
+    def pyramid(self, x: torch.Tensor, feats: Optional[List[torch.Tensor]] = None) -> Tuple[torch.Tensor, List[Tuple[int, int]]]:
+        """``feats``: the stage outputs when the backbone already ran (``backbone_pair``)."""
         x = x.contiguous()
         if x.dtype == torch.uint8 and not self.accepts_uint8(x):
             x = x.float()
         B = x.shape[0]
-        feats = self.backbone(x)
+        if feats is None:
+            feats = self.backbone(x)
         shapes = ([(x.shape[1], x.shape[2])] if self.skiplink else []) + [(f.shape[1], f.shape[2]) for f in feats]
         sizes = [h * w for h, w in shapes]
         starts = [sum(sizes[:i]) for i in range(len(sizes))]

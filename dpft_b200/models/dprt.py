@@ -68,8 +68,12 @@ class DPRT(nn.Module):
         # (~200 KB of shared memory); the radar layers are latency-bound, so 148 CTAs buy them nothing and starve the camera's
         # kernels of the neighbouring forwards: bench step 4.64 -> 4.49 ms at 48, one forward at a time unchanged (4.74 -> 4.72);
         # 16 is best pipelined (4.45) but makes the radar the critical path of a single forward (5.12)
-        # (profiles/r02_side_view_ctas_ab.txt)
-        self.side_view_ctas = int(os.environ.get("DPFT_SIDE_VIEW_CTAS", "48"))
+        # (profiles/r02_side_view_ctas_ab.txt); 64 since the two radar views share launches (below)
+        self.side_view_ctas = int(os.environ.get("DPFT_SIDE_VIEW_CTAS", "64"))
+        # two side views of the same architecture on equally shaped inputs share their Bottleneck launches (conv2d_nhwc_pair;
+        # the cap above then covers both): 52 launches fewer per forward, the serial conv time of a step 5.33 -> 4.70 ms, the
+        # pipelined step within the run-to-run spread (4.52 -> 4.47 ms), one forward at a time +0.5 % (profiles/r02_pair_side_views_ab.txt)
+        self.pair_side_views = os.environ.get("DPFT_PAIR_SIDE_VIEWS", "1") == "1"
         self.native_train = True       # train() on CUDA: ResNet stages through the sm_100a training kernels (16-bit
                                        # activations, dpft_b200/train_backbone.py); False = torch/cuDNN autograd in fp32
         self.train_dtype = torch.float16

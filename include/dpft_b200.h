@@ -101,6 +101,14 @@ DPFT_API int dpft_conv2d_nhwc(const void* x, const void* w, const float* bias, c
 DPFT_API int dpft_conv2d_nhwc_ex(const void* x, const void* w, const float* bias, const void* residual, void* y,
                                  int B, int H, int W, int Cin, int Cout, int R, int S, int stride, int pad, int relu,
                                  int block_n, int cluster_mode, int dtype, int max_ctas, void* stream);
+/* Two problems of IDENTICAL shape (different tensors and weights) in one launch: the two radar views of the fusion model run
+ * the same ResNet-50 on equally sized inputs.  Their layers are latency-bound, so the second problem rides along: half the
+ * launches and half the SM-time of the pair.  max_ctas caps the CTAs of both problems together (0 = one per SM).  Returns
+ * DPFT_ERR_UNSUPPORTED for a layer that is served by the halo or the weight-stationary kernel (call dpft_conv2d_nhwc_ex twice). */
+DPFT_API int dpft_conv2d_nhwc_pair(const void* x0, const void* w0, const float* bias0, const void* residual0, void* y0,
+                                   const void* x1, const void* w1, const float* bias1, const void* residual1, void* y1,
+                                   int B, int H, int W, int Cin, int Cout, int R, int S, int stride, int pad, int relu,
+                                   int dtype, int max_ctas, void* stream);
 
 /* OR-ed into `Cin` of dpft_stem_conv7x7_forward_ex and into `raw_channels` of dpft_fpn_output_forward: the raw input is
  * (B, H, W, C) uint8 — the frames an image decoder produces, before the reference's `.type(float32)`

@@ -179,3 +179,37 @@ def test_cta_budget_changes_only_the_grid(budget, case):
     after = conv.conv2d_nhwc(x, w, bias, stride, pad, True, res)          # the cap does not leak into later calls
     torch.cuda.synchronize()
     assert torch.equal(got, want) and torch.equal(after, want)
+
+
+PAIR_CASES = [(8, 64, 64, 64, 64, 1, 1, 0, False),        # radar stage-1 conv1 (generic kernel, 64-wide tiles)
+              (8, 64, 64, 64, 64, 3, 1, 1, False),        # 3x3 on a 64-wide map (below the halo kernel's width)
+              (8, 64, 64, 64, 256, 1, 1, 0, True),        # expand + residual, too few tiles for the weight-stationary kernel
+              (8, 32, 32, 256, 128, 1, 2, 0, False),      # strided 1x1
+              (8, 16, 16, 256, 256, 3, 1, 1, False),      # deep K: CTA pairs (cta_group::2) with two problems in the grid
+              (8, 8, 8, 1024, 512, 1, 1, 0, False),
+              (2, 16, 100, 64, 64, 3, 1, 1, False),       # halo-kernel layer: the pair entry declines, two launches instead
+              (8, 45, 80, 256, 1024, 1, 1, 0, True)]      # weight-stationary layer: declined as well
+
+
+@pytest.mark.parametrize("case", PAIR_CASES)
+@pytest.mark.parametrize("budget", [0, 48])
+def test_pair_launch_equals_two_launches(case, budget):
+    """dpft_conv2d_nhwc_pair: two problems of identical shape in one launch (gridDim.y = 2) must give, bit for bit, what two
+    launches give — generic kernel, CTA pairs, with and without the persistent-grid cap; layers of the halo / weight-stationary
+    kernels fall back to two launches."""
+    from dpft_b200 import conv
+    B, H, W, Cin, Cout, R, stride, pad, with_res = case
+    dev = "cuda:0"
+    g = torch.Generator(device=dev).manual_seed(Cin * 7 + Cout + R)
+    xs = [torch.randn(B, H, W, Cin, generator=g, device=dev).half() for _ in range(2)]
+    ws = [(torch.randn(Cout, R, R, Cin, generator=g, device=dev) / (R * R * Cin) ** 0.5).half() for _ in range(2)]
+    bs = [torch.randn(Cout, generator=g, device=dev) for _ in range(2)]
+    P, Q = (H + 2 * pad - R) // stride + 1, (W + 2 * pad - R) // stride + 1
+    rs = [torch.randn(B, P, Q, Cout, generator=g, device=dev).half() for _ in range(2)] if with_res else [None, None]
+    with conv.cta_budget(budget):
+        want = [conv.conv2d_nhwc(xs[i], ws[i], bs[i], stride, pad, True, rs[i]) for i in range(2)]
+        got = conv.conv2d_nhwc_pair(xs, ws, bs, stride, pad, True, rs)
+    torch.cuda.synchronize()
+    assert not torch.equal(want[0], want[1])
+    for i in range(2):
+        assert torch.equal(got[i], want[i]), i

@@ -130,3 +130,35 @@ def test_uint8_camera_frames_through_the_model_api():
         u8 = model({k: v.to("cuda:0") for k, v in as_u8[0].items()})
     for k in f32:
         assert torch.equal(f32[k], u8[k]), k
+
+
+def test_paired_side_views_give_identical_outputs():
+    """The two radar views of the fusion config (same ResNet-50, equally shaped inputs) share the launches of their Bottleneck
+    convolutions (conv2d_nhwc_pair): outputs must be bit-identical to the unpaired engine — eager, serial, graph and stream."""
+    from dpft_b200 import configs
+    cfg = synthetic.offline_config(configs.make_config("kradar"), n_queries=(20, 15, 1))
+    sizes = {"camera_mono": (96, 160, 3), "radar_bev": (64, 64, 6), "radar_front": (64, 64, 6)}
+    model = models.build("dprt", cfg).eval()
+    model.load_state_dict(synthetic.seeded_state_dict(model.state_dict(), seed=3))
+    model = model.to("cuda:0")
+    batches = [{k: v.to("cuda:0") for k, v in synthetic.synthetic_batch(cfg, 2, seed=80 + i, sizes=sizes).items()} for i in range(3)]
+    outs = {}
+    for paired in (False, True):
+        model.pair_side_views = paired
+        with torch.no_grad():
+            model.parallel_views = False
+            serial = {k: v.clone() for k, v in model(batches[0]).items()}
+            model.parallel_views = True
+            first = {k: v.clone() for k, v in model(batches[0]).items()}             # eager (first sighting after the switch)
+            replay = [{k: v.clone() for k, v in model(b).items()} for b in batches]   # captured graphs
+        streamed = [{k: v.clone() for k, v in o.items()} for o in model.infer_stream(batches, depth=2)]
+        outs[paired] = (serial, first, replay, streamed)
+    eng = model._engine
+    assert eng._paired_side_views(batches[0], [0, 1, 2]) == (1, 2)
+    for a, b in zip(outs[False], outs[True]):
+        for x, y in zip(a if isinstance(a, list) else [a], b if isinstance(b, list) else [b]):
+            for k in x:
+                assert torch.equal(x[k], y[k]), k
+    # unequal radar sizes: no pairing, same code path as before
+    other = {k: v.to("cuda:0") for k, v in synthetic.synthetic_batch(cfg, 2, seed=90, sizes={**sizes, "radar_front": (37, 64, 6)}).items()}
+    assert eng._paired_side_views(other, [0, 1, 2]) is None
