@@ -157,6 +157,8 @@ struct FpnOutParams {
     long long S, start;
     int H, W, Hc, Wc;
     int raw_u8;                // raw is (B, H, W, CIN) uint8 (what an image decoder produces): converted on load, values exact
+    float lat_c[16 * 6];       // the raw level's lateral weights by value (kernel parameter = constant bank): the column builder's
+                               // FMAs then take them as constant operands instead of 12 shared-memory loads per halo entry
 };
 
 // element idx of the raw input as fp32
@@ -499,7 +501,7 @@ __device__ __forceinline__ int nearest_src_scaled(int dst, float scale, int in_s
     return s < in_size - 1 ? s : in_size - 1;
 }
 
-template <int CIN, int ROWS>
+template <int CIN, int ROWS, bool LATC>
 __device__ __forceinline__ void fpn_build_column(const FpnOutParams& prm, uint8_t* s_a, const float* s_lat, const float* s_cb,
                                                  int b, int p0, int q0, int px, int rr0, float scale_h, float scale_w,
                                                  int hc0, int wc0) {
@@ -542,7 +544,7 @@ __device__ __forceinline__ void fpn_build_column(const FpnOutParams& prm, uint8_
             for (int o = 0; o < FC; ++o) {
                 float a = cb[o];
 #pragma unroll
-                for (int c = 0; c < CIN; ++c) a = fmaf(s_lat[o * CIN + c], xin[u][c], a);
+                for (int c = 0; c < CIN; ++c) a = fmaf(LATC ? prm.lat_c[o * CIN + c] : s_lat[o * CIN + c], xin[u][c], a);
                 v[o] = a;
             }
             uint32_t* pw = reinterpret_cast<uint32_t*>(pk);
@@ -554,9 +556,9 @@ __device__ __forceinline__ void fpn_build_column(const FpnOutParams& prm, uint8_
     }
 }
 
-template <int CIN>
+template <int CIN, bool LATC>
 __global__ void __launch_bounds__(TC_THREADS, 3)
-fpn_output_tc2_kernel(const FpnOutParams prm) {
+fpn_output_tc2_kernel(const __grid_constant__ FpnOutParams prm) {
     static_assert(CIN > 0, "the column builder is for the raw level");
     extern __shared__ __align__(128) uint8_t tsm[];
     uint8_t* s_a = tsm;
@@ -602,9 +604,9 @@ fpn_output_tc2_kernel(const FpnOutParams prm) {
     // inner halo tile, f16: thread (group g, column c) builds rows g*FB_ROWS .. of column c; the two right halo columns
     // (TC_TW, TC_TW + 1) are one more entry for the first 2 * (TC_TH + 2) threads.  Entries beyond TC_TW + 1 are never read
     // by the MMAs (tap ds reads entries ds .. ds + 127).
-    fpn_build_column<CIN, FB_ROWS>(prm, s_a, s_lat, s_cb, b, p0, q0, tid & (TC_TW - 1), (tid >> 7) * FB_ROWS, scale_h, scale_w, hc0, wc0);
+    fpn_build_column<CIN, FB_ROWS, LATC>(prm, s_a, s_lat, s_cb, b, p0, q0, tid & (TC_TW - 1), (tid >> 7) * FB_ROWS, scale_h, scale_w, hc0, wc0);
     if (tid < 2 * (TC_TH + 2))
-        fpn_build_column<CIN, 1>(prm, s_a, s_lat, s_cb, b, p0, q0, TC_TW + (tid & 1), tid >> 1, scale_h, scale_w, hc0, wc0);
+        fpn_build_column<CIN, 1, LATC>(prm, s_a, s_lat, s_cb, b, p0, q0, TC_TW + (tid & 1), tid >> 1, scale_h, scale_w, hc0, wc0);
     tc::fence_proxy_async();                 // generic-proxy smem writes -> visible to the tensor core (async proxy)
     tc::tcgen05_fence_before();
     __syncthreads();
@@ -1195,6 +1197,15 @@ extern "C" int dpft_fpn_output_forward(const float* inner, const float* raw, int
                                        const void* w_packed, const float* bias, const float* pos_y, const float* pos_x, void* pyramid,
                                        int pyramid_dtype, long long S, long long start, int B, int H, int W, int impl,
                                        void* stream) {
+    return dpft_fpn_output_forward_ex(inner, raw, raw_channels, lat_w, nullptr, lat_b, coarse, Hc, Wc, w, w_packed, bias, pos_y, pos_x,
+                                      pyramid, pyramid_dtype, S, start, B, H, W, impl, stream);
+}
+
+extern "C" int dpft_fpn_output_forward_ex(const float* inner, const float* raw, int raw_channels, const float* lat_w,
+                                          const float* lat_w_host, const float* lat_b, const float* coarse, int Hc, int Wc,
+                                          const float* w, const void* w_packed, const float* bias, const float* pos_y,
+                                          const float* pos_x, void* pyramid, int pyramid_dtype, long long S, long long start, int B,
+                                          int H, int W, int impl, void* stream) {
     DPFT_REQUIRE(pyramid_dtype == DPFT_F32 || pyramid_dtype == DPFT_F16, "fpn_output: pyramid dtype must be DPFT_F32 or DPFT_F16");
     DPFT_REQUIRE(w && bias && pos_y && pos_x && pyramid, "fpn_output: null pointer");
     DPFT_REQUIRE((inner != nullptr) != (raw != nullptr), "fpn_output: exactly one of inner / raw must be given");
@@ -1224,13 +1235,19 @@ extern "C" int dpft_fpn_output_forward(const float* inner, const float* raw, int
         const size_t smem = TC_A_BYTES + TC_B_BYTES + TC_TH * 8 + 16 + sizeof(float) * (FC * 6 + FC + TC_TH * FC + FB_CR * FB_CC * FC);
         static bool configured2 = false;
         if (!configured2) {
-            int st = cuda_status(cudaFuncSetAttribute(fpn_output_tc2_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "fpn tc2 attr");
-            if (!st) st = cuda_status(cudaFuncSetAttribute(fpn_output_tc2_kernel<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "fpn tc2 attr");
+            int st = cuda_status(cudaFuncSetAttribute(fpn_output_tc2_kernel<3, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "fpn tc2 attr");
+            if (!st) st = cuda_status(cudaFuncSetAttribute(fpn_output_tc2_kernel<6, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "fpn tc2 attr");
+            if (!st) st = cuda_status(cudaFuncSetAttribute(fpn_output_tc2_kernel<3, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "fpn tc2 attr");
+            if (!st) st = cuda_status(cudaFuncSetAttribute(fpn_output_tc2_kernel<6, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "fpn tc2 attr");
             if (st) return st;
             configured2 = true;
         }
-        if (raw_channels == 3) fpn_output_tc2_kernel<3><<<tgrid, TC_THREADS, smem, s>>>(prm);
-        else fpn_output_tc2_kernel<6><<<tgrid, TC_THREADS, smem, s>>>(prm);
+        if (lat_w_host) {                       // lateral weights as kernel parameters (constant operands of the builder's FMAs)
+            for (int i = 0; i < FC * raw_channels; ++i) prm.lat_c[i] = lat_w_host[i];
+            if (raw_channels == 3) fpn_output_tc2_kernel<3, true><<<tgrid, TC_THREADS, smem, s>>>(prm);
+            else fpn_output_tc2_kernel<6, true><<<tgrid, TC_THREADS, smem, s>>>(prm);
+        } else if (raw_channels == 3) fpn_output_tc2_kernel<3, false><<<tgrid, TC_THREADS, smem, s>>>(prm);
+        else fpn_output_tc2_kernel<6, false><<<tgrid, TC_THREADS, smem, s>>>(prm);
         DPFT_LAUNCH_CHECK("fpn_output_tc2_kernel");
         return DPFT_OK;
     }

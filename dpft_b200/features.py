@@ -87,7 +87,8 @@ def fpn_output_forward(pyramid: torch.Tensor, start: int, H: int, W: int, w: tor
                        pos_y: torch.Tensor, pos_x: torch.Tensor, inner: Optional[torch.Tensor] = None,
                        raw: Optional[torch.Tensor] = None, lat_w: Optional[torch.Tensor] = None,
                        lat_b: Optional[torch.Tensor] = None, coarse: Optional[torch.Tensor] = None, impl: int = 0,
-                       w_packed: Optional[torch.Tensor] = None) -> None:
+                       w_packed: Optional[torch.Tensor] = None, lat_w_host: Optional[torch.Tensor] = None) -> None:
+    """``lat_w_host``: contiguous float32 CPU copy of ``lat_w`` (raw level) — handed to the kernel as parameters."""
     B, S, _ = pyramid.shape
     if w_packed is None and impl in (2, 3):
         w_packed = fpn_pack_weights(w)
@@ -95,11 +96,13 @@ def fpn_output_forward(pyramid: torch.Tensor, start: int, H: int, W: int, w: tor
     raw_c = raw.shape[-1] if raw is not None else 0
     if raw is not None and raw.dtype == torch.uint8:
         raw_c |= RAW_U8
-    st = _lib().dpft_fpn_output_forward(native.ptr(inner), native.ptr(raw), raw_c, native.ptr(lat_w), native.ptr(lat_b),
-                                        native.ptr(coarse), hc, wc, native.ptr(w), native.ptr(w_packed), native.ptr(bias), native.ptr(pos_y),
-                                        native.ptr(pos_x), native.ptr(pyramid), native.dtype_code(pyramid), S, start, B, H, W,
-                                        impl, native.stream_ptr(pyramid.device))
-    native.check(st, "dpft_fpn_output_forward")
+    if lat_w_host is not None and (lat_w_host.is_cuda or lat_w_host.dtype != torch.float32 or not lat_w_host.is_contiguous()):
+        raise RuntimeError("fpn_output_forward: lat_w_host must be a contiguous float32 CPU tensor")
+    st = _lib().dpft_fpn_output_forward_ex(native.ptr(inner), native.ptr(raw), raw_c, native.ptr(lat_w), native.ptr(lat_w_host),
+                                           native.ptr(lat_b), native.ptr(coarse), hc, wc, native.ptr(w), native.ptr(w_packed),
+                                           native.ptr(bias), native.ptr(pos_y), native.ptr(pos_x), native.ptr(pyramid),
+                                           native.dtype_code(pyramid), S, start, B, H, W, impl, native.stream_ptr(pyramid.device))
+    native.check(st, "dpft_fpn_output_forward_ex")
     native.count_launch()
 
 
@@ -171,6 +174,9 @@ class NativeView:
             if skiplink and i == 0:
                 self.lat_w.append(lat.weight.detach().float()[:, :, 0, 0].contiguous().to(device))        # [16][Cin]
                 self.lat_b.append(lat.bias.detach().float().contiguous().to(device))
+                # host copy: travels as kernel parameters (DPFT_FPN_LAT_PARAMS=0 keeps the shared-memory path for A/B timing)
+                self.lat_w_host = (lat.weight.detach().float()[:, :, 0, 0].contiguous().cpu().clone()
+                                   if os.environ.get("DPFT_FPN_LAT_PARAMS", "1") == "1" else None)
             else:
                 cin = lat.weight.shape[1]
                 wpad = torch.zeros(64, cin, dtype=torch.float32)
@@ -227,7 +233,8 @@ class NativeView:
             H, W = shapes[0]
             py, px = self._tables(0, H, W)
             fpn_output_forward(pyr, 0, H, W, self.out_w[0], self.out_b[0], py, px, raw=x, lat_w=self.lat_w[0],
-                               lat_b=self.lat_b[0], coarse=inners[first], w_packed=self.out_w_packed[0])
+                               lat_b=self.lat_b[0], coarse=inners[first], w_packed=self.out_w_packed[0],
+                               lat_w_host=getattr(self, "lat_w_host", None))
         main.wait_event(done)
         del inners                      # alive until the join: their memory is not reused while the forked stream reads it
         return pyr, shapes
@@ -304,5 +311,6 @@ class NativeView:
             H, W = shapes[0]
             py, px = self._tables(0, H, W)
             fpn_output_forward(pyr, 0, H, W, self.out_w[0], self.out_b[0], py, px, raw=x, lat_w=self.lat_w[0],
-                               lat_b=self.lat_b[0], coarse=coarse, w_packed=self.out_w_packed[0])
+                               lat_b=self.lat_b[0], coarse=coarse, w_packed=self.out_w_packed[0],
+                               lat_w_host=getattr(self, "lat_w_host", None))
         return pyr, shapes

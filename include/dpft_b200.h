@@ -169,6 +169,13 @@ DPFT_API int dpft_fpn_output_forward(const float* inner, const float* raw, int r
                                      const void* w_packed, const float* bias, const float* pos_y, const float* pos_x, void* pyramid,
                                      int pyramid_dtype, long long S, long long start, int B, int H, int W, int impl,
                                      void* stream);
+/* Same; `lat_w_host` (optional) = a HOST copy of the raw level's lateral weights [16][raw_channels]: they then travel as kernel
+ * parameters and the tile builder's FMAs read them as constant operands (no shared-memory loads); results are identical. */
+DPFT_API int dpft_fpn_output_forward_ex(const float* inner, const float* raw, int raw_channels, const float* lat_w,
+                                        const float* lat_w_host, const float* lat_b, const float* coarse, int Hc, int Wc,
+                                        const float* w, const void* w_packed, const float* bias, const float* pos_y,
+                                        const float* pos_x, void* pyramid, int pyramid_dtype, long long S, long long start, int B,
+                                        int H, int W, int impl, void* stream);
 
 /* w [3][3][16][16] f32 -> the 4608-byte f16 operand image of the tcgen05 FPN output kernel (done once per model). */
 DPFT_API int dpft_fpn_pack_weights(const float* w, void* packed, void* stream);

@@ -171,6 +171,12 @@ def test_fpn_output_column_builder_matches_cuda_core(cin, H, W):
     assert float(c[:, :7].abs().max()) == 0.0                      # nothing written before `start`
     assert _rel(c, a) < 2e-3, _rel(c, a)
     assert _rel(c, b) < 1e-3, _rel(c, b)                           # same operand image up to the rounding of the FMA chain
+    # the lateral weights as kernel parameters (constant operands of the builder's FMAs) instead of shared-memory loads:
+    # the same FMA chain on the same values
+    d = torch.zeros(B, S, 16, device=DEV)
+    features.fpn_output_forward(d, 7, H, W, w, bias, py, px, impl=3, lat_w_host=kw["lat_w"].cpu().contiguous(), **kw)
+    torch.cuda.synchronize()
+    assert torch.equal(d, c)
 
 
 @pytest.mark.parametrize("size", [(2, 70, 131, 3), (1, 128, 228, 3), (3, 33, 300, 3)])
