@@ -1039,21 +1039,15 @@ static int conv2d_nhwc_impl(const void* x, const void* w, const float* bias, con
     if (pointwise && residual != nullptr && Cout % 256 == 0 && prm.kblocks <= 4 && (block_n == 0 || block_n == 256) &&
         (cluster_mode == 3 || (cluster_mode == 0 && use_ws() && prm.kblocks >= 2 &&
                                (long long)prm.m_tiles * (Cout / 256) >= 2LL * g_sm_count))) {
-        // tuning hook (tools/conv_bench.py): DPFT_WS_VARIANT picks another tile width / stage / ring split of the same kernel
+        // DPFT_WS_VARIANT=10 (tools/conv_bench.py) keeps the first, 256-wide split for A/B timing; the other splits that were
+        // measured (A stages 2..8, ring depth 2..6, two epilogue warps per quadrant) are in profiles/r02_conv_expand_ws_variants.txt
         static const int ws_variant = [] { const char* e = getenv("DPFT_WS_VARIANT"); return e ? atoi(e) : 0; }();
-        const int wbn = (ws_variant == 1 || ws_variant == 5 || ws_variant == 10 || prm.kblocks == 1) ? 256 : 128;
+        const int wbn = (ws_variant == 10 || prm.kblocks == 1) ? 256 : 128;
         prm.n_tiles = Cout / wbn;
         if (prm.n_tiles <= g_sm_count) {
             st = encode_2d(&tb, w, (uint64_t)Cin, (uint64_t)Cout, (uint64_t)Cin * 2, BLOCK_K, wbn, is_f16);
             if (st) return st;
             if (prm.kblocks == 1) return launch_ws<256, 1, 4, 8>(ta, tb, td, tr, prm, s);
-            if (ws_variant == 1) return launch_ws<256, 4, 3, 2>(ta, tb, td, tr, prm, s);
-            if (ws_variant == 2) return launch_ws<128, 4, 4, 6>(ta, tb, td, tr, prm, s);
-            if (ws_variant == 4) return launch_ws<128, 4, 4, 6, 2>(ta, tb, td, tr, prm, s);
-            if (ws_variant == 5) return launch_ws<256, 4, 2, 4, 2>(ta, tb, td, tr, prm, s);
-            if (ws_variant == 6) return launch_ws<128, 4, 5, 5>(ta, tb, td, tr, prm, s);
-            if (ws_variant == 7) return launch_ws<128, 4, 7, 3>(ta, tb, td, tr, prm, s);
-            if (ws_variant == 9 && prm.kblocks <= 2) return launch_ws<128, 2, 6, 6>(ta, tb, td, tr, prm, s);
             if (ws_variant == 10) return prm.kblocks <= 2 ? launch_ws<256, 2, 4, 6>(ta, tb, td, tr, prm, s)
                                                           : launch_ws<256, 4, 2, 4>(ta, tb, td, tr, prm, s);
             if (prm.kblocks <= 2) return launch_ws<128, 2, 8, 4>(ta, tb, td, tr, prm, s);
@@ -1062,8 +1056,6 @@ static int conv2d_nhwc_impl(const void* x, const void* w, const float* bias, con
         prm.n_tiles = Cout / bn;
     }
     DPFT_REQUIRE(cluster_mode != 3, "conv2d: cluster_mode 3 (weight-stationary) needs a 1x1 stride-1 layer with a residual, Cout %% 256 == 0, Cin <= 256");
-    // tuning hook (with tools/conv_bench.py): DPFT_CONV_STREAM_VARIANT picks another stage / residual-buffer / epilogue-warp split
-    static const int variant = [] { const char* e = getenv("DPFT_CONV_STREAM_VARIANT"); return e ? atoi(e) : 0; }();
     if (pairs) {
         cudaStream_t s2 = (cudaStream_t)stream;
         if (residual != nullptr && prm.kblocks <= 4) {   // forced pairs on an expand layer (cluster_mode 2): the stream-tuned split
@@ -1083,19 +1075,6 @@ static int conv2d_nhwc_impl(const void* x, const void* w, const float* bias, con
         return launch<128, 6, 3, 2>(ta, tb, td, tr, prm, s2);
     }
     const bool stream_bound = residual != nullptr && prm.kblocks <= 4;   // 1x1 expand convs: deep residual prefetch
-    if (stream_bound && variant == 1) {
-        if (bn == 256) return launch<256, 3, 2>(ta, tb, td, tr, prm, s);
-        if (bn == 128) return launch<128, 4, 3>(ta, tb, td, tr, prm, s);
-    }
-    if (stream_bound && variant == 2) {
-        if (bn == 256) return launch<256, 2, 3>(ta, tb, td, tr, prm, s);
-        if (bn == 128) return launch<128, 3, 5>(ta, tb, td, tr, prm, s);
-    }
-    if (stream_bound && variant == 3) {              // the two-warps-per-quadrant epilogue these layers used before
-        if (bn == 256) return launch<256, 2, 5>(ta, tb, td, tr, prm, s);
-        if (bn == 128) return launch<128, 2, 7>(ta, tb, td, tr, prm, s);
-        return launch<64, 3, 7>(ta, tb, td, tr, prm, s);
-    }
     // Stream-bound layers run FOUR epilogue warps per TMEM lane quadrant (16 columns of an item each, 18 warps per CTA): the
     // epilogue is a chain of dependent short operations (TMEM load, smem residual, pack, staging store), and four warps
     // per scheduler hide its latency better than two (s1_conv3 97 -> 89 us = 0.91 of the HBM peak, whole step -1.7 %).
