@@ -63,6 +63,9 @@ class GradientBucket:
         self.group = group
         self.average = average
         self.communicate = True          # False: skip the all-reduces (bench.py times the step with and without them)
+        # streams other than the current one that produce gradients (DPRT.training_streams(): the extra views' backward runs
+        # on their forward streams); an all-reduce of a chunk waits for them so that it never reads a gradient still being written
+        self._model = model
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         skip = set(unused_parameter_names(model))
         named = [(n, p) for n, p in model.named_parameters() if p.requires_grad and n not in skip]
@@ -121,6 +124,11 @@ class GradientBucket:
         if self.world == 1 or not self.communicate or self._handles[chunk] is not None:
             return
         a, b = self.chunk_bounds[chunk]
+        if hasattr(self._model, "training_streams"):
+            cur = torch.cuda.current_stream(self.flat.device) if self.flat.is_cuda else None
+            for s in self._model.training_streams():
+                if cur is not None and s != cur:
+                    cur.wait_stream(s)
         self._handles[chunk] = dist.all_reduce(self.flat[a:b], op=dist.ReduceOp.SUM, group=self.group, async_op=True)
 
     def finish(self) -> None:

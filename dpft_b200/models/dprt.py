@@ -77,6 +77,8 @@ class DPRT(nn.Module):
         self.native_train = True       # train() on CUDA: ResNet stages through the sm_100a training kernels (16-bit
                                        # activations, dpft_b200/train_backbone.py); False = torch/cuDNN autograd in fp32
         self.train_dtype = torch.float16
+        # train(): the extra views' backbones + necks on forked streams (their backward follows them there); False = one stream
+        self.train_parallel_views = os.environ.get("DPFT_TRAIN_PARALLEL_VIEWS", "1") == "1"
         self._engine = None
 
     @classmethod
@@ -97,20 +99,41 @@ class DPRT(nn.Module):
         return state
 
     # -- composed (module by module) path -------------------------------------------------------------------
+    def _view_features(self, name: str, batch: Dict[str, torch.Tensor]) -> "OrderedDict[str, torch.Tensor]":
+        bb = self.backbones[name]
+        if hasattr(bb, "native_train"):
+            bb.native_train, bb.train_dtype = self.native_train, self.train_dtype
+        f = bb(batch[name])
+        if self.skiplinks[name]:
+            f = OrderedDict([("0", batch[name])] + list(f.items()))
+        f = self.necks[name](f)
+        return self.embeddings[name](f)
+
     def extract_features(self, batch: Dict[str, torch.Tensor], only=None) -> Dict[str, "OrderedDict[str, torch.Tensor]"]:
-        feats = {}
-        for name in (self.inputs if only is None else only):
-            bb = self.backbones[name]
-            if hasattr(bb, "native_train"):
-                bb.native_train, bb.train_dtype = self.native_train, self.train_dtype
-            f = bb(batch[name])
-            if self.skiplinks[name]:
-                f = OrderedDict([("0", batch[name])] + list(f.items()))
-            f = self.necks[name](f)
-            feats[name] = self.embeddings[name](f)
-        return feats
+        names = list(self.inputs if only is None else only)
+        x0 = batch[names[0]] if names else None
+        if (self.training and self.train_parallel_views and len(names) > 1 and x0 is not None and x0.is_cuda
+                and torch.is_grad_enabled()):
+            return self._extract_features_forked(batch, names)
+        return {name: self._view_features(name, batch) for name in names}
+
+    def _extract_features_forked(self, batch, names) -> Dict[str, "OrderedDict[str, torch.Tensor]"]:
+        """Training: the views are independent until the fuser, and autograd runs every backward node on the stream its forward
+        ran on — so forward AND backward of the small radar backbones (2 x ~50 layers of latency-bound training kernels) overlap
+        the camera's instead of queueing behind them (dpft_b200/streams.py)."""
+        from ..streams import fork_map
+        feats = fork_map([(lambda n=name: self._view_features(n, batch)) for name in names], batch[names[0]].device)
+        return dict(zip(names, feats))
+
+    def training_streams(self):
+        """Side streams the forked parts of a training step run on (GradientBucket waits for them before an all-reduce)."""
+        from ..streams import registered
+        p = next(self.parameters(), None)
+        return registered(p.device) if p is not None and p.is_cuda else []
 
     def forward_composed(self, batch: Dict[str, torch.Tensor]) -> "OrderedDict[str, torch.Tensor]":
+        for mp in getattr(self.fuser, "mpfusion", {}).values():       # the per-view decoder layers follow the same switch
+            mp.train_parallel_views = self.train_parallel_views
         feats = self.extract_features(batch)
         out = self.querent(batch)
         return self.fuser(batch=[feats[i] for i in self.inputs],

@@ -251,8 +251,16 @@ class MPFusion(nn.Module):
         return self.reduction_layer(queries.reshape(B, N, self.d_model * self.m_views))
 
     def forward(self, query, batch, reference_points, query_positions):
-        outs = [layer(query, levels, ref, query_positions)
-                for layer, levels, ref in zip(self.ml_fusion_layers.values(), batch, reference_points)]
+        layers = list(zip(self.ml_fusion_layers.values(), batch, reference_points))
+        if (self.training and len(layers) > 1 and query.is_cuda and torch.is_grad_enabled()
+                and getattr(self, "train_parallel_views", True)):
+            # training: the views' layers are independent until the reduction — one stream per view, forward and (because
+            # autograd follows the forward's streams) backward; issue order = view order, so dropout masks are unchanged
+            from ..streams import fork_map
+            outs = fork_map([(lambda l=layer, v=levels, r=ref: l(query, v, r, query_positions)) for layer, levels, ref in layers],
+                            query.device)
+        else:
+            outs = [layer(query, levels, ref, query_positions) for layer, levels, ref in layers]
         return self.reduce(query, torch.stack(outs, dim=-1), query_positions)
 
 

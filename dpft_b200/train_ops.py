@@ -87,8 +87,10 @@ _workspaces = {}
 
 
 def bn_workspace(device) -> torch.Tensor:
-    """Partial-sum scratch shared by every BatchNorm call on a device (calls are stream-ordered)."""
-    key = torch.device(device)
+    """Partial-sum scratch of the BatchNorm calls of ONE stream (calls on a stream are ordered; the views of a training step
+    run on forked streams and must not share it)."""
+    dev = torch.device(device)
+    key = (dev, torch.cuda.current_stream(dev).cuda_stream)
     ws = _workspaces.get(key)
     if ws is None:
         ws = _workspaces[key] = torch.empty(BN_MAX_PARTS * 2 * 2048, dtype=torch.float32, device=device)

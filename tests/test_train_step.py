@@ -92,3 +92,47 @@ def test_graph_replay_matches_eager_gpu(native_train):
             assert int(b_e[n]) == int(b_g[n]) == 5, n     # five steps each: the warm-up passes leave no trace
     with pytest.raises(RuntimeError, match="shapes"):
         step({k: v[:1] for k, v in batches[0].items()})
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("native_train", [True, False])
+def test_forked_training_views_equal_the_single_stream_step(native_train):
+    """train(): the extra views' backbone + neck (forward and, because autograd runs a node's backward on its forward's stream,
+    backward) on forked streams must give the loss and the gradients of the single-stream step — same kernels, same order per
+    view; only fp32 atomics in the weight gradients / deformable-attention scatter may reorder (bound: 1e-4 of each tensor's
+    largest entry).  Dropout is left at the config's value: the masks depend on host program order, which does not change."""
+    dev = "cuda:0"
+    cfg = synthetic.offline_config(configs.make_config("kradar"), n_queries=(6, 5, 1))          # three views, dropout as shipped
+    sizes = {"camera_mono": (96, 160, 3), "radar_bev": (64, 64, 6), "radar_front": (64, 64, 6)}
+    torch.manual_seed(0)
+    base = models.build("dprt", cfg)
+    base.load_state_dict(synthetic.seeded_state_dict(base.state_dict(), seed=1))
+    batch = synthetic.synthetic_batch(cfg, 2, seed=11, sizes=sizes, device=dev)
+    old_tf32 = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32)
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    res = []
+    try:
+        for forked in (False, False, True, True):       # two runs each: the serial pair gives the noise floor of the atomics
+            m = copy.deepcopy(base).to(dev).train()
+            m.native_train, m.train_parallel_views = native_train, forked
+            torch.manual_seed(123)
+            torch.cuda.manual_seed(123)
+            loss = _loss(m(batch), batch)
+            loss.backward()
+            torch.cuda.synchronize()
+            res.append((float(loss.detach()), {n: p.grad.detach().clone() for n, p in m.named_parameters() if p.grad is not None}))
+            assert (len(m.training_streams()) > 0) == forked
+    finally:
+        torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = old_tf32
+
+    def worst(a, b):
+        return max(float((a[n] - b[n]).abs().max()) / (float(a[n].abs().max()) + 1e-12) for n in a)
+
+    (l0, g0), (l0b, g0b), (l1, g1), (l1b, g1b) = res
+    floor = worst(g0, g0b)
+    assert abs(l0 - l1) <= 1e-5 * abs(l0) and abs(l0 - l1b) <= 1e-5 * abs(l0), (l0, l1, l1b)
+    assert g0.keys() == g1.keys()
+    for g in (g1, g1b):
+        w = worst(g0, g)
+        assert w <= max(3.0 * floor, 1e-4), (w, floor)
