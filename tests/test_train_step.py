@@ -112,6 +112,15 @@ def test_forked_training_views_equal_the_single_stream_step(native_train):
     torch.backends.cudnn.allow_tf32 = False
     torch.backends.cuda.matmul.allow_tf32 = False
     res = []
+    from dpft_b200 import streams
+    calls = {"n": 0}
+    real_fork_map = streams.fork_map
+
+    def counting_fork_map(fns, device):
+        calls["n"] += 1
+        return real_fork_map(fns, device)
+
+    streams.fork_map = counting_fork_map
     try:
         for forked in (False, False, True, True):       # two runs each: the serial pair gives the noise floor of the atomics
             m = copy.deepcopy(base).to(dev).train()
@@ -122,8 +131,10 @@ def test_forked_training_views_equal_the_single_stream_step(native_train):
             loss.backward()
             torch.cuda.synchronize()
             res.append((float(loss.detach()), {n: p.grad.detach().clone() for n, p in m.named_parameters() if p.grad is not None}))
-            assert (len(m.training_streams()) > 0) == forked
+            # the feature extraction and each of the four decoder iterations fork when the switch is on, nothing forks when off
+            assert calls["n"] == (0 if not forked else 5 * (len(res) - 2)), (forked, calls["n"])
     finally:
+        streams.fork_map = real_fork_map
         torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = old_tf32
 
     def worst(a, b):
