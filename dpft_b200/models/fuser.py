@@ -257,10 +257,10 @@ class MPFusion(nn.Module):
             # training: the views' layers are independent until the reduction — one stream per view, forward and (because
             # autograd follows the forward's streams) backward; issue order = view order, so dropout masks are unchanged
             from ..streams import fork_map
-            outs = fork_map([(lambda l=layer, v=levels, r=ref: l(query, v, r, query_positions)) for layer, levels, ref in layers],
-                            query.device)
+            outs = fork_map([(lambda l=layer, v=levels, r=ref: l(query, v, r() if callable(r) else r, query_positions))
+                             for layer, levels, ref in layers], query.device)
         else:
-            outs = [layer(query, levels, ref, query_positions) for layer, levels, ref in layers]
+            outs = [layer(query, levels, ref() if callable(ref) else ref, query_positions) for layer, levels, ref in layers]
         return self.reduce(query, torch.stack(outs, dim=-1), query_positions)
 
 
@@ -325,7 +325,9 @@ class IMPFusion(nn.Module):
         query_pos = self.query_embedding.weight.unsqueeze(0).expand(B, -1, -1)
         pyramids = [FeaturePyramid.from_levels(levels) for levels in batch]
         for layer, head in zip(self.mpfusion.values(), self.heads):
-            refs = [self.get_reference_points(out["center"][..., :3], t, p, s) for (t, p), s in zip(projection, shape)]
+            center = out["center"][..., :3]
+            # handed over as thunks: MPFusion evaluates each view's projection inside that view's (possibly forked) branch
+            refs = [(lambda t=t, p=p, s=s: self.get_reference_points(center, t, p, s)) for (t, p), s in zip(projection, shape)]
             query = layer(query, pyramids, refs, query_pos)
             out = head(query, out)
         return out
