@@ -122,7 +122,8 @@ class DPRT(nn.Module):
         ran on — so forward AND backward of the small radar backbones (2 x ~50 layers of latency-bound training kernels) overlap
         the camera's instead of queueing behind them (dpft_b200/streams.py)."""
         from ..streams import fork_map
-        feats = fork_map([(lambda n=name: self._view_features(n, batch)) for name in names], batch[names[0]].device)
+        feats = fork_map([(lambda n=name: self._view_features(n, batch)) for name in names], batch[names[0]].device,
+                         reads=[batch[name] for name in names])
         return dict(zip(names, feats))
 
     def training_streams(self):

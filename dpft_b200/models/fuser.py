@@ -258,7 +258,9 @@ class MPFusion(nn.Module):
             # autograd follows the forward's streams) backward; issue order = view order, so dropout masks are unchanged
             from ..streams import fork_map
             outs = fork_map([(lambda l=layer, v=levels, r=ref: l(query, v, r() if callable(r) else r, query_positions))
-                             for layer, levels, ref in layers], query.device)
+                             for layer, levels, ref in layers], query.device,
+                            reads=[query, query_positions, [getattr(v, "flat", v) for _, v, _ in layers],
+                                   getattr(self, "_fork_reads", ())])
         else:
             outs = [layer(query, levels, ref() if callable(ref) else ref, query_positions) for layer, levels, ref in layers]
         return self.reduce(query, torch.stack(outs, dim=-1), query_positions)
@@ -328,7 +330,9 @@ class IMPFusion(nn.Module):
             center = out["center"][..., :3]
             # handed over as thunks: MPFusion evaluates each view's projection inside that view's (possibly forked) branch
             refs = [(lambda t=t, p=p, s=s: self.get_reference_points(center, t, p, s)) for (t, p), s in zip(projection, shape)]
+            layer._fork_reads = [center, [list(tp) for tp in projection], list(shape)]      # what the thunks read (streams.fork_map)
             query = layer(query, pyramids, refs, query_pos)
+            layer._fork_reads = ()
             out = head(query, out)
         return out
 

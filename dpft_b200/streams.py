@@ -15,6 +15,7 @@ import torch
 
 DEFAULT = os.environ.get("DPFT_TRAIN_PARALLEL_VIEWS", "1") == "1"
 _pool: Dict[torch.device, List[torch.cuda.Stream]] = {}
+_extra: Dict[torch.device, List[torch.cuda.Stream]] = {}
 
 
 def side_streams(device, n: int) -> List[torch.cuda.Stream]:
@@ -25,9 +26,17 @@ def side_streams(device, n: int) -> List[torch.cuda.Stream]:
     return pool[:n]
 
 
+def new_stream(device) -> torch.cuda.Stream:
+    """A registered stream of its own (not one of the fork_map slots): e.g. the weight-gradient stream of a backbone."""
+    dev = torch.device(device)
+    s = torch.cuda.Stream(device=dev)
+    _extra.setdefault(dev, []).append(s)
+    return s
+
+
 def registered(device) -> List[torch.cuda.Stream]:
     """Every side stream handed out on this device so far."""
-    return list(_pool.get(torch.device(device), []))
+    return list(_pool.get(torch.device(device), [])) + list(_extra.get(torch.device(device), []))
 
 
 def _record(obj, stream) -> None:
@@ -42,10 +51,17 @@ def _record(obj, stream) -> None:
             _record(v, stream)
 
 
-def fork_map(fns: Sequence[Callable[[], object]], device) -> List[object]:
+def fork_map(fns: Sequence[Callable[[], object]], device, reads=()) -> List[object]:
     """Results of ``fn()`` for every fn: the first on the current stream, the others on side streams forked from it and joined
     back before returning.  Host issue order is the list order (random-number offsets are assigned in that order, so dropout
-    masks do not depend on whether the work is forked)."""
+    masks do not depend on whether the work is forked).
+
+    ``reads``: every tensor (nested lists / dicts allowed) that was allocated OUTSIDE the branches and is read inside them.
+    The branches — and later their backward nodes, on the same side streams — read these after the host has moved on;
+    autograd frees a saved tensor the moment the last node that saved it has been ISSUED, and without ``record_stream`` the
+    caching allocator would hand its block straight back to the allocating stream while a side stream still reads it (seen:
+    the weight gradient of a forked view's first layer, which reads the input batch, wrong in 2 of 3 runs of a long-lived
+    process and never in a fresh one)."""
     dev = torch.device(device)
     main = torch.cuda.current_stream(dev)
     sides = side_streams(dev, len(fns) - 1)
@@ -59,6 +75,7 @@ def fork_map(fns: Sequence[Callable[[], object]], device) -> List[object]:
             continue
         side = sides[k - 1]
         side.wait_event(fork)
+        _record(reads, side)
         with torch.cuda.stream(side):
             results[k] = fn()
             done = torch.cuda.Event()

@@ -80,6 +80,15 @@ class NativeStages:
         self.zero_bias = torch.zeros(4096, dtype=torch.float32, device=self.device)
         self._packed_version = None
 
+    def _wgrad_stream(self):
+        import os
+        if os.environ.get("DPFT_WGRAD_STREAM", "1") != "1":
+            return None
+        if getattr(self, "_ws", None) is None:
+            from .streams import new_stream
+            self._ws = new_stream(self.device)
+        return self._ws
+
     # parameters in the order the autograd node receives them / returns their gradients
     def parameters(self) -> List[torch.Tensor]:
         out = []
@@ -143,9 +152,23 @@ class NativeStages:
             return T.bn_backward(dz, z, y, state, s.bn.weight, relu, bng[s.bn_off: s.bn_off + s.cout],
                                  bng[self.bn_channels + s.bn_off: self.bn_channels + s.bn_off + s.cout], want_g, sm)
 
+        # Weight gradients are leaves of the backward sweep (only the optimiser reads them): they go to a stream of their own and
+        # fill the tails of the data-gradient / BatchNorm chain, which is the dependency chain (DPFT_WGRAD_STREAM=0: same stream).
+        cur = torch.cuda.current_stream(dev)
+        ws = self._wgrad_stream() if dev.type == "cuda" else None
+
         def wgrad(s: _ConvSpec, x, dy):
             o = self.wgrad_offsets[s.idx]
-            T.conv2d_wgrad(x, dy, s.r, s.r, s.stride, s.pad, out=wg[o: o + s.conv.weight.numel()])
+            if ws is None:
+                T.conv2d_wgrad(x, dy, s.r, s.r, s.stride, s.pad, out=wg[o: o + s.conv.weight.numel()])
+                return
+            ready = torch.cuda.Event()
+            ready.record(cur)
+            ws.wait_event(ready)
+            with torch.cuda.stream(ws):
+                T.conv2d_wgrad(x, dy, s.r, s.r, s.stride, s.pad, out=wg[o: o + s.conv.weight.numel()])
+            x.record_stream(ws)
+            dy.record_stream(ws)
 
         def dgrad(s: _ConvSpec, dy, x, residual=None):
             return T.conv2d_dgrad(dy, self.packer.dgrad[s.idx], self.zero_bias, (x.shape[1], x.shape[2]), s.stride, s.pad, residual)
@@ -176,6 +199,8 @@ class NativeStages:
                 res = g
             dz = dgrad(c1, dy1, x, residual=res)
             tape[bi] = None                                  # release the block's activations as the sweep passes
+        if ws is not None:
+            cur.wait_stream(ws)                              # join: the gradients below are read on the sweep's stream
         grads = []
         for s in self.specs:
             o = self.wgrad_offsets[s.idx]

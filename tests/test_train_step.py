@@ -116,9 +116,9 @@ def test_forked_training_views_equal_the_single_stream_step(native_train):
     calls = {"n": 0}
     real_fork_map = streams.fork_map
 
-    def counting_fork_map(fns, device):
+    def counting_fork_map(fns, device, **kw):
         calls["n"] += 1
-        return real_fork_map(fns, device)
+        return real_fork_map(fns, device, **kw)
 
     streams.fork_map = counting_fork_map
     try:
