@@ -124,11 +124,20 @@ class GradientBucket:
         if self.world == 1 or not self.communicate or self._handles[chunk] is not None:
             return
         a, b = self.chunk_bounds[chunk]
-        if hasattr(self._model, "training_streams"):
-            cur = torch.cuda.current_stream(self.flat.device) if self.flat.is_cuda else None
+        if hasattr(self._model, "training_streams") and self.flat.is_cuda:
+            cur = torch.cuda.current_stream(self.flat.device)
+            capturing = torch.cuda.is_current_stream_capturing()
             for s in self._model.training_streams():
-                if cur is not None and s != cur:
-                    cur.wait_stream(s)
+                if s == cur:
+                    continue
+                if capturing:
+                    # a registered stream that has not been forked into this capture yet (a backbone's weight-gradient stream
+                    # before that backbone's backward starts) holds no work of this step: waiting on it would pull an
+                    # un-captured dependency into the graph and invalidate the capture
+                    with torch.cuda.stream(s):
+                        if not torch.cuda.is_current_stream_capturing():
+                            continue
+                cur.wait_stream(s)
         self._handles[chunk] = dist.all_reduce(self.flat[a:b], op=dist.ReduceOp.SUM, group=self.group, async_op=True)
 
     def finish(self) -> None:
