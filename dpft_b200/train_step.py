@@ -92,7 +92,9 @@ class GraphedTrainStep:
         self._graph = torch.cuda.CUDAGraph()
         from . import native
         l0 = native.launches()
-        with torch.cuda.graph(self._graph):
+        # thread_local: other threads (the NCCL watchdog polling its events) keep calling the CUDA API during a capture that
+        # now spans several streams; in the default global mode such a call invalidates the capture
+        with torch.cuda.graph(self._graph, capture_error_mode="thread_local"):
             self._loss = self._eager(self._static)
         self.native_launches_per_step = native.launches() - l0      # our own kernels inside one replay
         self._signature = self._sig(batch)
