@@ -53,7 +53,7 @@ def parse():
     ap.add_argument("--no-train", action="store_true", help="skip the `train` object (BASELINE config 4 step) of the default run")
     ap.add_argument("--no-library-baseline", action="store_true", help="skip `gpu_library_baseline` (reference model through torch+cuDNN)")
     ap.add_argument("--train-steps", type=int, default=20, help="timed steps of the `train` object")
-    ap.add_argument("--train-timeout", type=int, default=420, help="seconds after which the line is printed without `train`")
+    ap.add_argument("--train-timeout", type=int, default=180, help="seconds after which the line is printed without `train`")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--small", action="store_true", help="debug: tiny inputs (NOT a valid bench number)")
     ap.add_argument("--mode", default="infer", choices=["infer", "train"],
