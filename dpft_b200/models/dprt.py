@@ -112,8 +112,9 @@ class DPRT(nn.Module):
     def extract_features(self, batch: Dict[str, torch.Tensor], only=None) -> Dict[str, "OrderedDict[str, torch.Tensor]"]:
         names = list(self.inputs if only is None else only)
         x0 = batch[names[0]] if names else None
+        from ..streams import single_process
         if (self.training and self.train_parallel_views and len(names) > 1 and x0 is not None and x0.is_cuda
-                and torch.is_grad_enabled()):
+                and torch.is_grad_enabled() and single_process()):
             return self._extract_features_forked(batch, names)
         return {name: self._view_features(name, batch) for name in names}
 
@@ -133,8 +134,9 @@ class DPRT(nn.Module):
         return registered(p.device) if p is not None and p.is_cuda else []
 
     def forward_composed(self, batch: Dict[str, torch.Tensor]) -> "OrderedDict[str, torch.Tensor]":
+        from ..streams import single_process
         for mp in getattr(self.fuser, "mpfusion", {}).values():       # the per-view decoder layers follow the same switch
-            mp.train_parallel_views = self.train_parallel_views
+            mp.train_parallel_views = self.train_parallel_views and single_process()
         feats = self.extract_features(batch)
         out = self.querent(batch)
         return self.fuser(batch=[feats[i] for i in self.inputs],

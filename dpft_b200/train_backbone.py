@@ -84,11 +84,8 @@ class NativeStages:
         import os
         if os.environ.get("DPFT_WGRAD_STREAM", "1") != "1":
             return None
-        # Single process only.  Under data parallelism the step also holds the NCCL all-reduces of the gradient bucket; with the
-        # weight-gradient streams on top the captured step hung once in three two-GPU runs (never without them), so they stay off
-        # there until that is understood (the forked views, validated at N = 2, carry most of the gain).
-        import torch.distributed as dist
-        if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+        from .streams import single_process
+        if not single_process():                     # see streams.single_process
             return None
         if getattr(self, "_ws", None) is None:
             from .streams import new_stream
