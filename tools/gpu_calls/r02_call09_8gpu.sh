@@ -5,7 +5,7 @@ O=gpurun_out/r02c09; mkdir -p $O
 nvidia-smi -L | wc -l
 for N in 8; do
 T0=$(date +%s)
-timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port $((29520 + N)) bench.py --gpus $N --steps 20 --warmup 5 --train-timeout 150 > $O/bench_n$N.out 2> $O/bench_n$N.err
+timeout 200 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port $((29520 + N)) bench.py --gpus $N --steps 20 --warmup 5 --train-timeout 100 > $O/bench_n$N.out 2> $O/bench_n$N.err
 echo "bench N=$N rc=$? wall=$(( $(date +%s) - T0 )) s"
 tail -1 $O/bench_n$N.out > $O/bench_n$N.json; grep -v "OMP_NUM_THREADS\|\*\*\*\*" $O/bench_n$N.err | tail -5
 python - $N <<'PY'

@@ -3,7 +3,7 @@
 O=gpurun_out/r02c11; mkdir -p $O
 nvidia-smi -L | wc -l
 T0=$(date +%s)
-timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node 4 --master-addr 127.0.0.1 --master-port 29544 bench.py --gpus 4 --steps 20 --warmup 5 --train-timeout 150 > $O/bench_n4.out 2> $O/bench_n4.err
+timeout 240 python -m torch.distributed.run --nnodes=1 --nproc-per-node 4 --master-addr 127.0.0.1 --master-port 29544 bench.py --gpus 4 --steps 20 --warmup 5 --train-timeout 120 > $O/bench_n4.out 2> $O/bench_n4.err
 echo "bench N=4 rc=$? wall=$(( $(date +%s) - T0 )) s"
 tail -1 $O/bench_n4.out > $O/bench_n4.json; grep -v "OMP_NUM_THREADS\|\*\*\*\*" $O/bench_n4.err | tail -5
 python - <<'PY'
