@@ -11,8 +11,8 @@ the highest-ranked prediction of its class with IoU > threshold; the precision/r
 line through its first and last point (``utils/misc.py:43-84`` — not a piecewise interpolation); the smallest class id that
 occurs in a sample is treated as background and left out of the mean; a sample without any foreground class scores 1.
 
-Box overlaps come from ``dpft_b200.criterion`` (``box3d_overlap`` restates the absent ``pytorch3d`` op: parity unpinned for that
-one function, see there); everything else is pinned against the unmodified reference metric code (tests/test_metrics.py).
+Box overlaps come from ``dpft_b200.criterion`` (``box3d_overlap`` restates the absent ``pytorch3d`` op: not pinned to the package
+itself, equal to an exact independent polyhedron intersection, see there); everything else is pinned against the unmodified reference metric code (tests/test_metrics.py).
 """
 from __future__ import annotations
 
