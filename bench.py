@@ -10,16 +10,26 @@ BASELINE cfg-3 query grid: 300 queries) over one synthetic batch of B=8 frames p
 
   value   frames/s with the batches already resident in HBM, through DPRT.infer_stream with --depth forwards in flight
           (each on its own stream, captured graph and memory pool): ONE device-timed region around exactly K forwards
-          (CUDA events, max over ranks); the loop alternates two input batches (227 MB of inputs > 126 MB L2)
-  e2e     the same loop with HOST (pinned) input buffers: H2D of every batch and D2H of its four outputs inside the
-          timed region
+          (CUDA events, max over ranks); the loop alternates two input batches (227 MB of inputs > 126 MB L2) that live
+          in the engine's own input slots (model.stream_input_slots)
+  e2e     the same loop with HOST (pinned) input buffers — uint8 camera frames as the camera delivers them, float32 radar
+          cubes: H2D of every batch and D2H of its four outputs inside the timed region (`e2e_fp32_inputs`: the same with
+          the reference dataset's float32 camera tensors)
   sequential   one forward at a time (model(batch)), per-step events, L2 flushed by a 256 MiB write between steps: the
-          latency view, and the number earlier rounds reported as `value`
-  roofline     the dominant kernel (tcgen05 convolution, every launch of one step) + the deformable-attention forward kernel
-  cpu_baseline the CPU oracle port of the reference forward on the host cores (rank 0, N=1, bounded sample)
+          latency view, and the number round 1 reported as `value`
+  sustained    the `value` loop repeated until the timed region is at least 2 s (clocks and power sampled under load)
+  parity       the timed batch's outputs against the reference's CPU forward of the same frames
+  roofline     the dominant kernel (tcgen05 convolution, every launch of one step; `in_step` = the same launches inside
+          the pipelined step) + the deformable-attention op and the fused decoder's gather
+  cpu_baseline the unmodified reference package's CPU forward (baseline/_ref; the oracle port if it is absent) on the host
+          cores (rank 0, N=1, bounded sample)
+  gpu_library_baseline   the unmodified reference model on this GPU through torch + cuDNN, timed as its evaluator does
+  train        BASELINE config 4: forward + backward + chunked NCCL all-reduce of the gradient bucket + AdamW, one CUDA
+          graph per step, timed with and without the all-reduce (`allreduce_ms_exposed`)
 
---impl reference times the reference's CPU forward (the oracle port in oracle/dprt_oracle.py — the reference is
-pure Python and cannot travel to the GPU box) on the same workload, one bounded sample per step.
+--impl reference times the UNMODIFIED reference package (installed into the git-ignored baseline/_ref by
+__graft_entry__.build(); it travels to the GPU box) through its own `build('dprt', config)` / `forward` on the host cores, same
+workload and batch size, each step one forward, bounded to 240 s in all; rank 0 only under torchrun.
 """
 import argparse
 import json
