@@ -23,6 +23,8 @@ def single_process() -> bool:
     multi-process step stays on the single-stream schedule that is validated at N = 2 / 4 / 8."""
     import torch.distributed as dist
     return not (dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1)
+
+
 _pool: Dict[torch.device, List[torch.cuda.Stream]] = {}
 _extra: Dict[torch.device, List[torch.cuda.Stream]] = {}
 
