@@ -255,7 +255,7 @@ class HungarianAnassigner(nn.Module):
     linear_sum_assignment per sample.  Returns (index_i, index_j, mask), each (B, Mmax): matched prediction / target indices
     in the LSAP's order (ascending prediction index), padded slots masked out.
 
-    ``solver="device"`` (EXPERIMENTAL, CUDA tensors only): the assignment is solved by ``dpft_lsap_forward`` on the GPU
+    ``solver="device"`` (opt-in, CUDA tensors only; green on B200 against the scipy solves, tests/test_criterion_metrics_gpu.py): the assignment is solved by ``dpft_lsap_forward`` on the GPU
     instead — no host synchronisation at all in the criterion."""
 
     def __init__(self, loss_weights: Dict[str, float] = None, giou_weight: float = 1.0, solver: str = "host", **kwargs):

@@ -1216,7 +1216,7 @@ extern "C" int dpft_fpn_output_forward_ex(const float* inner, const float* raw, 
                      S, start, H, W, Hc, Wc, raw_u8};
     cudaStream_t s = (cudaStream_t)stream;
     DPFT_REQUIRE(impl >= 0 && impl <= 3, "fpn_output: impl must be 0 (auto), 1 (CUDA cores), 2 (tensor cores) or 3 (tensor cores, "
-                 "column-owning tile builder: experimental)");
+                 "column-owning tile builder)");
     if (!inner) {
         DPFT_REQUIRE(lat_w && lat_b, "fpn_output: lateral weights needed for the raw level");
         DPFT_REQUIRE(coarse == nullptr || (Hc > 0 && Wc > 0), "fpn_output: bad coarse size");

@@ -2,7 +2,7 @@
 // problem of the reference's HungarianAnassigner (src/dprt/training/assigner.py:134-141: `C.cpu()` + scipy's
 // linear_sum_assignment per sample) on the device, so the criterion needs no host synchronisation and the whole training
 // step stays capturable in one CUDA graph.  The algorithm is in lsap_core.h (shared with the host harness that checks it
-// against scipy).  EXPERIMENTAL: written without GPU access; dpft_b200.criterion uses it only on request.
+// against scipy; on B200: tests/test_criterion_metrics_gpu.py).  dpft_b200.criterion uses it on request (lsap_solver="device").
 #include "common.cuh"
 #include "lsap_core.h"
 

@@ -1,4 +1,4 @@
-"""Index maps of the experimental raw-level FPN tile builder (fpn_output_tc2_kernel), emulated on the CPU
+"""Index maps of the column-owning raw-level FPN tile builder (fpn_output_tc2_kernel), emulated on the CPU
 (tools/emulate_fpn_builder.py): every halo entry the MMAs read is written exactly once with the value the definition
 gives, and the staged coarse patch is large enough wherever the host-side eligibility test lets the kernel run."""
 import numpy as np
