@@ -41,7 +41,8 @@ def _worker(rank, world, port, result_path):
     dist.init_process_group("gloo", rank=rank, world_size=world)
     torch.set_num_threads(2)
     from helpers import oracle_op_injected
-    from dpft_b200 import ddp
+    from dpft_b200 import ddp, streams
+    assert not streams.single_process()            # data parallel: the training step keeps the single-stream schedule
     model, batch = _build()
     if rank == 1:                                   # rank 1 starts from different weights: broadcast must fix that
         with torch.no_grad():
@@ -84,7 +85,8 @@ def test_flat_bucket_allreduce_matches_full_batch(tmp_path):
 
 
 def test_bucket_layout_single_process():
-    from dpft_b200 import ddp
+    from dpft_b200 import ddp, streams
+    assert streams.single_process()                # no process group: forked training streams are allowed
     model, _ = _build()
     bucket = ddp.GradientBucket(model, n_chunks=4)
     assert bucket.n_chunks == 4 and bucket.chunk_bounds[0][0] == 0 and bucket.chunk_bounds[-1][1] == bucket.flat.numel()
